@@ -1,0 +1,146 @@
+"""ctypes binding of libgrl_b200.so (the C ABI declared in include/grl_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  Only raw device pointers, sizes and the current CUDA stream cross the ABI.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgrl_b200.so")
+
+GRL_OK = 0
+BASIS_GRAD_FLOATS = 64 * 16 + 64 + 64 * 64 + 64
+NODE_GRAD_FLOATS = 256 * 64 + 256 + 64 * 256 + 64 + 64 + 64 + 64 + 16 * 16 * 64
+EDGE_GRAD_FLOATS = 64 * 64
+
+_fp = C.c_void_p
+_i32 = C.c_int32
+
+
+class GrlEmbedDesc(C.Structure):
+    _fields_ = [("n_nodes", _i32), ("n_scalars", _i32), ("n_vectors", _i32), ("dim", _i32),
+                ("scalars", _fp), ("vectors", _fp), ("ori", _fp), ("weight", _fp), ("x", _fp),
+                ("grad_x", _fp), ("grad_weight_partials", _fp), ("n_partials", _i32)]
+
+
+class GrlBasisDesc(C.Structure):
+    _fields_ = [("n_edges", _i32), ("dim", _i32), ("edge_src", _fp), ("edge_dst", _fp), ("pos_src", _fp),
+                ("pos_dst", _fp), ("ori", _fp), ("w1t", _fp), ("b1", _fp), ("w2t", _fp), ("b2", _fp), ("basis", _fp),
+                ("w2", _fp), ("grad_basis", _fp), ("grad_partials", _fp), ("n_partials", _i32)]
+
+
+class GrlConvDesc(C.Structure):
+    _fields_ = [("n_src", _i32), ("n_dst", _i32), ("n_edges", _i32),
+                ("rowptr_dst", _fp), ("edge_src", _fp), ("edge_dst", _fp), ("rowptr_src", _fp), ("src_eid", _fp),
+                ("x_src", _fp), ("x_dst", _fp), ("basis", _fp), ("fiber_kernel", _fp), ("wk_t", _fp), ("wk", _fp),
+                ("bias", _fp), ("ln_g", _fp), ("ln_b", _fp), ("w1_t", _fp), ("w1", _fp), ("b1", _fp), ("w2_t", _fp),
+                ("w2_c", _fp), ("b2", _fp), ("x1", _fp), ("out", _fp), ("accumulate_out", _i32),
+                ("grad_out", _fp), ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp),
+                ("grad_basis", _fp), ("accumulate_grad_basis", _i32), ("node_grad_partials", _fp),
+                ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32)]
+
+
+class GrlProjDesc(C.Structure):
+    _fields_ = [("batch", _i32), ("k", _i32), ("proj_type", _i32), ("eps_mean", C.c_float), ("eps_cov", C.c_float),
+                ("mean", _fp), ("v", _fp), ("old_mean", _fp), ("old_v", _fp), ("proj_mean", _fp), ("proj_v", _fp),
+                ("eta", _fp), ("grad_proj_mean", _fp), ("grad_proj_v", _fp), ("grad_mean", _fp), ("grad_v", _fp)]
+
+
+# name -> (restype, argtypes); every symbol include/grl_b200.h declares
+SIGNATURES = {
+    "grl_abi_version": (C.c_int, []),
+    "grl_last_error": (C.c_char_p, []),
+    "grl_sm_count": (C.c_int, []),
+    "grl_knn_edge_ptr": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "grl_knn_graph": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _fp]),
+    "grl_radius_neighbors": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp]),
+    "grl_dense_edges": (C.c_int, [C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _fp]),
+    "grl_csr_build": (C.c_int, [_fp, C.c_int64, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
+    "grl_embed_fwd": (C.c_int, [C.POINTER(GrlEmbedDesc), _fp]),
+    "grl_embed_bwd": (C.c_int, [C.POINTER(GrlEmbedDesc), _fp]),
+    "grl_edge_basis_fwd": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
+    "grl_edge_basis_bwd": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
+    "grl_fbconv_edge_fwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_fbconv_node_fwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_fbconv_node_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_fbconv_edge_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
+    "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),
+    "grl_trpl_fwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),
+    "grl_trpl_bwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),
+}
+
+_lib = None
+launch_count = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it)
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(geometry_rl_b200 has no CPU or eager fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().grl_last_error().decode()
+
+
+def check(rc: int, what: str):
+    if rc != GRL_OK:
+        raise RuntimeError(f"{what} failed with code {rc}: {last_error()}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("geometry_rl_b200 kernels need CUDA tensors (no CPU path exists)")
+    if not t.is_contiguous():
+        raise RuntimeError("geometry_rl_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def ptr_any(t):
+    """Device pointer without the contiguity check (strided COO rows, fp64 workspaces)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("geometry_rl_b200 kernels need CUDA tensors (no CPU path exists)")
+    return t.data_ptr()
+
+
+def call(name: str, *args):
+    """Invoke an ABI function on the current torch stream and raise on a non-zero return code."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    launch_count += 1
+    check(rc, name)
+
+
+_sm = None
+
+
+def sm_count() -> int:
+    global _sm
+    if _sm is None:
+        _sm = load().grl_sm_count()
+    return _sm

@@ -1,0 +1,122 @@
+// Orientation lift + node encoder, forward and weight-gradient backward.
+//   x[n][o][c] = sum_s scal[n][s] W[c][s] + sum_v <vec[n][v][:dim], ori[o]> W[c][S+v]
+// Reference: geometry_rl/modules/pyg_models/ponita/utils/to_from_sphere.py:4-9 (scalar_to_sphere,
+// vec_to_sphere) + hepi.py:136-143 (node_encoder, bias-free Linear) / ponita/ponita.py:358 (x_embedder).
+#include "grl_common.cuh"
+
+namespace grl {
+
+constexpr int kMaxF = 16;
+
+__device__ __forceinline__ void embed_features(const GrlEmbedDesc& d, int n, int o, float (&feat)[kMaxF]) {
+  const int S = d.n_scalars, V = d.n_vectors;
+  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+#pragma unroll
+  for (int f = 0; f < kMaxF; ++f) {
+    float v = 0.f;
+    if (f < S) {
+      v = d.scalars[(size_t)n * S + f];
+    } else if (f < S + V) {
+      const float* p = d.vectors + ((size_t)n * V + (f - S)) * 3;
+      v = (p[0] * ox + p[1] * oy) + ((d.dim == 3) ? p[2] * oz : 0.f);
+    }
+    feat[f] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) embed_fwd_kernel(const GrlEmbedDesc d) {
+  __shared__ __align__(16) float Wt[kMaxF * kC];  // Wt[f][c] = W[c][f]
+  const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
+  const int F = d.n_scalars + d.n_vectors;
+  for (int i = tid; i < kMaxF * kC; i += kThreads) {
+    const int f = i / kC, c = i % kC;
+    Wt[i] = (f < F) ? d.weight[c * F + f] : 0.f;
+  }
+  __syncthreads();
+  for (int n = blockIdx.x; n < d.n_nodes; n += gridDim.x) {
+    float feat[kMaxF];
+    embed_features(d, n, o, feat);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < kMaxF; ++f) {
+      const float4 w = ld4(Wt + f * kC + 4 * cg);
+      a.x = fmaf(feat[f], w.x, a.x);
+      a.y = fmaf(feat[f], w.y, a.y);
+      a.z = fmaf(feat[f], w.z, a.z);
+      a.w = fmaf(feat[f], w.w, a.w);
+    }
+    st4(d.x + (size_t)n * kRow + o * kC + 4 * cg, a);
+  }
+}
+
+// gW[c][f] = sum_{n,o} grad_x[n][o][c] feat[n][o][f]; per-CTA partial, cross-o reduction through smem.
+__global__ void __launch_bounds__(kThreads) embed_bwd_kernel(const GrlEmbedDesc d) {
+  __shared__ __align__(16) float red[kO * kC];
+  const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
+  const int F = d.n_scalars + d.n_vectors;
+  float g[kMaxF][4];
+#pragma unroll
+  for (int f = 0; f < kMaxF; ++f) g[f][0] = g[f][1] = g[f][2] = g[f][3] = 0.f;
+  for (int n = blockIdx.x; n < d.n_nodes; n += gridDim.x) {
+    float feat[kMaxF];
+    embed_features(d, n, o, feat);
+    const float4 gx = ldg4(d.grad_x + (size_t)n * kRow + o * kC + 4 * cg);
+#pragma unroll
+    for (int f = 0; f < kMaxF; ++f) {
+      g[f][0] = fmaf(gx.x, feat[f], g[f][0]);
+      g[f][1] = fmaf(gx.y, feat[f], g[f][1]);
+      g[f][2] = fmaf(gx.z, feat[f], g[f][2]);
+      g[f][3] = fmaf(gx.w, feat[f], g[f][3]);
+    }
+  }
+  float* P = d.grad_weight_partials + (size_t)blockIdx.x * kC * F;
+#pragma unroll
+  for (int f = 0; f < kMaxF; ++f) {
+    if (f < F) {
+      __syncthreads();
+      st4(red + o * kC + 4 * cg, make_float4(g[f][0], g[f][1], g[f][2], g[f][3]));
+      __syncthreads();
+      if (tid < kC) {
+        float t = 0.f;
+#pragma unroll
+        for (int oo = 0; oo < kO; ++oo) t += red[oo * kC + tid];
+        P[tid * F + f] = t;
+      }
+    }
+  }
+}
+
+}  // namespace grl
+
+extern "C" {
+
+static int check_embed(const GrlEmbedDesc* d, const char* who) {
+  GRL_REQUIRE(d, GRL_EINVAL, "%s: null descriptor", who);
+  GRL_REQUIRE(d->n_nodes > 0 && (d->dim == 2 || d->dim == 3), GRL_EINVAL, "%s: n_nodes=%d dim=%d", who, d->n_nodes, d->dim);
+  GRL_REQUIRE(d->n_scalars >= 0 && d->n_vectors >= 0 && d->n_scalars + d->n_vectors >= 1 &&
+                  d->n_scalars + d->n_vectors <= grl::kMaxF, GRL_EUNSUPPORTED, "%s: S+V=%d not in [1,16]", who,
+              d->n_scalars + d->n_vectors);
+  GRL_REQUIRE((d->n_scalars == 0 || d->scalars) && (d->n_vectors == 0 || d->vectors) && d->ori, GRL_EINVAL,
+              "%s: null pointer", who);
+  return GRL_OK;
+}
+
+int grl_embed_fwd(const GrlEmbedDesc* d, grl_stream_t stream) {
+  const int rc = check_embed(d, "grl_embed_fwd");
+  if (rc != GRL_OK) return rc;
+  GRL_REQUIRE(d->weight && d->x, GRL_EINVAL, "grl_embed_fwd: null pointer");
+  int grid = 8 * grl::sm_count();
+  if (grid > d->n_nodes) grid = d->n_nodes;
+  grl::embed_fwd_kernel<<<grid, grl::kThreads, 0, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_embed_fwd");
+}
+
+int grl_embed_bwd(const GrlEmbedDesc* d, grl_stream_t stream) {
+  const int rc = check_embed(d, "grl_embed_bwd");
+  if (rc != GRL_OK) return rc;
+  GRL_REQUIRE(d->grad_x && d->grad_weight_partials && d->n_partials > 0, GRL_EINVAL, "grl_embed_bwd: null pointer");
+  grl::embed_bwd_kernel<<<d->n_partials, grl::kThreads, 0, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_embed_bwd");
+}
+
+}  // extern "C"

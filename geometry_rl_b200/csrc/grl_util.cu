@@ -1,0 +1,69 @@
+// Error plumbing, device query and the deterministic cross-CTA partial reduction.
+#include <cstdarg>
+#include <cstdio>
+
+#include "grl_common.cuh"
+
+namespace grl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return GRL_ECUDA;
+  }
+  return GRL_OK;
+}
+
+int sm_count() {
+  // immutable per-device capability cache (the only global state behind the ABI)
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// out[i] (+)= sum_p partials[p][i] in fixed p order.
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int64_t n, float* __restrict__ out,
+                                       int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < n_partials; ++p) s += partials[(int64_t)p * n + i];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+}  // namespace grl
+
+extern "C" {
+
+int grl_abi_version(void) { return 1; }
+const char* grl_last_error(void) { return grl::g_err; }
+int grl_sm_count(void) { return grl::sm_count(); }
+
+int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,
+                        grl_stream_t stream) {
+  GRL_REQUIRE(partials && out && n_partials > 0 && n_floats > 0, GRL_EINVAL, "grl_reduce_partials: bad arguments");
+  const int threads = 256;
+  int64_t blocks = (n_floats + threads - 1) / threads;
+  if (blocks > 4 * grl::sm_count()) blocks = 4 * grl::sm_count();
+  grl::reduce_partials_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(partials, n_partials, n_floats, out,
+                                                                                  accumulate);
+  return grl::check_launch("grl_reduce_partials");
+}
+
+}  // extern "C"

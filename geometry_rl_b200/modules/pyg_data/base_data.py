@@ -1,0 +1,171 @@
+"""Observation tensors -> batched graph + per-node features, on the GPU.
+
+Mirrors the interface of the reference's `BaseData` (geometry_rl/modules/pyg_data/base_data.py:9-75):
+`build_data(*obs_tensors, train=) -> (graph, input_vector)` with a topology cache keyed on the batch
+size (`_should_reconstruct_placeholders`, rigid_tasks_data.py:254-255).  Differences in mechanism,
+not in results:
+  * topology is built by the batched K1 CUDA kernels instead of a Python loop of per-graph
+    knn_graph calls; the coalesced COO it yields is bit-identical to the reference's edge_index;
+  * `HeteroCartesian` / `HeteroDistance` edge attributes (recomputed every call by the reference,
+    rigid_tasks_data.py:250, but read by none of HEPi / EMPN / DeepSets / transformer) are not produced.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ... import ops
+from .graph import GraphBatch
+
+
+def noise_like(tensor: torch.Tensor, std: float = 0.1) -> torch.Tensor:
+    """pyg_data/utils.py:13-15."""
+    return torch.randn_like(tensor) * std
+
+
+class BaseData:
+    # subclasses fill these in
+    TASK: str = ""
+    ALL_NODE_TYPES: Sequence[str] = ()
+    PARTICLE_TYPE: str = ""
+    ACTUATOR_TYPE: str = "grippers"
+    INTERNAL_MODE: str = "knn"
+    EDGE_TYPES: Sequence[Tuple[str, str, str]] = ()
+    HAS_INFOS: bool = False
+
+    def __init__(self, observation_dim: Dict, observation_names: Dict, full_graph_obs: bool = False,
+                 dist_as_pos: bool = False, output_mask_key: Optional[str] = None, training_noise: bool = False,
+                 training_noise_std: float = 1e-2, concat_input_vector: bool = True, angular_velocity: bool = True,
+                 knn_k: int = 3, knn_to_actuators_k: int = -1, **kwargs):
+        self._output_mask_key = output_mask_key
+        self.training_noise = training_noise
+        self.training_noise_std = training_noise_std
+        self.concat_input_vector = concat_input_vector
+        self.observation_dim = {k: [v[0] if isinstance(v, (tuple, list)) else int(v) for v in vs]
+                                for k, vs in observation_dim.items()}
+        self.observation_names = observation_names
+        self.full_graph_obs = full_graph_obs
+        self.dist_as_pos = dist_as_pos
+        self.angular_velocity = angular_velocity
+        self.knn_k = knn_k
+        self.knn_to_actuators_k = knn_to_actuators_k
+        if knn_to_actuators_k > 0:
+            # the reference's own kNN-to-actuator branch never assigns TASK edges for rigid tasks
+            # (rigid_tasks_data.py:302-312) and no shipped config selects it
+            raise NotImplementedError("knn_to_actuators_k > 0 is not reachable with the shipped configs")
+        self.node_type_list = self._kept_node_types()
+        self._example_data: Optional[GraphBatch] = None
+
+    # ---- configuration hooks ---------------------------------------------------------------------
+    def _kept_node_types(self) -> List[str]:
+        raise NotImplementedError
+
+    @property
+    def example_data(self):
+        return self._example_data
+
+    def output_mask(self, data: GraphBatch, key: Optional[str]) -> slice:
+        if key is not None:
+            start = data.node_offsets[key]
+            return slice(start, start + data.nodes_per_graph[key])
+        return slice(None)
+
+    # ---- public entry point (base_data.py:45-55) ----------------------------------------------------
+    def build_data(self, *args, **kwargs):
+        inputs = self._preprocess_input(*args, **kwargs)
+        if self._should_reconstruct_placeholders(**inputs):
+            self._construct_placeholders(**inputs)
+        with torch.no_grad():
+            data = self._update_placeholders(**inputs)
+            input_vector = self.construct_input_vector(data, **inputs)
+        return data, input_vector
+
+    def _should_reconstruct_placeholders(self, batch_size, **ignored) -> bool:
+        return self._example_data is None or len(self._example_data) != batch_size
+
+    # ---- obs splitting (rigid_tasks_data.py:93-150) ---------------------------------------------------
+    def _preprocess_input(self, scalars, position_vectors, velocity_vectors, norm_position_vectors,
+                          norm_velocity_vectors, infos=None, train: bool = True, **ignored) -> Dict:
+        B = scalars.shape[0]
+        out = {"batch_size": B, "device": scalars.device, "train": train}
+
+        def split(t, group, as_vec):
+            parts = torch.split(t, self.observation_dim[group], dim=1)
+            names = self.observation_names[group]
+            return {str.__str__(n): (p.reshape(B, -1, 3) if as_vec else p) for n, p in zip(names, parts)}
+
+        out["scalars"] = split(scalars, "scalars", False)
+        out["position_vectors"] = split(position_vectors, "position_vectors", True)
+        out["velocity_vectors"] = split(velocity_vectors, "velocity_vectors", True)
+        out["norm_position_vectors"] = split(norm_position_vectors, "position_vectors", True)
+        out["norm_velocity_vectors"] = split(norm_velocity_vectors, "velocity_vectors", True)
+        out["infos"] = split(infos, "infos", False) if (infos is not None and self.HAS_INFOS) else {}
+        return out
+
+    # ---- topology (K1 kernels) ----------------------------------------------------------------------
+    def _num_valid(self, infos, batch_size, device) -> Optional[torch.Tensor]:
+        return None
+
+    def _construct_placeholders(self, position_vectors, infos, batch_size, device, **ignored):
+        if device.type != "cuda":
+            raise RuntimeError("geometry_rl_b200 builds graph topology with CUDA kernels; observations must be on "
+                               "a CUDA device (there is no CPU fallback)")
+        B = batch_size
+        npg = {t: position_vectors[t].shape[1] for t in self.ALL_NODE_TYPES}
+        kept = self.node_type_list
+        g = GraphBatch(B, {t: npg[t] for t in kept}, device)
+        num_valid = self._num_valid(infos, B, device)
+        e_int, e_agent, e_task = self.EDGE_TYPES
+        P, A = npg[self.PARTICLE_TYPE], npg[self.ACTUATOR_TYPE]
+        pts = position_vectors[self.PARTICLE_TYPE]
+        for et in self.EDGE_TYPES:  # insertion order INTERNAL, AGENT, TASK (rigid_tasks_data.py:285-319)
+            src, _, dst = et
+            if src not in kept or dst not in kept:
+                continue
+            if et == e_int:
+                if self.INTERNAL_MODE == "knn":
+                    coo, ptr = ops.knn_graph(pts, num_valid, self.knn_k)
+                else:
+                    coo, ptr = ops.dense_edges(0, B, P, P, device)
+            elif et == e_agent:
+                if A > 1:
+                    coo, ptr = ops.dense_edges(0, B, A, A, device)
+                else:
+                    coo = torch.empty(2, 0, dtype=torch.int64, device=device)
+                    ptr = torch.zeros(B + 1, dtype=torch.int64, device=device)
+            else:
+                coo, ptr = ops.dense_edges(1, B, P, A, device, num_valid=num_valid)
+            g.add_edge_type(et, coo, ptr)
+        for t in kept:  # HeteroNodeCategorical: one-hot over the PRE-subgraph type list (transforms.py:43-76)
+            oh = torch.zeros(B * npg[t], len(self.ALL_NODE_TYPES), device=device)
+            oh[:, list(self.ALL_NODE_TYPES).index(t)] = 1
+            g[t].properties = oh
+        g.output_mask_key = self._output_mask_key
+        g.output_mask = self.output_mask(g, self._output_mask_key)
+        self._example_data = g
+
+    def _update_placeholders(self, position_vectors, norm_position_vectors, device, **ignored) -> GraphBatch:
+        data = self._example_data.shallow_copy()
+        for t in self.node_type_list:
+            data[t].pos = position_vectors[t].reshape(-1, 3)
+            data[t].norm_pos = norm_position_vectors[t].reshape(-1, 3)
+        return data
+
+    # ---- per-node features ---------------------------------------------------------------------------
+    def _vectors(self, data, node_type, norm_position_vectors, norm_velocity_vectors, train) -> torch.Tensor:
+        raise NotImplementedError
+
+    def construct_input_vector(self, data: GraphBatch, norm_position_vectors, norm_velocity_vectors, train=True,
+                               **ignored):
+        scalar_dict, vector_dict, full = {}, {}, {}
+        for t in self.node_type_list:
+            vectors = self._vectors(data, t, norm_position_vectors, norm_velocity_vectors, train)
+            scalar_dict[t] = data[t].properties
+            vector_dict[t] = vectors
+            if self.concat_input_vector:
+                full[t] = torch.cat([data[t].properties, vectors], dim=1)
+        return full if self.concat_input_vector else (scalar_dict, vector_dict)
+
+    def _noisy(self, x: torch.Tensor, train: bool) -> torch.Tensor:
+        if train and self.training_noise:
+            return x + noise_like(x, self.training_noise_std)
+        return x

@@ -1,0 +1,112 @@
+"""Device-resident batched heterogeneous graph: the stand-in for the `HeteroData` batch the
+reference's data builders return (geometry_rl/modules/pyg_data/rigid_tasks_data.py:324-343).
+
+It exposes the attributes the reference's models read (`node_types`, `edge_types`,
+`edge_index_dict`, `graph[node_type].pos`, `output_mask_key`, `output_mask`, `len(graph)`) and, in
+addition, the sorted-CSR `EdgeSet`s the CUDA kernels consume.  Topology lives on the GPU and is built
+by the K1 kernels (ops.knn_graph / dense_edges / build_edge_set); it is constructed once per batch
+size and re-used, exactly like the reference's cached placeholder (rigid_tasks_data.py:254-255).
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ... import ops
+
+EdgeType = Tuple[str, str, str]
+
+
+class NodeStore:
+    """Attribute bag of one node type (pos, norm_pos, properties)."""
+
+    def __init__(self, num_nodes: int):
+        self.num_nodes = num_nodes
+        self.pos: Optional[torch.Tensor] = None
+        self.norm_pos: Optional[torch.Tensor] = None
+        self.properties: Optional[torch.Tensor] = None
+
+
+class GraphBatch:
+    def __init__(self, num_graphs: int, nodes_per_graph: Dict[str, int], device):
+        self.num_graphs = num_graphs
+        self.nodes_per_graph = dict(nodes_per_graph)
+        self.node_types: List[str] = list(nodes_per_graph.keys())
+        self.device = device
+        self._stores = {t: NodeStore(num_graphs * n) for t, n in nodes_per_graph.items()}
+        self.edge_types: List[EdgeType] = []
+        self.edge_sets: Dict[EdgeType, ops.EdgeSet] = {}
+        self.output_mask_key: Optional[str] = None
+        self.output_mask: slice = slice(None)
+        self.homo_batch = None
+        self._homo: Optional[ops.EdgeSet] = None
+
+    # -- HeteroData-like surface ---------------------------------------------------------------
+    def __len__(self):
+        return self.num_graphs
+
+    def __getitem__(self, key) -> NodeStore:
+        return self._stores[str.__str__(key) if isinstance(key, str) else key]
+
+    @property
+    def edge_index_dict(self) -> Dict[EdgeType, torch.Tensor]:
+        return {et: es.coo for et, es in self.edge_sets.items()}
+
+    @property
+    def num_nodes(self) -> int:
+        return self.num_graphs * sum(self.nodes_per_graph.values())
+
+    @property
+    def node_offsets(self) -> Dict[str, int]:
+        out, off = {}, 0
+        for t in self.node_types:
+            out[t] = off
+            off += self.nodes_per_graph[t]
+        return out
+
+    def add_edge_type(self, et: EdgeType, coo: torch.Tensor, edge_ptr: torch.Tensor):
+        src, _, dst = et
+        self.edge_types.append(et)
+        self.edge_sets[et] = ops.build_edge_set(coo, edge_ptr, self.num_graphs, self.nodes_per_graph[src],
+                                                self.nodes_per_graph[dst])
+
+    def shallow_copy(self) -> "GraphBatch":
+        """`example_data.clone()` of the reference without copying the (immutable) topology."""
+        g = GraphBatch.__new__(GraphBatch)
+        g.__dict__.update(self.__dict__)
+        g._stores = {}
+        for t, s in self._stores.items():
+            ns = NodeStore(s.num_nodes)
+            ns.properties = s.properties
+            g._stores[t] = ns
+        return g
+
+    # -- homogeneous view (ponita_gcn.py:65-83) ----------------------------------------------------
+    def homogeneous(self) -> ops.EdgeSet:
+        """All edge types merged into one graph whose nodes are the node types concatenated per graph
+        (node_types order); per graph the edges keep edge-type insertion order, as to_homogeneous()
+        yields them, so the segmented sums see the same edge order as the reference."""
+        if self._homo is None:
+            B, dev = self.num_graphs, self.device
+            n_tot = sum(self.nodes_per_graph.values())
+            offs = self.node_offsets
+            counts = [self.edge_sets[et].edge_ptr[1:] - self.edge_sets[et].edge_ptr[:-1] for et in self.edge_types]
+            total = torch.stack(counts).sum(0) if counts else torch.zeros(B, dtype=torch.int64, device=dev)
+            homo_ptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+            homo_ptr[1:] = torch.cumsum(total, 0)
+            E = int(homo_ptr[-1].item())
+            coo = torch.empty(2, max(E, 1), dtype=torch.int64, device=dev)
+            before = torch.zeros(B, dtype=torch.int64, device=dev)
+            for et, cnt in zip(self.edge_types, counts):
+                es = self.edge_sets[et]
+                if es.n_edges > 0:
+                    src, _, dst = et
+                    g = torch.repeat_interleave(torch.arange(B, device=dev), cnt)
+                    r = torch.arange(es.n_edges, device=dev) - es.edge_ptr[:-1][g]
+                    dest = homo_ptr[:-1][g] + before[g] + r
+                    ls = es.coo[0] - g * self.nodes_per_graph[src]
+                    ld = es.coo[1] - g * self.nodes_per_graph[dst]
+                    coo[0, dest] = g * n_tot + offs[src] + ls
+                    coo[1, dest] = g * n_tot + offs[dst] + ld
+                before = before + cnt
+            self._homo = ops.build_edge_set(coo[:, :E], homo_ptr, B, n_tot, n_tot)
+        return self._homo

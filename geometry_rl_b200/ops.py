@@ -1,0 +1,363 @@
+"""torch.autograd wrappers around the C-ABI kernels (host side of the hot path).
+
+Everything here is plumbing: tensor allocation, weight re-packing, descriptor filling and the
+autograd graph.  All arithmetic on latents / edges happens inside libgrl_b200.so; there is no
+eager fallback — tensors must live on a CUDA device.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+ROW = 16 * 64
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: edge construction and CSR
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class EdgeSet:
+    """One edge type of a batched graph, in the layouts the kernels consume.
+
+    `coo` keeps the reference's coalesced [2, E] int64 edge_index (parity artefact, rows = source,
+    target); everything else is in "edge order" = dst-sorted CSR order with ties in COO order."""
+    n_src: int
+    n_dst: int
+    n_edges: int
+    coo: torch.Tensor
+    edge_ptr: torch.Tensor  # [B+1] int64
+    rowptr_dst: torch.Tensor  # [n_dst+1] int32
+    edge_src: torch.Tensor  # [E] int32
+    edge_dst: torch.Tensor  # [E] int32
+    eid_coo: torch.Tensor  # [E] int32: edge order -> COO position
+    rowptr_src: torch.Tensor  # [n_src+1] int32
+    src_eid: torch.Tensor  # [E] int32: src-sorted entry -> edge-order position
+
+
+def knn_edge_ptr(num_valid: Optional[torch.Tensor], B: int, P: int, k: int, device) -> torch.Tensor:
+    edge_ptr = torch.empty(B + 1, dtype=torch.int64, device=device)
+    L.call("grl_knn_edge_ptr", L.ptr(num_valid), B, P, k, L.ptr(edge_ptr))
+    return edge_ptr
+
+
+def knn_graph(pos: torch.Tensor, num_valid: Optional[torch.Tensor], k: int):
+    """pos [B,P,3] fp32 -> (coo [2,E] int64 coalesced, edge_ptr [B+1])."""
+    pos = _f32c(pos)
+    B, P, _ = pos.shape
+    if num_valid is not None:
+        num_valid = num_valid.to(torch.int32).contiguous()
+    edge_ptr = knn_edge_ptr(num_valid, B, P, k, pos.device)
+    E = int(edge_ptr[-1].item())  # topology is built once per batch size; this sync is off the step path
+    coo = torch.empty(2, max(E, 1), dtype=torch.int64, device=pos.device)
+    if E > 0:
+        L.call("grl_knn_graph", L.ptr(pos), L.ptr(num_valid), L.ptr(edge_ptr), B, P, k, L.ptr(coo), coo.stride(0))
+    return coo[:, :E], edge_ptr
+
+
+def radius_neighbors(pos: torch.Tensor, num_valid: Optional[torch.Tensor], radius: float, max_neighbors: int):
+    pos = _f32c(pos)
+    B, P, _ = pos.shape
+    if num_valid is not None:
+        num_valid = num_valid.to(torch.int32).contiguous()
+    nbr = torch.empty(B, P, max_neighbors, dtype=torch.int32, device=pos.device)
+    cnt = torch.empty(B, P, dtype=torch.int32, device=pos.device)
+    L.call("grl_radius_neighbors", L.ptr(pos), L.ptr(num_valid), B, P, float(radius), max_neighbors, L.ptr(nbr),
+           L.ptr(cnt))
+    return nbr, cnt
+
+
+def dense_edges(mode: int, B: int, n_src: int, n_dst: int, device, num_valid: Optional[torch.Tensor] = None):
+    """mode 0: ordered pairs j != k among n_src; mode 1: valid sources x all destinations."""
+    if mode == 0:
+        counts = torch.full((B,), n_src * (n_src - 1), dtype=torch.int64, device=device)
+    else:
+        nv = (num_valid.to(torch.int64) if num_valid is not None
+              else torch.full((B,), n_src, dtype=torch.int64, device=device))
+        counts = nv * n_dst
+    edge_ptr = torch.zeros(B + 1, dtype=torch.int64, device=device)
+    edge_ptr[1:] = torch.cumsum(counts, 0)
+    E = int(edge_ptr[-1].item())
+    coo = torch.empty(2, max(E, 1), dtype=torch.int64, device=device)
+    if E > 0:
+        nvp = num_valid.to(torch.int32).contiguous() if num_valid is not None else None
+        L.call("grl_dense_edges", mode, L.ptr(nvp), L.ptr(edge_ptr), B, n_src, n_dst, L.ptr(coo), coo.stride(0))
+    return coo[:, :E], edge_ptr
+
+
+def _csr(coo: torch.Tensor, edge_ptr: torch.Tensor, B: int, n_key: int, key_row: int):
+    E = coo.shape[1]
+    dev = coo.device
+    rowptr = torch.zeros(B * n_key + 1, dtype=torch.int32, device=dev)
+    other = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    if E > 0:
+        assert coo.stride(1) == 1
+        L.call("grl_csr_build", L.ptr_any(coo), coo.stride(0), L.ptr(edge_ptr), B, n_key, key_row, L.ptr(rowptr),
+               L.ptr(other), L.ptr(eid))
+    return rowptr, other[:E], eid[:E]
+
+
+def build_edge_set(coo: torch.Tensor, edge_ptr: torch.Tensor, B: int, n_src_per_graph: int,
+                   n_dst_per_graph: int) -> EdgeSet:
+    """dst-sorted CSR (edge order) and src-sorted CSR of a batched, graph-major COO."""
+    E = coo.shape[1]
+    if coo.stride(1) != 1:
+        coo = coo.contiguous()
+    rowptr_dst, edge_src, eid_coo = _csr(coo, edge_ptr, B, n_dst_per_graph, 1)
+    edge_dst = coo[1][eid_coo.long()].to(torch.int32) if E > 0 else edge_src.clone()
+    coo2 = torch.stack([edge_src.long(), edge_dst.long()]) if E > 0 else coo
+    rowptr_src, _, src_eid = _csr(coo2, edge_ptr, B, n_src_per_graph, 0)
+    return EdgeSet(B * n_src_per_graph, B * n_dst_per_graph, E, coo, edge_ptr, rowptr_dst, edge_src.contiguous(),
+                   edge_dst.contiguous(), eid_coo.contiguous(), rowptr_src, src_eid.contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# partial-gradient helpers
+# ------------------------------------------------------------------------------------------------
+def _reduce(partials: torch.Tensor) -> torch.Tensor:
+    n_p, n = partials.shape
+    out = torch.empty(n, dtype=torch.float32, device=partials.device)
+    L.call("grl_reduce_partials", L.ptr(partials), n_p, n, L.ptr(out), 0)
+    return out
+
+
+def _n_partials(n_units: int) -> int:
+    return max(1, min(n_units, L.sm_count()))
+
+
+# ------------------------------------------------------------------------------------------------
+# lift + node encoder
+# ------------------------------------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scalars, vectors, weight, ori3, dim):
+        scalars, vectors, weight = _f32c(scalars), _f32c(vectors), _f32c(weight)
+        N, S = scalars.shape
+        V = vectors.shape[1] // 3
+        assert weight.shape == (64, S + V), f"node encoder weight {tuple(weight.shape)} vs S+V={S + V}"
+        x = torch.empty(N, 16, 64, dtype=torch.float32, device=scalars.device)
+        d = L.GrlEmbedDesc(n_nodes=N, n_scalars=S, n_vectors=V, dim=dim, scalars=L.ptr(scalars), vectors=L.ptr(vectors),
+                           ori=L.ptr(ori3), weight=L.ptr(weight), x=L.ptr(x))
+        L.call("grl_embed_fwd", C.byref(d))
+        ctx.save_for_backward(scalars, vectors, ori3)
+        ctx.meta = (N, S, V, dim)
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        scalars, vectors, ori3 = ctx.saved_tensors
+        N, S, V, dim = ctx.meta
+        gx = _f32c(gx)
+        n_p = _n_partials(N)
+        partials = torch.empty(n_p, 64 * (S + V), dtype=torch.float32, device=gx.device)
+        d = L.GrlEmbedDesc(n_nodes=N, n_scalars=S, n_vectors=V, dim=dim, scalars=L.ptr(scalars), vectors=L.ptr(vectors),
+                           ori=L.ptr(ori3), grad_x=L.ptr(gx), grad_weight_partials=L.ptr(partials), n_partials=n_p)
+        L.call("grl_embed_bwd", C.byref(d))
+        return None, None, _reduce(partials).view(64, S + V), None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# edge basis
+# ------------------------------------------------------------------------------------------------
+class EdgeBasisFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos_src, pos_dst, w1, b1, w2, b2, ori3, dim, es: EdgeSet):
+        pos_src, pos_dst = _f32c(pos_src), _f32c(pos_dst)
+        dev = pos_src.device
+        w1t = torch.zeros(16, 64, dtype=torch.float32, device=dev)
+        w1t[:14] = w1.detach().t()
+        w2t = w2.detach().t().contiguous()
+        b1c, b2c = _f32c(b1.detach()), _f32c(b2.detach())
+        basis = torch.empty(es.n_edges, 16, 64, dtype=torch.float32, device=dev)
+        d = L.GrlBasisDesc(n_edges=es.n_edges, dim=dim, edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst),
+                           pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
+                           w2t=L.ptr(w2t), b2=L.ptr(b2c), basis=L.ptr(basis))
+        if es.n_edges > 0:
+            L.call("grl_edge_basis_fwd", C.byref(d))
+        ctx.save_for_backward(pos_src, pos_dst, w1t, b1c, w2t, b2c, _f32c(w2.detach()), ori3)
+        ctx.es, ctx.dim = es, dim
+        return basis
+
+    @staticmethod
+    def backward(ctx, g_basis):
+        pos_src, pos_dst, w1t, b1c, w2t, b2c, w2, ori3 = ctx.saved_tensors
+        es, dim = ctx.es, ctx.dim
+        dev = pos_src.device
+        if es.n_edges == 0:
+            z = torch.zeros
+            return (None, None, z(64, 14, device=dev), z(64, device=dev), z(64, 64, device=dev), z(64, device=dev),
+                    None, None, None)
+        g_basis = _f32c(g_basis)
+        n_p = _n_partials((es.n_edges + 7) // 8)
+        partials = torch.empty(n_p, L.BASIS_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        d = L.GrlBasisDesc(n_edges=es.n_edges, dim=dim, edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst),
+                           pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
+                           w2t=L.ptr(w2t), b2=L.ptr(b2c), w2=L.ptr(w2), grad_basis=L.ptr(g_basis),
+                           grad_partials=L.ptr(partials), n_partials=n_p)
+        L.call("grl_edge_basis_bwd", C.byref(d))
+        g = _reduce(partials)
+        gw1 = g[:1024].view(64, 16)[:, :14].contiguous()
+        gb1 = g[1024:1088]
+        gw2 = g[1088:1088 + 4096].view(64, 64)
+        gb2 = g[1088 + 4096:]
+        return None, None, gw1, gb1, gw2, gb2, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# separable fibre-bundle convolution + ConvNeXt update
+# ------------------------------------------------------------------------------------------------
+class FiberConvFn(torch.autograd.Function):
+    """out = x_dst + MLP(LN(fibre(scatter(kernel(basis) * x_src[src])) + bias)).
+
+    `x_dst is None` means a homogeneous graph (source and destination nodes are the same tensor)."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet):
+        homo = x_dst is None
+        x_src = _f32c(x_src)
+        xd = x_src if homo else _f32c(x_dst)
+        basis, fk = _f32c(basis), _f32c(fk)
+        dev = x_src.device
+        assert x_src.shape[0] == es.n_src and xd.shape[0] == es.n_dst, "latent rows do not match the edge set"
+        assert tuple(x_src.shape[1:]) == (16, 64) and tuple(w1.shape) == (256, 64) and tuple(w2.shape) == (64, 256)
+        wk_d, w1_d, w2_d = wk.detach(), w1.detach(), w2.detach()
+        wk_c = _f32c(wk_d)
+        wk_t = wk_d.t().contiguous()
+        w1_c = _f32c(w1_d)
+        w1_t = w1_d.view(4, 64, 64).transpose(1, 2).contiguous()
+        w2_t = w2_d.view(64, 4, 64).permute(1, 2, 0).contiguous()
+        w2_c = w2_d.view(64, 4, 64).permute(1, 0, 2).contiguous()
+        bias_c, lng_c, lnb_c = _f32c(bias.detach()), _f32c(ln_g.detach()), _f32c(ln_b.detach())
+        b1_c, b2_c = _f32c(b1.detach()), _f32c(b2.detach())
+        x1 = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=dev)
+        out = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=dev)
+        d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
+                          edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), rowptr_src=L.ptr(es.rowptr_src),
+                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), x_dst=L.ptr(xd), basis=L.ptr(basis),
+                          fiber_kernel=L.ptr(fk), wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
+                          ln_b=L.ptr(lnb_c), w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_t=L.ptr(w2_t),
+                          w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
+        L.call("grl_fbconv_edge_fwd", C.byref(d))
+        L.call("grl_fbconv_node_fwd", C.byref(d))
+        ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1)
+        ctx.es, ctx.homo = es, homo
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1 = ctx.saved_tensors
+        es, homo = ctx.es, ctx.homo
+        dev = x_src.device
+        g_out = _f32c(g_out)
+        g_x1 = torch.empty_like(x1)
+        g_xsrc = torch.empty_like(x_src)
+        g_basis = torch.empty_like(basis)
+        n_pn = _n_partials((es.n_dst + 7) // 8)
+        n_pe = _n_partials((es.n_src + 15) // 16)
+        node_part = torch.empty(n_pn, L.NODE_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        edge_part = torch.empty(n_pe, L.EDGE_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
+                          edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), rowptr_src=L.ptr(es.rowptr_src),
+                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), basis=L.ptr(basis), fiber_kernel=L.ptr(fk),
+                          wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c), ln_b=L.ptr(lnb_c),
+                          w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_c=L.ptr(w2_c), x1=L.ptr(x1),
+                          grad_out=L.ptr(g_out), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),
+                          grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=L.ptr(g_basis),
+                          accumulate_grad_basis=0, node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
+                          edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
+        L.call("grl_fbconv_node_bwd", C.byref(d))
+        L.call("grl_fbconv_edge_bwd", C.byref(d))
+        g = _reduce(node_part)
+        o = 0
+        gw1 = g[o:o + 256 * 64].view(256, 64); o += 256 * 64
+        gb1 = g[o:o + 256]; o += 256
+        gw2 = g[o:o + 64 * 256].view(64, 256); o += 64 * 256
+        gb2 = g[o:o + 64]; o += 64
+        glng = g[o:o + 64]; o += 64
+        glnb = g[o:o + 64]; o += 64
+        gbias = g[o:o + 64]; o += 64
+        gfk = g[o:o + 16 * 16 * 64].view(16, 16, 64)
+        gwk = _reduce(edge_part).view(64, 64)
+        g_xdst = None if homo else g_out
+        return g_xsrc, g_xdst, g_basis, gfk, gwk, gbias, glng, glnb, gw1, gb1, gw2, gb2, None
+
+
+def fiber_conv(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet):
+    return FiberConvFn.apply(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es)
+
+
+def aggregate_messages(x_src, basis, wk, es: EdgeSet) -> torch.Tensor:
+    """x1 only (no grad): used by the one-time calibration of conv.py:104-105,151-157."""
+    x_src, basis = _f32c(x_src.detach()), _f32c(basis.detach())
+    wk_t = wk.detach().t().contiguous()
+    x1 = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=x_src.device)
+    d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
+                      edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), x_src=L.ptr(x_src), basis=L.ptr(basis),
+                      wk_t=L.ptr(wk_t), x1=L.ptr(x1))
+    L.call("grl_fbconv_edge_fwd", C.byref(d))
+    return x1
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: GAE
+# ------------------------------------------------------------------------------------------------
+def gae(reward, value_T1, done, terminated, gamma: float, lmbda: float):
+    """reward/done/terminated [B,T], value_T1 [B,T+1] -> (advantage, value_target) [B,T]."""
+    reward, value_T1 = _f32c(reward), _f32c(value_T1)
+    B, T = reward.shape
+    assert value_T1.shape == (B, T + 1)
+    done_u8 = done.to(torch.uint8).contiguous()
+    term_u8 = terminated.to(torch.uint8).contiguous()
+    adv = torch.empty_like(reward)
+    vt = torch.empty_like(reward)
+    L.call("grl_gae_scan", L.ptr(reward), L.ptr(value_T1), L.ptr(done_u8), L.ptr(term_u8), float(gamma), float(lmbda), B,
+           T, L.ptr(adv), L.ptr(vt))
+    return adv, vt
+
+
+# ------------------------------------------------------------------------------------------------
+# K4: trust-region projection
+# ------------------------------------------------------------------------------------------------
+class TrplProjectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, v, old_mean, old_v, eps_mean, eps_cov, proj_type):
+        mean, v, old_mean, old_v = _f32c(mean), _f32c(v), _f32c(old_mean), _f32c(old_v)
+        B, k = mean.shape
+        pm, pv = torch.empty_like(mean), torch.empty_like(v)
+        eta = torch.empty(B, 2, dtype=torch.float64, device=mean.device)
+        d = L.GrlProjDesc(batch=B, k=k, proj_type=proj_type, eps_mean=float(eps_mean), eps_cov=float(eps_cov),
+                          mean=L.ptr(mean), v=L.ptr(v), old_mean=L.ptr(old_mean), old_v=L.ptr(old_v), proj_mean=L.ptr(pm),
+                          proj_v=L.ptr(pv), eta=L.ptr_any(eta))
+        L.call("grl_trpl_fwd", C.byref(d))
+        ctx.save_for_backward(mean, v, old_mean, old_v, eta)
+        ctx.meta = (float(eps_mean), float(eps_cov), proj_type)
+        return pm, pv
+
+    @staticmethod
+    def backward(ctx, g_pm, g_pv):
+        mean, v, old_mean, old_v, eta = ctx.saved_tensors
+        eps_mean, eps_cov, proj_type = ctx.meta
+        B, k = mean.shape
+        g_pm = _f32c(g_pm) if g_pm is not None else torch.zeros_like(mean)
+        g_pv = _f32c(g_pv) if g_pv is not None else torch.zeros_like(v)
+        gm, gv = torch.empty_like(mean), torch.empty_like(v)
+        d = L.GrlProjDesc(batch=B, k=k, proj_type=proj_type, eps_mean=eps_mean, eps_cov=eps_cov, mean=L.ptr(mean),
+                          v=L.ptr(v), old_mean=L.ptr(old_mean), old_v=L.ptr(old_v), eta=L.ptr_any(eta),
+                          grad_proj_mean=L.ptr(g_pm), grad_proj_v=L.ptr(g_pv), grad_mean=L.ptr(gm), grad_v=L.ptr(gv))
+        L.call("grl_trpl_bwd", C.byref(d))
+        return gm, gv, None, None, None, None, None
+
+
+def trpl_project(mean, v, old_mean, old_v, eps_mean, eps_cov, proj_type="kl"):
+    """Projected (mean, v) of a diagonal Gaussian; v is the diagonal of the reference's "std" matrix."""
+    code = {"kl": 0, "w2": 1}[proj_type]
+    return TrplProjectFn.apply(mean, v, old_mean, old_v, eps_mean, eps_cov, code)

@@ -1,0 +1,225 @@
+/*
+ * grl_b200.h — C ABI of the B200-native (sm_100a) GeometryRL policy-training hot path.
+ *
+ * The reference (thobotics/geometry_rl) has no FFI of its own: its hot path is Python calling
+ * third-party wheels.  Each entry point below replaces one such call site (cited as
+ * reference-file:line, paths relative to the reference checkout).  The Python host layer
+ * (geometry_rl_b200/_lib.py, ops.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless a parameter name ends in `_host`.
+ *  - Buffers (inputs, outputs, workspaces) are allocated and owned by the caller; nothing is
+ *    allocated or freed behind the ABI.
+ *  - Every function is stream-ordered on `stream` (a cudaStream_t), never synchronises, keeps no
+ *    mutable global state and is safe to capture in a CUDA graph.
+ *  - Return value: GRL_OK or a negative GRL_E* code; grl_last_error() returns a thread-local
+ *    message.  No exceptions cross the ABI.
+ *  - Latent rows are [O=16][C=64] fp32 (4096 B per node); "edge order" is the dst-sorted CSR
+ *    order produced by grl_csr_build.
+ */
+#ifndef GRL_B200_H_
+#define GRL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRL_OK 0
+#define GRL_EINVAL (-1)      /* bad shape / null pointer / inconsistent sizes            */
+#define GRL_EUNSUPPORTED (-2) /* O != 16, C != 64, hidden != 256, k > GRL_MAX_ACTION_DIM … */
+#define GRL_ECUDA (-3)       /* cudaGetLastError() != cudaSuccess after a launch          */
+
+#define GRL_NUM_ORI 16
+#define GRL_CHANNELS 64
+#define GRL_HIDDEN 256
+#define GRL_BASIS_FEATS 14   /* PolynomialFeatures(2) of (i1, i2): 2 + 4 + 8               */
+#define GRL_MAX_ACTION_DIM 16
+#define GRL_MAX_KNN 8
+
+typedef void* grl_stream_t; /* cudaStream_t */
+
+int grl_abi_version(void);
+const char* grl_last_error(void);
+/* Number of SMs of the current device (grid sizing for the persistent kernels). */
+int grl_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  edge construction -> sorted CSR
+ * replaces torch_geometric.nn.knn_graph(points[:P_i], k) + HeteroData.coalesce() per graph in a
+ * Python loop: geometry_rl/modules/pyg_data/rigid_tasks_data.py:275-321, rope_tasks_data.py:251.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Per-graph edge counts of a kNN graph: count[b] = P_b * min(k, P_b - 1), and their exclusive
+ * prefix sum edge_ptr[B+1].  num_valid may be NULL (all P points valid). */
+int grl_knn_edge_ptr(const int32_t* num_valid, int B, int P, int k, int64_t* edge_ptr, grl_stream_t stream);
+
+/* Batched brute-force kNN (loop=False) over pos[B][P][3] (first num_valid[b] points of graph b),
+ * emitted as the COALESCED COO the reference ends up with: row0 = neighbour (source), row1 =
+ * centre (target), sorted by (row0,row1), global node index = b*P + local.  coo is [2][E_total]
+ * int64 with E_total = edge_ptr[B].  Squared distances are (dx*dx + dy*dy) + dz*dz with separate
+ * fp32 roundings; ties -> lower index. */
+int grl_knn_graph(const float* pos, const int32_t* num_valid, const int64_t* edge_ptr, int B, int P, int k,
+                  int64_t* coo, int64_t coo_row_stride, grl_stream_t stream);
+
+/* Radius graph (extension, no reference counterpart): neighbours within `radius`,
+ * at most max_neighbors nearest, same output convention but into a PADDED buffer:
+ * nbr[B][P][max_neighbors] (local index or -1), cnt[B][P]. */
+int grl_radius_neighbors(const float* pos, const int32_t* num_valid, int B, int P, float radius, int max_neighbors,
+                         int32_t* nbr, int32_t* cnt, grl_stream_t stream);
+
+/* Dense edge sets the reference builds with nested Python loops
+ * (rigid_tasks_data.py:289-300,313-319): write the coalesced batched COO for
+ *   mode 0: all ordered pairs j != k among n_src nodes per graph      (AGENT / cloth INTERNAL)
+ *   mode 1: every valid source j < num_valid[b] -> every destination k (TASK)
+ * edge_ptr[B+1] must hold the exclusive prefix sum of the per-graph counts. */
+int grl_dense_edges(int mode, const int32_t* num_valid, const int64_t* edge_ptr, int B, int n_src, int n_dst,
+                    int64_t* coo, int64_t coo_row_stride, grl_stream_t stream);
+
+/* Stable counting sort of a batched COO (graph-major, graph b owns edges [edge_ptr[b],
+ * edge_ptr[b+1]) and key nodes [b*n_key, (b+1)*n_key)) by row `key_row` (1 = dst, 0 = src):
+ *   rowptr[B*n_key + 1], other[E] (the non-key endpoint), eid[E] (position in the input COO).
+ * Relative order of edges with equal key is preserved (== summation order of a sequential
+ * scatter over the coalesced COO). */
+int grl_csr_build(const int64_t* coo, int64_t coo_row_stride, const int64_t* edge_ptr, int B, int n_key, int key_row,
+                  int32_t* rowptr, int32_t* other, int32_t* eid, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  fused equivariant message passing (forward and backward)
+ * replaces hepi.py:109-123,136-171 / ponita/conv.py:71-149 / ponita/ponita.py:149-185,219-230:
+ * PolynomialFeatures+basis_fn, kernel Linear, gather*mul, torch_scatter.scatter (conv.py:141),
+ * fibre einsum (conv.py:90), LayerNorm+Linear+GELU+Linear node update (conv.py:64-69,112).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Lift + node encoder (to_from_sphere.py:4-9, hepi.py:136-143):
+ *   x[n][o][c] = sum_s scal[n][s] W[c][s] + sum_v <vec[n][v][:dim], ori[o]> W[c][S+v]          */
+typedef struct {
+  int32_t n_nodes, n_scalars, n_vectors, dim; /* dim = 2 | 3 */
+  const float* scalars;                        /* [N][S]                                        */
+  const float* vectors;                        /* [N][V][3]                                     */
+  const float* ori;                            /* [16][3] (z = 0 when dim == 2)                 */
+  const float* weight;                         /* [64][S+V] row-major (nn.Linear.weight)        */
+  float* x;                                    /* [N][16][64]                                   */
+  /* backward */
+  const float* grad_x;                         /* [N][16][64]                                   */
+  float* grad_weight_partials;                 /* [n_partials][64][S+V]                         */
+  int32_t n_partials;
+} GrlEmbedDesc;
+int grl_embed_fwd(const GrlEmbedDesc* d, grl_stream_t stream);
+int grl_embed_bwd(const GrlEmbedDesc* d, grl_stream_t stream);
+
+/* Edge basis (hepi.py:109-123 + basis_fn hepi.py:76-82): per edge (edge order) and orientation
+ * invariants (i1,i2) -> 14 polynomial features -> Linear(14,64) GELU Linear(64,64) GELU.       */
+typedef struct {
+  int32_t n_edges, dim;
+  const int32_t* edge_src;   /* [E] index into pos_src                                          */
+  const int32_t* edge_dst;   /* [E] index into pos_dst                                          */
+  const float* pos_src;      /* [Ns][3]                                                         */
+  const float* pos_dst;      /* [Nd][3]                                                         */
+  const float* ori;          /* [16][3]                                                         */
+  const float* w1t;          /* [16][64]: w1t[f][n] = W1[n][f], rows 14,15 zero                 */
+  const float* b1;           /* [64]                                                            */
+  const float* w2t;          /* [64][64]: w2t[k][n] = W2[n][k]                                  */
+  const float* b2;           /* [64]                                                            */
+  float* basis;              /* [E][16][64]                                                     */
+  /* backward */
+  const float* w2;           /* [64][64] row-major W2[n][k]                                     */
+  const float* grad_basis;   /* [E][16][64]                                                     */
+  float* grad_partials;      /* [n_partials][GRL_BASIS_GRAD_FLOATS]                             */
+  int32_t n_partials;
+} GrlBasisDesc;
+/* partial layout: gW1[64][16] | gb1[64] | gW2[64][64] | gb2[64] */
+#define GRL_BASIS_GRAD_FLOATS (64 * 16 + 64 + 64 * 64 + 64)
+int grl_edge_basis_fwd(const GrlBasisDesc* d, grl_stream_t stream);
+int grl_edge_basis_bwd(const GrlBasisDesc* d, grl_stream_t stream);
+
+/* One separable fibre-bundle convolution + ConvNeXt node update. */
+typedef struct {
+  int32_t n_src, n_dst, n_edges;
+  /* dst-sorted CSR (edge order) */
+  const int32_t* rowptr_dst; /* [n_dst+1]                                                       */
+  const int32_t* edge_src;   /* [E]                                                             */
+  const int32_t* edge_dst;   /* [E]                                                             */
+  /* src-sorted CSR: entries reference edge-order positions */
+  const int32_t* rowptr_src; /* [n_src+1]                                                       */
+  const int32_t* src_eid;    /* [E] edge-order position of the q-th src-sorted entry            */
+  const float* x_src;        /* [n_src][16][64]                                                 */
+  const float* x_dst;        /* [n_dst][16][64]                                                 */
+  const float* basis;        /* [E][16][64]                                                     */
+  const float* fiber_kernel; /* [16(o)][16(p)][64]: x2[p] = 1/16 sum_o x1[o] * fk[o][p]         */
+  const float* wk_t;         /* [64][64]: wk_t[j][c] = kernel.weight[c][j]                      */
+  const float* wk;           /* [64][64] kernel.weight[c][j]                                    */
+  const float* bias;         /* [64]                                                            */
+  const float* ln_g;         /* [64]                                                            */
+  const float* ln_b;         /* [64]                                                            */
+  const float* w1_t;         /* [4][64(k)][64(n)]: w1_t[q][k][n] = W1[q*64+n][k]                */
+  const float* w1;           /* [256][64] row-major                                             */
+  const float* b1;           /* [256]                                                           */
+  const float* w2_t;         /* [4][64(k)][64(n)]: w2_t[q][k][n] = W2[n][q*64+k]                */
+  const float* w2_c;         /* [4][64(n)][64(m)]: w2_c[q][n][m] = W2[n][q*64+m]                */
+  const float* b2;           /* [64]                                                            */
+  float* x1;                 /* [n_dst][16][64] aggregated messages (saved for backward)        */
+  float* out;                /* [n_dst][16][64]                                                 */
+  int32_t accumulate_out;    /* out += x_dst + mlp(...) (HeteroConv group "sum")                */
+  /* backward */
+  const float* grad_out;     /* [n_dst][16][64]                                                 */
+  float* grad_x1;            /* [n_dst][16][64] workspace                                       */
+  float* grad_x_src;         /* [n_src][16][64]                                                 */
+  const float* grad_x_src_init; /* optional [n_src][16][64] added in (may alias nothing)        */
+  float* grad_basis;         /* [E][16][64]                                                     */
+  int32_t accumulate_grad_basis;
+  float* node_grad_partials; /* [n_partials_node][GRL_NODE_GRAD_FLOATS]                         */
+  int32_t n_partials_node;
+  float* edge_grad_partials; /* [n_partials_edge][64*64] (kernel.weight)                        */
+  int32_t n_partials_edge;
+} GrlConvDesc;
+/* node partial layout: gW1[256][64] | gb1[256] | gW2[64][256] | gb2[64] | g_ln_g[64] | g_ln_b[64]
+ *                      | g_bias[64] | g_fk[16][16][64] */
+#define GRL_NODE_GRAD_FLOATS (256 * 64 + 256 + 64 * 256 + 64 + 64 + 64 + 64 + 16 * 16 * 64)
+int grl_fbconv_edge_fwd(const GrlConvDesc* d, grl_stream_t stream); /* basis,x_src -> x1            */
+int grl_fbconv_node_fwd(const GrlConvDesc* d, grl_stream_t stream); /* x1,x_dst -> out             */
+int grl_fbconv_node_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_out -> grad_x1, node partials */
+int grl_fbconv_edge_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_x1 -> grad_x_src, grad_basis, edge partials */
+
+/* out[i] = sum_p partials[p][i], fixed order (deterministic cross-CTA reduction). */
+int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,
+                        grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  GAE: replaces torchrl.objectives.value.GAE(...)(data) at examples/torchrl/train.py:134-140,
+ * 249-252 (the advantage arithmetic; the critic call stays with the caller).
+ * reward/done/terminated [B][T], value [B][T+1] (shifted=True layout) -> adv, value_target [B][T].
+ * ------------------------------------------------------------------------------------------ */
+int grl_gae_scan(const float* reward, const float* value_T1, const uint8_t* done, const uint8_t* terminated,
+                 float gamma, float lmbda, int B, int T, float* advantage, float* value_target, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  TRPL projection of a diagonal Gaussian (mean + "std := cov" diagonal v):
+ * replaces projections/kl_projection_layer.py:15-111,162-204 (ITPAL cpp_projection on the CPU),
+ * projections/w2_projection_layer.py:15-68, base_projection_layer.py:71-100.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t batch, k;
+  int32_t proj_type;      /* 0 = KL, 1 = W2 (commuting, scale_prec = True)                      */
+  float eps_mean, eps_cov;
+  const float* mean;      /* [B][k]                                                             */
+  const float* v;         /* [B][k] diagonal of the matrix the reference calls "std"            */
+  const float* old_mean;  /* [B][k]                                                             */
+  const float* old_v;     /* [B][k]                                                             */
+  float* proj_mean;       /* [B][k]                                                             */
+  float* proj_v;          /* [B][k]                                                             */
+  double* eta;            /* [B][2] saved (cov dual eta | W2 weight, mean omega); 0 = inactive  */
+  /* backward */
+  const float* grad_proj_mean; /* [B][k]                                                        */
+  const float* grad_proj_v;    /* [B][k]                                                        */
+  float* grad_mean;            /* [B][k]                                                        */
+  float* grad_v;               /* [B][k]                                                        */
+} GrlProjDesc;
+int grl_trpl_fwd(const GrlProjDesc* d, grl_stream_t stream);
+int grl_trpl_bwd(const GrlProjDesc* d, grl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRL_B200_H_ */

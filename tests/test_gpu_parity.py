@@ -1,0 +1,267 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  The CUDA path, called through the C ABI,
+is compared with (a) fixtures recorded from the unmodified reference (tests/golden) and (b) the CPU
+oracle on seeded synthetic inputs.  Tolerances (north_star): bit-exact integer outputs; fp32 outputs
+and gradients within 1e-5 relative to the tensor's max magnitude (2e-5 for gradients that pass through
+two erf/rsqrt chains, stated per assert)."""
+import pytest
+import torch
+
+from geometry_rl_b200.synthetic import CONFIGS, synthetic_obs
+from tests.helpers import load_golden, oracle_graph_from_obs
+from tests import gpu_helpers as G
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+GTOL = 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: topology, bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg_name,B", [("rigid_insertion_multi_hepi_trpl_cfg", 37), ("rope_shaping_hepi_trpl_cfg", 9),
+                                        ("cloth_hanging_multi_hepi_trpl_cfg", 11),
+                                        ("rigid_pushing_multi_empn_trpl_cfg", 64),
+                                        ("rigid_insertion_two_agents_multi_transformer_trpl_cfg", 8)])
+def test_topology_bit_exact(cfg_name, B):
+    cfg = CONFIGS[cfg_name]
+    gen = torch.Generator().manual_seed(100 + B)
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
+    og_, _ = oracle_graph_from_obs(cfg, obs, policy=True)
+    data = G.make_data(cfg, policy=True)
+    graph, feats = data.build_data(*G.obs_args(cfg, obs, policy=True), train=False)
+    assert graph.node_types == og_.node_types
+    assert [tuple(e) for e in graph.edge_types] == [tuple(e) for e in og_.edge_types]
+    for et in og_.edge_types:
+        assert torch.equal(graph.edge_index_dict[et].cpu(), og_.edge_index_dict[et]), f"COO mismatch {et}"
+        es = graph.edge_sets[et]
+        # CSR invariants: dst-sorted, stable; src-sorted view is a permutation of the same edges
+        ei = og_.edge_index_dict[et]
+        if ei.shape[1]:
+            order = torch.sort(ei[1], stable=True).indices
+            assert torch.equal(es.edge_src.cpu().long(), ei[0][order])
+            assert torch.equal(es.edge_dst.cpu().long(), ei[1][order])
+            assert torch.equal(es.eid_coo.cpu().long(), order)
+            so = torch.sort(ei[0][order], stable=True).indices
+            assert torch.equal(es.src_eid.cpu().long(), so)
+            deg = torch.bincount(ei[1], minlength=es.n_dst)
+            assert torch.equal(es.rowptr_dst.cpu().long()[1:] - es.rowptr_dst.cpu().long()[:-1], deg)
+    assert (graph.output_mask.start, graph.output_mask.stop) == (og_.output_mask.start, og_.output_mask.stop)
+    if cfg.model == "empn":
+        assert torch.equal(graph.homogeneous().coo.cpu(), og_.homogeneous_edge_index())
+
+
+def test_knn_ragged_and_tiny():
+    """Edge cases: graphs with 0, 1, 2, k and k+1 valid points; P not a multiple of anything."""
+    from geometry_rl_b200 import ops
+    from oracle.graph import knn_edges
+    torch.manual_seed(0)
+    P, k = 13, 3
+    nv = torch.tensor([0, 1, 2, 3, 4, 13, 7], dtype=torch.int32)
+    pos = torch.randn(len(nv), P, 3)
+    coo, ptr = ops.knn_graph(pos.cuda(), nv.cuda(), k)
+    exp = []
+    for b in range(len(nv)):
+        exp.append(knn_edges(pos[b, : int(nv[b])], k) + b * P)
+    exp = torch.cat(exp, dim=1)
+    assert torch.equal(coo.cpu(), exp)
+    counts = torch.tensor([e for e in [int(n) * max(0, min(k, int(n) - 1)) for n in nv]])
+    assert torch.equal((ptr[1:] - ptr[:-1]).cpu(), counts)
+
+
+def test_radius_neighbors_property():
+    from geometry_rl_b200 import ops
+    torch.manual_seed(1)
+    B, P, r, m = 5, 40, 0.9, 4
+    pos = torch.randn(B, P, 3)
+    nbr, cnt = ops.radius_neighbors(pos.cuda(), None, r, m)
+    nbr, cnt = nbr.cpu(), cnt.cpu()
+    d = torch.cdist(pos.double(), pos.double())
+    for b in range(B):
+        for i in range(P):
+            within = ((d[b, i] <= r) & (torch.arange(P) != i)).sum()
+            assert int(cnt[b, i]) == min(int(within), m)
+            js = nbr[b, i, : int(cnt[b, i])].long()
+            assert bool((d[b, i, js] <= r + 1e-6).all())
+            if len(js) > 1:
+                assert bool((d[b, i, js][1:] >= d[b, i, js][:-1] - 1e-7).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# K2: policy bodies against the reference fixtures (outputs + every parameter gradient)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["hepi_rigid_insertion", "hepi_cloth_hanging", "hepi_rope_shaping",
+                                  "empn_rigid_pushing"])
+def test_policy_body_matches_reference_fixture(name):
+    rec = load_golden(name)
+    cfg = CONFIGS[rec["config"]]
+    net = G.make_policy_body(cfg)
+    net.load_state_dict(rec["state_dict"], strict=True)
+    net.train()
+    data = G.make_data(cfg, policy=True)
+    graph, u = data.build_data(*G.obs_args(cfg, rec["obs"], policy=True), train=True)
+    for et in graph.edge_types:
+        assert torch.equal(graph.edge_index_dict[et].cpu(), rec["graph"]["edge_index"]["___".join(et)])
+    for nt in graph.node_types:
+        assert torch.equal(u[0][nt].cpu(), rec["scalar_dict"][nt])
+        assert torch.equal(u[1][nt].cpu(), rec["vector_dict"][nt])
+    out, hidden = net.one_step(graph, u)
+    assert G.rel(out, rec["out"]) < TOL, G.err_report("out", out, rec["out"])
+    assert G.rel(hidden, rec["hidden"]) < TOL, G.err_report("hidden", hidden, rec["hidden"])
+    loss = (out * rec["w_out"].cuda()).sum() + (hidden * rec["w_hid"].cuda()).sum()
+    loss.backward()
+    params = dict(net.named_parameters())
+    bad = []
+    for k, gref in rec["grads"].items():
+        g = params[k].grad
+        if gref is None:
+            if g is not None and float(g.abs().max()) != 0.0:
+                bad.append(f"{k}: expected no grad")
+            continue
+        if g is None:
+            bad.append(f"{k}: missing grad")
+        elif G.rel(g, gref) >= GTOL:
+            bad.append(G.err_report(k, g, gref))
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("cfg_name,B", [("rigid_insertion_multi_hepi_trpl_cfg", 96),
+                                        ("rigid_pushing_multi_empn_trpl_cfg", 80),
+                                        ("cloth_hanging_multi_hepi_trpl_cfg", 50), ("rope_shaping_hepi_trpl_cfg", 12)])
+def test_policy_body_matches_oracle(cfg_name, B):
+    from oracle import models as om
+    cfg = CONFIGS[cfg_name]
+    gen = torch.Generator().manual_seed(7)
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
+    torch.manual_seed(3)
+    net = G.make_policy_body(cfg)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("bias") and float(p.abs().max()) == 0:
+                p.normal_(0, 0.05)
+    net.eval()  # no calibration: identical weights on both sides
+    data = G.make_data(cfg, policy=True)
+    graph, u = data.build_data(*G.obs_args(cfg, obs, policy=True), train=False)
+    out, hidden = net.one_step(graph, u)
+    w_out = torch.randn(out.shape, generator=gen)
+    w_hid = torch.randn(hidden.shape, generator=gen)
+    ((out * w_out.cuda()).sum() + (hidden * w_hid.cuda()).sum()).backward()
+
+    og_, (sc, vec) = oracle_graph_from_obs(cfg, obs, policy=True)
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+    kw = dict(dim=cfg.ponita_dim, output_dim=cfg.output_dim, output_dim_vec=cfg.output_dim_vec)
+    o_out, o_hid = (om.hepi_forward if cfg.model == "hepi" else om.empn_forward)(sd, og_, sc, vec, **kw)
+    ((o_out * w_out).sum() + (o_hid * w_hid).sum()).backward()
+    assert G.rel(out, o_out) < TOL, G.err_report("out", out, o_out)
+    assert G.rel(hidden, o_hid) < TOL, G.err_report("hidden", hidden, o_hid)
+    bad = []
+    for k, p in net.named_parameters():
+        og = sd[k].grad
+        if og is None or float(og.abs().max()) == 0.0:
+            continue
+        if G.rel(p.grad, og) >= GTOL:
+            bad.append(G.err_report(k, p.grad, og))
+    assert not bad, "\n".join(bad)
+
+
+def test_calibration_matches_reference_semantics():
+    """First training-mode forward re-scales kernel / fiber_kernel by std ratios (conv.py:151-157) AFTER
+    using the un-calibrated weights; second forward then reproduces the fixture recorded post-calibration."""
+    from oracle import models as om
+    cfg = CONFIGS["rigid_insertion_multi_hepi_trpl_cfg"]
+    gen = torch.Generator().manual_seed(5)
+    obs = synthetic_obs(cfg, 16, gen, env_ids=torch.arange(16) * 60)
+    torch.manual_seed(11)
+    net = G.make_policy_body(cfg)
+    sd0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    net.train()
+    data = G.make_data(cfg, policy=True)
+    graph, u = data.build_data(*G.obs_args(cfg, obs, policy=True), train=True)
+    out1, _ = net.one_step(graph, u)
+    og_, (sc, vec) = oracle_graph_from_obs(cfg, obs, policy=True)
+    kw = dict(dim=cfg.ponita_dim, output_dim=cfg.output_dim, output_dim_vec=cfg.output_dim_vec)
+    o1, _ = om.hepi_forward(sd0, og_, sc, vec, **kw)
+    assert G.rel(out1, o1) < TOL, G.err_report("first forward uses un-calibrated weights", out1, o1)
+    sd1 = net.state_dict()
+    k = "processor.0.convs.<object_geometry___internal___object_geometry>.kernel.weight"
+    assert bool(sd1["processor.0.convs.<object_geometry___internal___object_geometry>.callibrated"])
+    assert not torch.allclose(sd1[k].cpu(), sd0[k])
+    # expected factor from the oracle's intermediates
+    inter = {}
+    lat = om.F.linear(om.lift(sc["object_geometry"], vec["object_geometry"], sd0["ori_grid"]), sd0["node_encoder.weight"])
+    et = ("object_geometry", "internal", "object_geometry")
+    ei = og_.edge_index_dict[et]
+    sp, oi = om.invariants(sd0["ori_grid"], og_.pos["object_geometry"][ei[0]], og_.pos["object_geometry"][ei[1]])
+    kb, fb = om.basis_mlp(sp, sd0, "basis_fn"), om.basis_mlp(oi, sd0, "fiber_basis_fn")
+    pre = "processor.0.convs.<object_geometry___internal___object_geometry>"
+    x2 = om.fiber_bundle_conv(lat, lat, ei, kb, fb, sd0, pre, intermediates=inter) - sd0[f"{pre}.bias"]
+    f1 = lat.std() / inter["x1"].std()
+    assert G.rel(sd1[k], sd0[k] * f1) < 1e-4, G.err_report("kernel calibration", sd1[k], sd0[k] * f1)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: GAE
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T", [(7, 1), (5, 31), (4, 32), (3, 33), (64, 100), (17, 200)])
+def test_gae_matches_reverse_loop(B, T):
+    from geometry_rl_b200 import ops
+    from oracle.gae import gae_reverse_loop
+    gen = torch.Generator().manual_seed(B * 1000 + T)
+    r = torch.randn(B, T, generator=gen)
+    v = torch.randn(B, T + 1, generator=gen)
+    done = torch.rand(B, T, generator=gen) < 0.1
+    done[:, -1] = True
+    term = done & (torch.rand(B, T, generator=gen) < 0.5)
+    adv, vt = ops.gae(r.cuda(), v.cuda(), done.cuda(), term.cuda(), 0.99, 0.95)
+    a_ref, vt_ref = gae_reverse_loop(r, v, done, term, 0.99, 0.95)
+    assert adv.shape == (B, T) and vt.shape == (B, T)  # output order == input order [B_env, T]
+    assert G.rel(adv, a_ref) < TOL, G.err_report("adv", adv, a_ref)
+    assert G.rel(vt, vt_ref) < TOL, G.err_report("value_target", vt, vt_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4: projection against the reference fixture (KLProjectionLayer / WassersteinProjectionLayer run
+# unmodified; ITPAL replaced by the restated fp64 solve -> KL cov parity is "unpinned")
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["kl_k6", "w2_k6", "kl_k3", "w2_k3", "kl_k12", "w2_k12"])
+def test_projection_matches_reference_fixture(key):
+    from geometry_rl_b200 import ops
+    from oracle import projection as op
+    r = load_golden("projection")[key]
+    ptype = key.split("_")[0]
+    mean = r["mean"].cuda().requires_grad_(True)
+    v = r["v"].cuda().requires_grad_(True)
+    pm, pv = ops.trpl_project(mean, v, r["q_mean"].cuda(), r["q_v"].cuda(), r["eps_mean"], r["eps_cov"], ptype)
+    assert G.rel(pm, r["proj_mean"]) < TOL, G.err_report("proj_mean", pm, r["proj_mean"])
+    assert G.rel(pv, r["proj_v"]) < TOL, G.err_report("proj_v", pv, r["proj_v"])
+    logp = op.mvn_diag_log_prob(r["action"].cuda(), pm, pv)
+    ent = op.mvn_diag_entropy(pv)
+    trl = op.trust_region_loss(mean, v, pm, pv, r["coeff"], ptype)
+    total = -(torch.exp(logp - logp.detach()) * r["adv"].cuda()).mean() - 0.005 * ent.mean() + trl
+    g_mean, g_v = torch.autograd.grad(total, (mean, v))
+    assert G.rel(g_mean, r["g_mean"]) < GTOL, G.err_report("g_mean", g_mean, r["g_mean"])
+    assert G.rel(g_v, r["g_v"]) < GTOL, G.err_report("g_v", g_v, r["g_v"])
+
+
+def test_projection_kkt_large_batch():
+    """Size-independent property at full minibatch size: projected KL_cov <= eps (1 + 1e-5), identity inside
+    the trust region, mean Mahalanobis part <= eps_mean (1 + 1e-5)."""
+    from geometry_rl_b200 import ops
+    from oracle import projection as op
+    torch.manual_seed(0)
+    B, k, em, ec = 4096, 6, 0.05, 0.0025
+    q_mean = torch.randn(B, k) * 0.3
+    q_v = (0.5 + torch.rand(B, k)) ** 2
+    s = torch.rand(B, 1)
+    mean = q_mean + torch.randn(B, k) * 0.5 * s
+    v = q_v * torch.exp(torch.randn(B, k) * 0.2 * s)
+    pm, pv = ops.trpl_project(mean.cuda(), v.cuda(), q_mean.cuda(), q_v.cuda(), em, ec, "kl")
+    pm, pv = pm.cpu().double(), pv.cpu().double()
+    mp, cp = op.gaussian_kl(pm, pv, q_mean.double(), q_v.double())
+    assert float(mp.max()) <= em * (1 + 1e-4)
+    assert float(cp.max()) <= ec * (1 + 1e-4)
+    mp0, cp0 = op.gaussian_kl(mean.double(), v.double(), q_mean.double(), q_v.double())
+    inside = cp0 <= ec * (1 - 1e-6)
+    assert bool(inside.any()) and bool((~inside).any())
+    assert torch.allclose(pv[inside], v.double()[inside], rtol=1e-6)
+    assert float((cp[~inside & (cp0 > ec * (1 + 1e-6))] - ec).abs().max()) < ec * 1e-4
