@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — policy-update throughput of the B200-native GeometryRL hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+A "step" is one minibatch iteration of examples/torchrl/train.py:259-316 on synthetic rollout frames of the
+config's graph shape: policy forward (graph features -> EMPN/HEPi/transformer -> Gaussian head), TRPL
+projection, TRPLLoss, DeepSets critic forward, both backward passes, (DP: one NCCL gradient all-reduce),
+optional grad-norm clip, two Adam steps.  Prints ONE JSON line (see the task contract): `value` = samples/s
+with minibatches resident in HBM, `e2e` = the same step fed from pinned HOST memory with the loss read back,
+`roofline` = the dominant kernel's algorithmic bytes / CUDA-event duration against MEASURED_PEAKS.json,
+`cpu_baseline` = the CPU oracle port of the same step on this box's host cores (bounded sample).
+
+`--impl reference` times that CPU port alone (the reference itself is pure Python on top of torchrl / PyG /
+ITPAL wheels that are not installable offline, so it cannot run unmodified here)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+DEFAULT_CONFIG = "rigid_pushing_multi_empn_trpl_cfg"  # BASELINE.json configs[1]: 4096 envs x 16 steps, 1 B200
+METRIC = "policy update samples/sec (policy fwd+bwd + TRPL projection + critic + Adam)"
+N_ROTATE = 8  # distinct minibatches cycled through the timed region
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--minibatch", type=int, default=0, help="samples per GPU per step (default: the config's)")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="samples per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def graph_counts(cfg, policy_data, B):
+    """Per-minibatch node / edge counts of the policy graph (for the algorithmic-bytes model)."""
+    g = policy_data.example_data
+    n_nodes = g.num_nodes
+    if cfg.model == "empn":
+        convs = [(n_nodes, n_nodes, g.homogeneous().n_edges)] * 2
+    elif cfg.model == "hepi":
+        convs = [(es.n_src, es.n_dst, es.n_edges) for es in g.edge_sets.values() if es.n_edges > 0]
+    else:
+        convs = []
+    return n_nodes, convs
+
+
+# algorithmic HBM bytes of ONE launch of each kernel (DESIGN.md "Kernels"): R = 4096 B latent row
+R = 16 * 64 * 4
+
+
+def kernel_bytes(name, shape):
+    n_src, n_dst, E = shape
+    return {
+        # basis is recomputable from 2 positions + 2 indices per edge; the materialised [E,R] write is real traffic
+        "grl_edge_basis_fwd": E * (R + 32),
+        "grl_edge_basis_bwd": E * (R + 32),
+        "grl_fbconv_edge_fwd": E * R + n_src * R + n_dst * R + E * 8,
+        "grl_fbconv_node_fwd": 3 * n_dst * R,
+        "grl_fbconv_node_bwd": 3 * n_dst * R,
+        "grl_fbconv_edge_bwd": 2 * E * R + 2 * n_src * R + n_dst * R + E * 12,
+    }.get(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the same step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_rate(cfg, sample, steps, warmup, seed=0):
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.synthetic import synthetic_obs
+    from oracle.step import OracleAgent, make_minibatch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    actor, critic, _, _, _ = learner.build_agent(cfg, "cpu", seed=seed)
+    agent = OracleAgent(cfg, actor.state_dict(), critic.state_dict())
+    gen = torch.Generator().manual_seed(1234)
+    obs = synthetic_obs(cfg, sample, gen, env_ids=torch.arange(sample) * max(1, cfg.num_envs // sample))
+    mb = make_minibatch(cfg, agent, obs, gen)
+    params = [p for p in list(agent.actor.values()) + list(agent.critic.values()) if p.is_floating_point()]
+    opt = torch.optim.Adam(params, lr=cfg.lr, eps=1e-5)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        agent.step_grads(mb)
+        if cfg.clip_grad_norm:
+            torch.nn.utils.clip_grad_norm_(params, cfg.max_grad_norm)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return sample * len(times) / total, cores, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from geometry_rl_b200.synthetic import CONFIGS
+    cfg = CONFIGS[args.config]
+    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    rate, cores, sec = cpu_step_rate(cfg, args.cpu_sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config, "minibatch_per_step": args.cpu_sample},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} update steps of {args.cpu_sample} samples (oracle/step.py, torch CPU fp32, "
+                                   f"fp64 KL dual solve instead of ITPAL)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from geometry_rl_b200 import _lib, learner
+    from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs
+    from geometry_rl_b200.smoke import to_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    dp = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        from geometry_rl_b200.parallel import DataParallel
+        dp = DataParallel()
+    torch.backends.cuda.matmul.allow_tf32 = False  # strict fp32 everywhere (parity mode)
+    torch.backends.cudnn.allow_tf32 = False
+
+    cfg = CONFIGS[args.config]
+    B = args.minibatch or cfg.mini_batch_size
+    actor, critic, projection, loss_module, adv_module = learner.build_agent(cfg, dev, seed=0)  # same init on all ranks
+    lrn = learner.Learner(cfg, actor, critic, loss_module, dp=dp)
+
+    # ---- synthetic minibatches of this rank's environments (weak scaling: B samples per GPU) -----------
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_batches = []
+    for i in range(N_ROTATE):
+        # slot j always belongs to the same env block -> the same geometry as the cached topology of slot j
+        env_ids = (torch.arange(B) * max(1, cfg.num_envs // B) + rank) % cfg.num_envs
+        obs = synthetic_obs(cfg, B, gen, env_ids=env_ids)
+        with torch.no_grad():
+            dist_ = actor.get_dist(to_device(obs, dev))  # first call also runs the one-time calibration
+            v = critic.module(*[obs[k].to(dev) for k in critic.in_keys])
+        mb = synthetic_minibatch(obs, dist_.mean, dist_.var_diag, v, gen)
+        host_batches.append({k: t.pin_memory() for k, t in mb.items()})
+    if dp is not None:  # calibration changed kernel weights from rank-local data: make replicas identical again
+        for p in list(actor.parameters()) + list(critic.parameters()):
+            dist.broadcast(p.data, 0)
+    dev_batches = [to_device(b, dev) for b in host_batches]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0].values())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dp is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dp is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    for i in range(args.warmup):
+        lrn.update(dev_batches[i % N_ROTATE])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = lrn.update(dev_batches[i % N_ROTATE])
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host minibatch -> H2D -> step -> loss scalar D2H, every step ----------------
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    s0.record()
+    loss_host = 0.0
+    for i in range(args.steps):
+        mb = {k: t.to(dev, non_blocking=True) for k, t in host_batches[i % N_ROTATE].items()}
+        out = lrn.update(mb)
+        loss_host = float(out["actor_loss"].item())  # device -> host read of the step's result
+    s1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), (time.perf_counter() - t_wall) * 1e3 if dp is None else 0.0))
+    e2e = {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": 4, "last_actor_loss": loss_host}
+
+    # ---- per-kernel CUDA-event pass (same steps, events around every C-ABI launch) ------------------------
+    roofline = None
+    if rank == 0:
+        _lib.event_timing(True)
+        for i in range(min(args.steps, 5)):
+            lrn.update(dev_batches[i % N_ROTATE])
+        torch.cuda.synchronize()
+        per_kernel = _lib.event_timing(False)  # name -> list of (ms, n_src, n_dst, n_edges)
+        tot = {k: sum(x[0] for x in v) for k, v in per_kernel.items()}
+        step_kernel_ms = sum(tot.values())
+        top = max(tot, key=tot.get)
+        peak, peak_src = measured_peaks()
+        # average over the launches of the dominant kernel: algorithmic bytes of each launch / its duration
+        ab = sum(kernel_bytes(top, x[1:]) or 0 for x in per_kernel[top])
+        dur = tot[top] * 1e-3
+        achieved = ab / dur / 1e9 if dur > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": tot[top] / len(per_kernel[top]), "launches_per_step": len(per_kernel[top]) / min(args.steps, 5),
+                    "algorithmic_bytes_per_launch": ab / len(per_kernel[top]),
+                    "share_of_kernel_time": tot[top] / step_kernel_ms,
+                    "kernel_ms_per_step": {k: round(v / min(args.steps, 5), 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, cores, sec = cpu_step_rate(cfg, args.cpu_sample, 2, 1)
+        cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"2 update steps of {args.cpu_sample} samples after 1 warm-up (oracle/step.py: torch CPU fp32 "
+                         f"restatement of the reference step, fp64 KL dual solve instead of ITPAL), {sec:.2f} s/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.config, "model": cfg.model, "minibatch_per_gpu": B, "global_minibatch": B * world,
+                       "parallelism": f"dp{world}", "l2": f"rotating {N_ROTATE} minibatches; per-step working set "
+                       f"(latents {B * 49 * 4096 / 1e6:.0f} MB each) exceeds the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dp is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,11 +127,34 @@ def ptr_any(t):
     return t.data_ptr()
 
 
-def call(name: str, *args):
-    """Invoke an ABI function on the current torch stream and raise on a non-zero return code."""
+_timing = None  # None | dict name -> list of (start_event, end_event, shape)
+
+
+def event_timing(enable: bool):
+    """bench.py's per-kernel pass: bracket every ABI launch with CUDA events on the launching stream.
+    event_timing(True) starts recording; event_timing(False) returns {name: [(ms, *shape), ...]}."""
+    global _timing
+    if enable:
+        _timing = {}
+        return None
+    rec, _timing = _timing, None
+    torch.cuda.synchronize()
+    return {k: [(a.elapsed_time(b),) + tuple(shape) for a, b, shape in v] for k, v in (rec or {}).items()}
+
+
+def call(name: str, *args, shape=(0, 0, 0)):
+    """Invoke an ABI function on the current torch stream and raise on a non-zero return code.
+    `shape` = (n_src, n_dst, n_edges) of the launch, only used to label bench.py's per-kernel timings."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
+    if _timing is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        b.record()
+        _timing.setdefault(name, []).append((a, b, shape))
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
     launch_count += 1
     check(rc, name)
 

@@ -1,0 +1,137 @@
+"""The learner side of examples/torchrl/train.py:134-146,249-316 without Hydra / collectors / logging:
+model assembly from a PathConfig (what AgentBuilder + make_ppo_models produce,
+examples/torchrl/builders/utils_algo_graph.py:208-276), the advantage phase and one minibatch update."""
+from typing import Dict, Optional
+
+import torch
+
+from .algorithms.trust_region_projections.models.policy.gnn_gaussian_policy_diag import GNNGaussianPolicyDiag
+from .algorithms.trust_region_projections.models.value.critic import BaseCritic
+from .algorithms.trust_region_projections.models.value.gnn_vf_net import GNNVFNet
+from .algorithms.trust_region_projections.objectives.operators import PolicyOperator, ValueOperator
+from .algorithms.trust_region_projections.objectives.trpl import TRPLLoss
+from .algorithms.trust_region_projections.objectives.value import GAE
+from .algorithms.trust_region_projections.projections.projection_factory import get_projection_layer
+from .synthetic import PathConfig, observation_layout, obs_keys
+
+
+def _task_module(cfg: PathConfig):
+    if cfg.task == "rigid":
+        from .modules.pyg_data import rigid_tasks_data as m
+        return m, m.RigidTasksData
+    if cfg.task == "rope":
+        from .modules.pyg_data import rope_tasks_data as m
+        return m, m.RopeTasksData
+    from .modules.pyg_data import cloth_tasks_data as m
+    return m, m.ClothTasksData
+
+
+def make_data(cfg: PathConfig, *, policy: bool):
+    """configs/algorithm/pyg_agent/data/*.yaml + the per-experiment overrides (policy: dist_as_pos,
+    output_mask_key=grippers, no full graph; critic: full_graph_obs, concat features)."""
+    dims, names = observation_layout(cfg)
+    _, D = _task_module(cfg)
+    concat = (not policy) or cfg.model == "transformer"
+    return D(observation_dim=dims, observation_names=names, full_graph_obs=not policy, dist_as_pos=policy,
+             output_mask_key="grippers" if policy else None, concat_input_vector=concat,
+             angular_velocity=cfg.angular_velocity, build_edges=policy and cfg.model != "transformer")
+
+
+def make_policy_body(cfg: PathConfig, device):
+    m, _ = _task_module(cfg)
+    NodeType, EdgeType, EdgeLevel = m.NodeType, m.EdgeType, m.EdgeLevel
+    if cfg.model == "hepi":
+        from .modules.pyg_models.hepi import HEPi
+        from .modules.pyg_models.ponita.conv import FiberBundleConv
+        # configs/algorithm/pyg_agent/model/hepi.yaml:17-48: INTERNAL at step 0, TASK + AGENT at step 1
+        codes = [[1, 0], [0, 1], [0, 1]]
+        mp = [[FiberBundleConv(64, 64, 64, groups=64, separable=True, widening_factor=4) if c else None for c in code]
+              for code in codes]
+        net = HEPi(input_dim_node=len(NodeType) + cfg.policy_aux_dim, input_dim_edge=len(EdgeType) + 4, hidden_dim=64,
+                   latent_dim=64, output_dim=cfg.output_dim, output_dim_vec=cfg.output_dim_vec, node_encoder_layers=2,
+                   edge_encoder_layers=2, node_decoder_layers=2, node_type_mapping=NodeType, edge_type_mapping=EdgeType,
+                   edge_level_mapping=EdgeLevel, message_passing=mp, num_messages=2, device=device, num_ori=16,
+                   degree=2, ponita_dim=cfg.ponita_dim, only_upper_hemisphere=cfg.only_upper_hemisphere)
+    elif cfg.model == "empn":
+        from .modules.pyg_models.ponita_gcn import PonitaGCN
+        net = PonitaGCN(input_dim_node=len(NodeType) + cfg.policy_aux_dim, output_dim=cfg.output_dim,
+                        output_dim_vec=cfg.output_dim_vec, num_layers=2, hidden_dim=64, dropout=0.0, num_ori=16,
+                        degree=2, widening_factor=4, attention=False, ponita_dim=cfg.ponita_dim)
+    else:
+        from .modules.pyg_models.transformer_vanilla import TransformerVanilla
+        net = TransformerVanilla(input_dim_node=len(NodeType) + 12, output_dim=64, num_layers=2, num_heads=2,
+                                 hidden_dim=64, dropout=0.0, concat_global=False)
+    return net.to(device)
+
+
+def policy_in_keys(cfg: PathConfig):
+    keys = obs_keys(cfg)
+    if cfg.policy_pos_is_norm:  # transformer cfg feeds the norm_* groups into the position / velocity slots
+        keys = ["norm_position_vectors" if k == "position_vectors" else
+                "norm_velocity_vectors" if k == "velocity_vectors" else k for k in keys]
+    return keys
+
+
+def build_agent(cfg: PathConfig, device, proj_type: str = "kl", seed: int = 0):
+    """-> (actor PolicyOperator, critic ValueOperator, projection, loss_module, adv_module)."""
+    torch.manual_seed(seed)
+    m, _ = _task_module(cfg)
+    body = make_policy_body(cfg, device)
+    policy = GNNGaussianPolicyDiag(gnn=body, hyper_data=make_data(cfg, policy=True),
+                                   action_dim=cfg.total_action_dim, num_actuators=cfg.num_actuators, init="orthogonal",
+                                   hidden_sizes=(64, 64), contextual_std=True, init_std=1.0, minimal_std=1e-5,
+                                   share_action_dim=True, post_fc=cfg.post_fc).to(device)
+    from .modules.pyg_models.deepsets import DeepSets
+    n_feat = len(m.NodeType) + (12 if cfg.task == "rigid" else 9)
+    vf = GNNVFNet(gnn=DeepSets(input_dim_node=n_feat, output_dim=64, hidden_dim=64, norm=["layer_norm", "layer_norm"]),
+                  hyper_data=make_data(cfg, policy=False), init="orthogonal", hidden_sizes=(64, 64))
+    torch.nn.init.orthogonal_(vf.final.weight, 0.01)  # builders/utils_algo_graph.py:195-198 (only nn.Linear)
+    vf.final.bias.data.zero_()
+    critic_net = BaseCritic(vf).to(device)
+    actor = PolicyOperator(policy, policy_in_keys(cfg))
+    critic = ValueOperator(critic_net, obs_keys(cfg))
+    projection = get_projection_layer(proj_type=proj_type, mean_bound=cfg.mean_bound, cov_bound=cfg.cov_bound,
+                                      trust_region_coeff=cfg.trust_region_coeff, scale_prec=True,
+                                      entropy_schedule=False, target_entropy=0.0, temperature=0.5, entropy_eq=False,
+                                      entropy_first=False, action_dim=cfg.total_action_dim, total_train_steps=1000,
+                                      cpu=False, dtype=torch.float32)
+    loss_module = TRPLLoss(actor, critic, projection=projection, clip_epsilon=0.2, entropy_bonus=True,
+                           entropy_coef=cfg.entropy_coef, critic_coef=cfg.critic_coef, loss_critic_type="l2",
+                           normalize_advantage=True, clip_value=cfg.clip_value)
+    adv_module = GAE(gamma=cfg.gamma, lmbda=cfg.gae_lambda, value_network=critic, average_gae=False, shifted=True)
+    return actor, critic, projection, loss_module, adv_module
+
+
+class Learner:
+    """train.py:145-146 (two Adam optimisers, eps=1e-5) + one iteration of the minibatch loop (:275-316)."""
+
+    def __init__(self, cfg: PathConfig, actor, critic, loss_module, dp=None, fused_adam: bool = True):
+        self.cfg, self.actor, self.critic, self.loss_module, self.dp = cfg, actor, critic, loss_module, dp
+        fused = fused_adam and next(actor.parameters()).is_cuda
+        self.actor_optim = torch.optim.Adam(actor.parameters(), lr=cfg.lr, eps=1e-5, fused=fused)
+        self.critic_optim = torch.optim.Adam(critic.parameters(), lr=cfg.lr, eps=1e-5, fused=fused)
+        self.num_network_updates = 0
+        if dp is not None:
+            dp.attach(loss_module)
+
+    def compute_losses(self, batch) -> Dict[str, torch.Tensor]:
+        self.loss_module._global_steps = self.num_network_updates
+        loss = self.loss_module(batch)
+        loss["actor_loss"] = loss["loss_objective"] + loss["loss_entropy"] + loss["loss_trust_region"]
+        return loss
+
+    def update(self, batch) -> Dict[str, torch.Tensor]:
+        loss = self.compute_losses(batch)
+        self.num_network_updates += 1
+        loss["actor_loss"].backward()
+        loss["loss_critic"].backward()
+        if self.dp is not None:
+            self.dp.allreduce_grads(list(self.actor.parameters()) + list(self.critic.parameters()))
+        if self.cfg.clip_grad_norm:
+            torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.cfg.max_grad_norm)
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.cfg.max_grad_norm)
+        self.actor_optim.step()
+        self.critic_optim.step()
+        self.actor_optim.zero_grad()
+        self.critic_optim.zero_grad()
+        return loss

@@ -35,7 +35,7 @@ class BaseData:
     def __init__(self, observation_dim: Dict, observation_names: Dict, full_graph_obs: bool = False,
                  dist_as_pos: bool = False, output_mask_key: Optional[str] = None, training_noise: bool = False,
                  training_noise_std: float = 1e-2, concat_input_vector: bool = True, angular_velocity: bool = True,
-                 knn_k: int = 3, knn_to_actuators_k: int = -1, **kwargs):
+                 knn_k: int = 3, knn_to_actuators_k: int = -1, build_edges: bool = True, **kwargs):
         self._output_mask_key = output_mask_key
         self.training_noise = training_noise
         self.training_noise_std = training_noise_std
@@ -48,11 +48,16 @@ class BaseData:
         self.angular_velocity = angular_velocity
         self.knn_k = knn_k
         self.knn_to_actuators_k = knn_to_actuators_k
+        # False for consumers that never read edges (DeepSets critic, transformer tokens): skips the K1 kernels
+        self.build_edges = build_edges
         if knn_to_actuators_k > 0:
             # the reference's own kNN-to-actuator branch never assigns TASK edges for rigid tasks
             # (rigid_tasks_data.py:302-312) and no shipped config selects it
             raise NotImplementedError("knn_to_actuators_k > 0 is not reachable with the shipped configs")
         self.node_type_list = self._kept_node_types()
+        # one cached topology per batch size (the reference keeps only the last one and rebuilds whenever the
+        # batch size changes, rigid_tasks_data.py:254-255; each is still "built once from the first batch seen")
+        self._placeholders: Dict[int, GraphBatch] = {}
         self._example_data: Optional[GraphBatch] = None
 
     # ---- configuration hooks ---------------------------------------------------------------------
@@ -80,7 +85,11 @@ class BaseData:
         return data, input_vector
 
     def _should_reconstruct_placeholders(self, batch_size, **ignored) -> bool:
-        return self._example_data is None or len(self._example_data) != batch_size
+        cached = self._placeholders.get(batch_size)
+        if cached is not None:
+            self._example_data = cached
+            return False
+        return True
 
     # ---- obs splitting (rigid_tasks_data.py:93-150) ---------------------------------------------------
     def _preprocess_input(self, scalars, position_vectors, velocity_vectors, norm_position_vectors,
@@ -119,7 +128,7 @@ class BaseData:
         pts = position_vectors[self.PARTICLE_TYPE]
         for et in self.EDGE_TYPES:  # insertion order INTERNAL, AGENT, TASK (rigid_tasks_data.py:285-319)
             src, _, dst = et
-            if src not in kept or dst not in kept:
+            if src not in kept or dst not in kept or not self.build_edges:
                 continue
             if et == e_int:
                 if self.INTERNAL_MODE == "knn":
@@ -142,6 +151,7 @@ class BaseData:
         g.output_mask_key = self._output_mask_key
         g.output_mask = self.output_mask(g, self._output_mask_key)
         self._example_data = g
+        self._placeholders[B] = g
 
     def _update_placeholders(self, position_vectors, norm_position_vectors, device, **ignored) -> GraphBatch:
         data = self._example_data.shallow_copy()

@@ -26,10 +26,10 @@ class DeepSets(nn.Module):
     def forward(self, data, input_vector, **kwargs):
         return self.one_step(data, input_vector, **kwargs)
 
-    def one_step(self, graph, u_dict: Dict[str, torch.Tensor], **ignored):
+    def one_step(self, graph, u_dict: Dict[str, torch.Tensor], norm_groups: int = 1, **ignored):
         B = len(graph)
         with torch.no_grad():
             x = torch.cat([u_dict[t].reshape(B, -1, u_dict[t].shape[-1]) for t in graph.node_types], dim=1)
-        x = self.mlp_inner(x)
+        x = self.mlp_inner(x, norm_groups)
         x = x.sum(dim=1)
-        return self.mlp_outer(x)
+        return self.mlp_outer(x, norm_groups)

@@ -32,21 +32,29 @@ class Linear(torch.nn.Module):
 
 
 class GraphLayerNorm(torch.nn.Module):
+    """PyG LayerNorm(mode='graph') with batch=None: ONE mean / std over the entire input tensor.
+
+    `groups` > 1 splits the leading axis into that many independent tensors (the time steps the reference
+    evaluates in a Python loop, value/gnn_vf_net.py:72-78); `stats_reduce` (data parallelism) maps the local
+    per-group (sum, sum of squares, count) to the global mean / biased std with gradients."""
+
     def __init__(self, in_channels: int, eps: float = 1e-5):
         super().__init__()
         self.in_channels, self.eps = in_channels, eps
         self.weight = torch.nn.Parameter(torch.ones(in_channels))
         self.bias = torch.nn.Parameter(torch.zeros(in_channels))
-        self.stats_reduce = None  # optional hook (sum, sumsq, count) -> global (data-parallel runs)
+        self.stats_reduce = None
 
-    def forward(self, x):
+    def forward(self, x, groups: int = 1):
+        shape = x.shape
+        xg = x.reshape(groups, -1)
         if self.stats_reduce is None:
-            x = x - x.mean()
-            out = x / (x.std(unbiased=False) + self.eps)
+            xg = xg - xg.mean(dim=1, keepdim=True)
+            out = xg / (xg.std(dim=1, unbiased=False, keepdim=True) + self.eps)
         else:
-            mean, std = self.stats_reduce(x)
-            out = (x - mean) / (std + self.eps)
-        return out * self.weight + self.bias
+            mean, std = self.stats_reduce(xg)  # [groups, 1] each
+            out = (xg - mean) / (std + self.eps)
+        return out.reshape(shape) * self.weight + self.bias
 
 
 class MLP(torch.nn.Module):
@@ -59,7 +67,8 @@ class MLP(torch.nn.Module):
         self.norms = torch.nn.ModuleList(
             [GraphLayerNorm(h) if norm is not None else torch.nn.Identity() for h in channel_list[1:-1]])
 
-    def forward(self, x):
+    def forward(self, x, norm_groups: int = 1):
         for lin, norm in zip(self.lins[:-1], self.norms):
-            x = F.relu(norm(lin(x)))
+            x = lin(x)
+            x = F.relu(norm(x, norm_groups) if isinstance(norm, GraphLayerNorm) else norm(x))
         return self.lins[-1](x)

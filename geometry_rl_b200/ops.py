@@ -182,7 +182,7 @@ class EdgeBasisFn(torch.autograd.Function):
                            pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
                            w2t=L.ptr(w2t), b2=L.ptr(b2c), basis=L.ptr(basis))
         if es.n_edges > 0:
-            L.call("grl_edge_basis_fwd", C.byref(d))
+            L.call("grl_edge_basis_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         ctx.save_for_backward(pos_src, pos_dst, w1t, b1c, w2t, b2c, _f32c(w2.detach()), ori3)
         ctx.es, ctx.dim = es, dim
         return basis
@@ -203,7 +203,7 @@ class EdgeBasisFn(torch.autograd.Function):
                            pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
                            w2t=L.ptr(w2t), b2=L.ptr(b2c), w2=L.ptr(w2), grad_basis=L.ptr(g_basis),
                            grad_partials=L.ptr(partials), n_partials=n_p)
-        L.call("grl_edge_basis_bwd", C.byref(d))
+        L.call("grl_edge_basis_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         g = _reduce(partials)
         gw1 = g[:1024].view(64, 16)[:, :14].contiguous()
         gb1 = g[1024:1088]
@@ -246,8 +246,8 @@ class FiberConvFn(torch.autograd.Function):
                           fiber_kernel=L.ptr(fk), wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
                           ln_b=L.ptr(lnb_c), w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_t=L.ptr(w2_t),
                           w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
-        L.call("grl_fbconv_edge_fwd", C.byref(d))
-        L.call("grl_fbconv_node_fwd", C.byref(d))
+        L.call("grl_fbconv_edge_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+        L.call("grl_fbconv_node_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1)
         ctx.es, ctx.homo = es, homo
         return out
@@ -274,8 +274,8 @@ class FiberConvFn(torch.autograd.Function):
                           grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=L.ptr(g_basis),
                           accumulate_grad_basis=0, node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
-        L.call("grl_fbconv_node_bwd", C.byref(d))
-        L.call("grl_fbconv_edge_bwd", C.byref(d))
+        L.call("grl_fbconv_node_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+        L.call("grl_fbconv_edge_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         g = _reduce(node_part)
         o = 0
         gw1 = g[o:o + 256 * 64].view(256, 64); o += 256 * 64
@@ -303,7 +303,7 @@ def aggregate_messages(x_src, basis, wk, es: EdgeSet) -> torch.Tensor:
     d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
                       edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), x_src=L.ptr(x_src), basis=L.ptr(basis),
                       wk_t=L.ptr(wk_t), x1=L.ptr(x1))
-    L.call("grl_fbconv_edge_fwd", C.byref(d))
+    L.call("grl_fbconv_edge_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
     return x1
 
 

@@ -1,0 +1,111 @@
+"""Data parallelism over minibatch samples (one process per GPU, torch.distributed; NCCL on the box, gloo
+in CPU tests).  The reference is single-process; to stay results-equivalent to it, every
+cross-sample reduction of the update step is made global here:
+
+  * advantage mean / unbiased std                       (objectives/trpl.py:286-289)
+  * loss means (local sum / global count) + ONE summed gradient bucket per network
+  * PyG LayerNorm(mode='graph') statistics of the DeepSets critic, forward and backward
+  * ESS logsumexp and the logged metric means / maxima  (trpl.py:294-300, base_projection_layer.py:355-369)
+
+Equal shard sizes are required (every rank holds B_global / world_size samples)."""
+from typing import Dict, Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+class _GraphNormStats(torch.autograd.Function):
+    """(mean, biased std) of the GLOBAL tensor per group from local rows; gradients flow back to local rows."""
+
+    @staticmethod
+    def forward(ctx, xg, dp):
+        n_local = xg.shape[1]
+        s = torch.stack([xg.sum(1), (xg * xg).sum(1)], 0)  # [2, G]
+        dp.all_reduce(s)
+        n = n_local * dp.world_size
+        mean = s[0] / n
+        var = (s[1] / n - mean * mean).clamp_min(0)
+        std = var.sqrt()
+        ctx.save_for_backward(xg, mean, std)
+        ctx.dp, ctx.n = dp, n
+        return mean[:, None], std[:, None]
+
+    @staticmethod
+    def backward(ctx, g_mean, g_std):
+        xg, mean, std = ctx.saved_tensors
+        g = torch.stack([g_mean[:, 0], g_std[:, 0]], 0).contiguous()
+        ctx.dp.all_reduce(g)  # every rank's loss depends on the shared statistics
+        gm, gs = g[0][:, None], g[1][:, None]
+        gx = gm / ctx.n + gs * (xg - mean[:, None]) / (ctx.n * std[:, None])
+        return gx, None
+
+
+class DataParallel:
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.collectives = 0
+
+    def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+        dist.all_reduce(t, op=op, group=self.group)
+        self.collectives += 1
+        return t
+
+    # ---- forward-side statistics ---------------------------------------------------------------------
+    def mean_std_unbiased(self, x: torch.Tensor):
+        x = x.detach().float()
+        s = torch.stack([x.sum(), (x * x).sum()])
+        self.all_reduce(s)
+        n = x.numel() * self.world_size
+        mean = s[0] / n
+        var = (s[1] - n * mean * mean) / (n - 1)
+        return mean, var.clamp_min(0).sqrt()
+
+    def logsumexp(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.all_reduce(x.max().clone(), dist.ReduceOp.MAX)
+        s = self.all_reduce((x - m).exp().sum())
+        return m + s.log()
+
+    def graph_norm_stats(self, xg: torch.Tensor):
+        return _GraphNormStats.apply(xg, self)
+
+    def aggregate_metrics(self, per_sample: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        keys = list(per_sample.keys())
+        sums = torch.stack([per_sample[k].sum() for k in keys])
+        maxs = torch.stack([per_sample[k].max() for k in keys])
+        self.all_reduce(sums)
+        self.all_reduce(maxs, dist.ReduceOp.MAX)
+        n = per_sample[keys[0]].numel() * self.world_size
+        out = {}
+        for i, k in enumerate(keys):
+            out[k] = sums[i] / n
+            out[f"{k}_max"] = maxs[i]
+        return out
+
+    # ---- gradient exchange -----------------------------------------------------------------------------
+    def allreduce_grads(self, params: Iterable[torch.nn.Parameter]):
+        """ONE flat fp32 bucket, summed (losses already divide by the global count)."""
+        ps: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        for p in ps:
+            if p.grad is None:  # e.g. the AGENT conv when A == 1: keep the bucket layout identical on all ranks
+                p.grad = torch.zeros_like(p)
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        self.all_reduce(flat)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
+        return flat.numel()
+
+    def attach(self, loss_module):
+        """Install the global-statistics hooks on a TRPLLoss and on every GraphLayerNorm of its critic."""
+        from .modules.pyg_models.pyg_compat import GraphLayerNorm
+        loss_module.dp = self
+        for m in loss_module.critic_network.modules():
+            if isinstance(m, GraphLayerNorm):
+                m.stats_reduce = self.graph_norm_stats
+        return loss_module

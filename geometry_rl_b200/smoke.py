@@ -1,0 +1,60 @@
+"""smoke(): one small HEPi update step + GAE on cuda:0, checked against the CPU oracle (the oracle is the
+checker here, never the thing run: every product tensor below comes out of libgrl_b200 / torch CUDA)."""
+import torch
+
+
+def to_device(batch, device):
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def run_smoke(cfg_name: str = "rigid_insertion_multi_hepi_trpl_cfg", B: int = 32, verbose: bool = True):
+    from . import learner
+    from .synthetic import CONFIGS, synthetic_obs, synthetic_rollout
+    from oracle.step import OracleAgent, make_minibatch
+
+    dev = torch.device("cuda:0")
+    cfg = CONFIGS[cfg_name]
+    actor, critic, projection, loss_module, adv_module = learner.build_agent(cfg, dev, seed=0)
+    gen = torch.Generator().manual_seed(1234)
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
+    # warm-up forward in training mode = the one-time calibration of train.py:72-74
+    with torch.no_grad():
+        actor.get_dist(to_device(obs, dev))
+    oracle = OracleAgent(cfg, actor.state_dict(), critic.state_dict())
+    mb = make_minibatch(cfg, oracle, obs, gen)
+    ref, ga, gc = oracle.step_grads(mb)
+
+    lrn = learner.Learner(cfg, actor, critic, loss_module)
+    out = lrn.compute_losses(to_device(mb, dev))
+    out["actor_loss"].backward()
+    out["loss_critic"].backward()
+    worst = 0.0
+    for k in ("loss_objective", "loss_trust_region", "loss_entropy", "loss_critic", "ESS", "kl"):
+        err = abs(float(out[k]) - float(ref[k])) / (abs(float(ref[k])) + 1e-6)
+        worst = max(worst, err)
+        assert err < 1e-4, f"smoke: {k} {float(out[k])} vs oracle {float(ref[k])}"
+    pol = dict(actor.get_submodule("0").module.named_parameters())
+    for k, g in ga.items():
+        if g is None or float(g.abs().max()) == 0.0:
+            continue
+        err = float((pol[k].grad.cpu() - g).abs().max()) / float(g.abs().max())
+        worst = max(worst, err)
+        assert err < 1e-4, f"smoke: grad {k} rel err {err}"
+    lrn.actor_optim.step()
+    lrn.critic_optim.step()
+
+    # GAE on a tiny rollout: batched-over-time critic + warp-scan kernel vs the per-step loop + reverse loop
+    roll = synthetic_rollout(cfg, gen, num_envs=6, rollout_len=9)
+    oracle2 = OracleAgent(cfg, actor.state_dict(), critic.state_dict())
+    a_ref, vt_ref, _ = oracle2.gae(roll)
+    keys = critic.in_keys
+    td = {k: roll[k][:, :-1].to(dev) for k in keys}
+    td["next"] = {k: roll[k][:, 1:].to(dev) for k in keys}
+    td["next"].update({"reward": roll["reward"].unsqueeze(-1).to(dev), "done": roll["done"].unsqueeze(-1).to(dev),
+                       "terminated": roll["terminated"].unsqueeze(-1).to(dev)})
+    adv_module(td)
+    err = float((td["advantage"][..., 0].cpu() - a_ref).abs().max()) / float(a_ref.abs().max())
+    assert err < 1e-4, f"smoke: GAE rel err {err}"
+    torch.cuda.synchronize()
+    if verbose:
+        print(f"smoke ok: {cfg_name} B={B} worst rel err {max(worst, err):.2e}")

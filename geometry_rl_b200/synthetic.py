@@ -228,3 +228,30 @@ def synthetic_rollout(cfg: PathConfig, generator: torch.Generator, num_envs: Opt
     out["done"] = done
     out["terminated"] = torch.zeros(B, T, dtype=torch.bool)
     return out
+
+
+LOG_2PI = 1.8378770664093453
+
+
+def synthetic_minibatch(obs: Dict[str, torch.Tensor], mean: torch.Tensor, var: torch.Tensor, value: torch.Tensor,
+                        generator: torch.Generator, drift: float = 0.35) -> Dict[str, torch.Tensor]:
+    """Minibatch content `TRPLLoss.forward` consumes, CPU tensors.  The old distribution is
+    the current policy output (mean, var) pushed away by up to `drift` old-std units so that both branches of
+    the mean and covariance projections are exercised (as after a few Adam steps in a real run); action ~ old
+    distribution; advantage / value_target / state_value are random around the critic output."""
+    mean, var, value = mean.detach().cpu(), var.detach().cpu(), value.detach().cpu()
+    B, k = mean.shape
+    g = generator
+    s = torch.rand(B, 1, generator=g)
+    q_mean = mean + torch.randn(B, k, generator=g) * drift * s * var.sqrt()
+    q_var = var * torch.exp(torch.randn(B, k, generator=g) * 0.12 * s)
+    action = q_mean + torch.randn(B, k, generator=g) * q_var.sqrt()
+    logp = -0.5 * (((action - q_mean) ** 2 / q_var).sum(-1) + k * LOG_2PI + q_var.log().sum(-1))
+    batch = {k_: v for k_, v in obs.items()}
+    batch.update({
+        "action": action, "loc": q_mean, "covariance_matrix": torch.diag_embed(q_var), "sample_log_prob": logp,
+        "advantage": torch.randn(B, 1, generator=g),
+        "state_value": value + 0.1 * torch.randn(B, 1, generator=g),
+        "value_target": value + 0.5 * torch.randn(B, 1, generator=g),
+    })
+    return {k_: (t.float().contiguous() if torch.is_tensor(t) and t.is_floating_point() else t) for k_, t in batch.items()}

@@ -196,7 +196,7 @@ def golden_transformer(B, seed, tag):
     x_tokens = torch.cat([u[nt].reshape(B, -1, u[nt].shape[-1]) for nt in graph.node_types], dim=1)
     _save({"B": B, "obs": obs, "state_dict": _sd(net), "tokens": x_tokens.clone(), "out": out.detach(), "w": w,
                 "output_mask": (graph.output_mask.start, graph.output_mask.stop), "grads": _grads(net)},
-               os.path.join(OUT, f"{tag}.pt"))
+          tag)
     print(tag, "out", tuple(out.shape))
 
 
@@ -319,7 +319,7 @@ def golden_equivariance(tag):
     osc = sphere_to_scalar(osc)
     ovec = sphere_to_vec(ovec.reshape(-1, num_ori, 1), model.ori_grid).reshape(bs, nn_, 1, dim)
     torch.save({"state_dict": _sd(model), "x": x.detach(), "pos": pos.reshape(bs * nn_, dim), "edge_index": ei,
-                "out_scalar": osc.detach(), "out_vec": ovec.detach(), "R": R}, tag)
+                "out_scalar": osc.detach(), "out_vec": ovec.detach(), "R": R}, os.path.join(OUT, f"{tag}.pt"))
     print(tag, "max scalar spread", float((osc - osc[:1]).abs().max()))
 
 

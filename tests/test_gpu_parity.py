@@ -240,7 +240,10 @@ def test_projection_matches_reference_fixture(key):
     total = -(torch.exp(logp - logp.detach()) * r["adv"].cuda()).mean() - 0.005 * ent.mean() + trl
     g_mean, g_v = torch.autograd.grad(total, (mean, v))
     assert G.rel(g_mean, r["g_mean"]) < GTOL, G.err_report("g_mean", g_mean, r["g_mean"])
-    assert G.rel(g_v, r["g_v"]) < GTOL, G.err_report("g_v", g_v, r["g_v"])
+    # W2: trace(I + S_q^-1 S^2 S_q^-1 - 2 S_q^-1 S) cancels catastrophically in fp32, so the reference's own
+    # fp32 gradient sits up to 4.1e-5 away from an fp64 evaluation of the same formulas
+    # (tests/test_oracle_golden.py::test_w2_grad_noise_floor pins that number) -> 1e-4 for W2 only.
+    assert G.rel(g_v, r["g_v"]) < (1e-4 if ptype == "w2" else GTOL), G.err_report("g_v", g_v, r["g_v"])
 
 
 def test_projection_kkt_large_batch():

@@ -1,0 +1,141 @@
+"""GPU parity of the whole update step (`-m gpu`): graph features -> policy -> head -> TRPL projection ->
+TRPLLoss -> critic -> both backward passes, and of the advantage phase (batched-over-time critic + GAE
+kernel), against the CPU oracle (oracle/step.py) on the same seeded synthetic inputs.
+Tolerances: losses 1e-5 relative; gradients 5e-5 relative to each tensor's max (fp32 accumulations over
+B*N*16 rows in a different order than torch's CPU kernels); W2 gradients 1e-4 (the reference's own fp32
+result is that far from an fp64 evaluation, see tests/test_oracle_golden.py::test_w2_grad_noise_floor)."""
+import pytest
+import torch
+
+from geometry_rl_b200.synthetic import CONFIGS, synthetic_obs, synthetic_rollout
+from tests.helpers import load_golden
+from tests import gpu_helpers as G
+
+pytestmark = pytest.mark.gpu
+
+SIZES = {"rigid_insertion_multi_hepi_trpl_cfg": 48, "rigid_pushing_multi_empn_trpl_cfg": 40,
+         "cloth_hanging_multi_hepi_trpl_cfg": 24, "rope_shaping_hepi_trpl_cfg": 6,
+         "rigid_insertion_two_agents_multi_transformer_trpl_cfg": 16}
+
+
+def _setup(cfg_name, proj_type="kl", seed=0):
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.smoke import to_device
+    from oracle.step import OracleAgent, make_minibatch
+    cfg = CONFIGS[cfg_name]
+    B = SIZES[cfg_name]
+    actor, critic, projection, loss_module, adv_module = learner.build_agent(cfg, G.dev(), proj_type=proj_type, seed=seed)
+    gen = torch.Generator().manual_seed(99 + seed)
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
+    with torch.no_grad():  # one-time calibration (train.py:72-74) before the weights are mirrored
+        actor.get_dist(to_device(obs, G.dev()))
+        for n, p in actor.named_parameters():  # zero-initialised biases would hide bias-gradient bugs
+            if n.endswith("bias") and float(p.abs().max()) == 0:
+                p.normal_(0, 0.05)
+    oracle = OracleAgent(cfg, actor.state_dict(), critic.state_dict(), proj_type=proj_type)
+    mb = make_minibatch(cfg, oracle, obs, gen)
+    return cfg, actor, critic, loss_module, adv_module, oracle, mb, gen
+
+
+@pytest.mark.parametrize("cfg_name", list(SIZES.keys()))
+@pytest.mark.parametrize("proj_type", ["kl", "w2"])
+def test_update_step_matches_oracle(cfg_name, proj_type):
+    if proj_type == "w2" and cfg_name not in ("rigid_insertion_multi_hepi_trpl_cfg", "cloth_hanging_multi_hepi_trpl_cfg"):
+        pytest.skip("W2 covered on two configs")
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.smoke import to_device
+    cfg, actor, critic, loss_module, _, oracle, mb, _ = _setup(cfg_name, proj_type)
+    ref, ga, gc = oracle.step_grads(mb)
+    lrn = learner.Learner(cfg, actor, critic, loss_module)
+    out = lrn.compute_losses(to_device(mb, G.dev()))
+    out["actor_loss"].backward()
+    out["loss_critic"].backward()
+    bad = []
+    for k in ("loss_objective", "loss_trust_region", "loss_entropy", "loss_critic", "ESS", "kl", "constraint",
+              "mean_constraint", "mean_constraint_max", "cov_constraint", "cov_constraint_max", "entropy", "entropy_diff"):
+        a, b = float(out[k]), float(ref[k])
+        if abs(a - b) > 1e-5 * abs(b) + 2e-7:
+            bad.append(f"{k}: {a} vs {b}")
+    gtol = 1e-4 if proj_type == "w2" else 5e-5
+    pol = dict(actor.get_submodule("0").module.named_parameters())
+    n_checked = 0
+    for k, g in ga.items():
+        if g is None or float(g.abs().max()) == 0.0:
+            continue
+        if pol[k].grad is None:
+            bad.append(f"{k}: missing grad")
+        elif G.rel(pol[k].grad, g) >= gtol:
+            bad.append(G.err_report(k, pol[k].grad, g))
+        n_checked += 1
+    vf = dict(critic.module._network1.named_parameters())
+    for k, g in gc.items():
+        if G.rel(vf[k].grad, g) >= 5e-5:
+            bad.append(G.err_report("critic " + k, vf[k].grad, g))
+        n_checked += 1
+    assert n_checked >= 30
+    assert not bad, "\n".join(bad)
+
+
+def test_gaussian_head_matches_reference_fixture():
+    from geometry_rl_b200.algorithms.trust_region_projections.models.policy.gnn_gaussian_policy_diag import (
+        GNNGaussianPolicyDiag)
+    rec = load_golden("gaussian_head")
+    for key, r in rec.items():
+        class _G(torch.nn.Module):
+            device = "cuda"
+
+            def one_step(self, data, iv):
+                h = r["hidden"].cuda()
+                return h if r["post_fc"] else (r["mean_in"].cuda(), h)
+
+        class _D:
+            def build_data(self, *a, **k):
+                return None, None
+
+        pol = GNNGaussianPolicyDiag(gnn=_G(), hyper_data=_D(), action_dim=r["action_dim"] * r["A"], num_actuators=r["A"],
+                                    init="orthogonal", hidden_sizes=(64, 64), contextual_std=True, init_std=1.0,
+                                    minimal_std=1e-5, share_action_dim=True, post_fc=r["post_fc"]).cuda()
+        missing = pol.load_state_dict({k: v for k, v in r["state_dict"].items()}, strict=True)
+        loc, cov = pol(torch.zeros(r["B"], 1, device="cuda"))
+        assert cov.shape == r["cov"].shape
+        assert G.rel(loc, r["loc"]) < 1e-6, key
+        assert G.rel(cov, r["cov"]) < 1e-6, key
+
+
+@pytest.mark.parametrize("cfg_name", ["rigid_insertion_multi_hepi_trpl_cfg", "rope_shaping_hepi_trpl_cfg",
+                                      "cloth_hanging_multi_hepi_trpl_cfg"])
+def test_advantage_phase_matches_oracle(cfg_name):
+    """adv_module(td[B_env,T]): ONE batched critic call over T+1 steps (per-step LayerNorm statistics kept) +
+    grl_gae_scan == the reference's per-step critic loop + reverse GAE loop."""
+    cfg, actor, critic, loss_module, adv_module, oracle, _, gen = _setup(cfg_name)
+    Benv, T = 5, 11
+    roll = synthetic_rollout(cfg, gen, num_envs=Benv, rollout_len=T)
+    a_ref, vt_ref, v_ref = oracle.gae(roll)
+    keys = critic.in_keys
+    td = {k: roll[k][:, :-1].cuda() for k in keys}
+    td["next"] = {k: roll[k][:, 1:].cuda() for k in keys}
+    td["next"].update({"reward": roll["reward"].unsqueeze(-1).cuda(), "done": roll["done"].unsqueeze(-1).cuda(),
+                       "terminated": roll["terminated"].unsqueeze(-1).cuda()})
+    adv_module(td)
+    assert td["advantage"].shape == (Benv, T, 1) and td["value_target"].shape == (Benv, T, 1)
+    assert G.rel(td["state_value"][..., 0], v_ref[:, :-1]) < 2e-5, G.err_report("value", td["state_value"][..., 0], v_ref[:, :-1])
+    assert G.rel(td["advantage"][..., 0], a_ref) < 2e-5, G.err_report("adv", td["advantage"][..., 0], a_ref)
+    assert G.rel(td["value_target"][..., 0], vt_ref) < 2e-5
+
+
+def test_learner_update_changes_parameters_and_is_deterministic():
+    """Two learners from the same seed fed the same minibatch end with bit-identical parameters
+    (deterministic segmented sums and fixed-order partial reductions: no atomics anywhere)."""
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.smoke import to_device
+    res = []
+    for _ in range(2):
+        cfg, actor, critic, loss_module, _, _, mb, _ = _setup("rigid_insertion_multi_hepi_trpl_cfg", seed=3)
+        lrn = learner.Learner(cfg, actor, critic, loss_module)
+        before = torch.cat([p.detach().reshape(-1).clone() for p in actor.parameters()])
+        for _ in range(2):
+            lrn.update(to_device(mb, G.dev()))
+        after = torch.cat([p.detach().reshape(-1) for p in actor.parameters()])
+        assert float((after - before).abs().max()) > 0
+        res.append(after.clone())
+    assert torch.equal(res[0], res[1])
