@@ -35,7 +35,7 @@ def run_smoke(cfg_name: str = "rigid_insertion_multi_hepi_trpl_cfg", B: int = 32
         assert err < 1e-4, f"smoke: {k} {float(out[k])} vs oracle {float(ref[k])}"
     pol = dict(actor.get_submodule("0").module.named_parameters())
     for k, g in ga.items():
-        if g is None or float(g.abs().max()) == 0.0:
+        if k not in pol or g is None or float(g.abs().max()) == 0.0:  # buffers (ori_grid) are not parameters
             continue
         err = float((pol[k].grad.cpu() - g).abs().max()) / float(g.abs().max())
         worst = max(worst, err)

@@ -60,7 +60,7 @@ def test_update_step_matches_oracle(cfg_name, proj_type):
     pol = dict(actor.get_submodule("0").module.named_parameters())
     n_checked = 0
     for k, g in ga.items():
-        if g is None or float(g.abs().max()) == 0.0:
+        if k not in pol or g is None or float(g.abs().max()) == 0.0:  # buffers (ori_grid) are not parameters
             continue
         if pol[k].grad is None:
             bad.append(f"{k}: missing grad")
