@@ -101,19 +101,6 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def graph_counts(cfg, policy_data, B):
-    """Per-minibatch node / edge counts of the policy graph (for the algorithmic-bytes model)."""
-    g = policy_data.example_data
-    n_nodes = g.num_nodes
-    if cfg.model == "empn":
-        convs = [(n_nodes, n_nodes, g.homogeneous().n_edges)] * 2
-    elif cfg.model == "hepi":
-        convs = [(es.n_src, es.n_dst, es.n_edges) for es in g.edge_sets.values() if es.n_edges > 0]
-    else:
-        convs = []
-    return n_nodes, convs
-
-
 # algorithmic HBM bytes of ONE launch of each kernel (DESIGN.md "Kernels"): R = 4096 B latent row
 R = 16 * 64 * 4
 
@@ -253,11 +240,13 @@ def run_ours(args):
         sampler.start()
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed steps
     e0.record()
     for i in range(args.steps):
         out = lrn.update(dev_batches[i % N_ROTATE])
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     launches = _lib.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1))

@@ -38,7 +38,7 @@ class GraphBatch:
         self.output_mask_key: Optional[str] = None
         self.output_mask: slice = slice(None)
         self.homo_batch = None
-        self._homo: Optional[ops.EdgeSet] = None
+        self._homo_cache: Dict[str, ops.EdgeSet] = {}  # shared by every shallow copy of this topology
 
     # -- HeteroData-like surface ---------------------------------------------------------------
     def __len__(self):
@@ -85,7 +85,7 @@ class GraphBatch:
         """All edge types merged into one graph whose nodes are the node types concatenated per graph
         (node_types order); per graph the edges keep edge-type insertion order, as to_homogeneous()
         yields them, so the segmented sums see the same edge order as the reference."""
-        if self._homo is None:
+        if "homo" not in self._homo_cache:
             B, dev = self.num_graphs, self.device
             n_tot = sum(self.nodes_per_graph.values())
             offs = self.node_offsets
@@ -108,5 +108,5 @@ class GraphBatch:
                     coo[0, dest] = g * n_tot + offs[src] + ls
                     coo[1, dest] = g * n_tot + offs[dst] + ld
                 before = before + cnt
-            self._homo = ops.build_edge_set(coo[:, :E], homo_ptr, B, n_tot, n_tot)
-        return self._homo
+            self._homo_cache["homo"] = ops.build_edge_set(coo[:, :E], homo_ptr, B, n_tot, n_tot)
+        return self._homo_cache["homo"]

@@ -1,0 +1,79 @@
+"""CPU: the C-ABI library loads, exports every symbol include/grl_b200.h declares, and the ctypes mirror of the
+descriptor structs has the C compiler's sizes / field offsets.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "grl_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(grl_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from geometry_rl_b200.csrc import build as b
+    b.build()
+    from geometry_rl_b200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    handle = lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in grl_b200.h but not exported"
+        assert name in lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert handle.grl_abi_version() == 1
+    assert handle.grl_last_error() is not None
+
+
+def test_struct_layouts_match_the_c_compiler(lib):
+    structs = {"GrlEmbedDesc": lib.GrlEmbedDesc, "GrlBasisDesc": lib.GrlBasisDesc, "GrlConvDesc": lib.GrlConvDesc,
+               "GrlProjDesc": lib.GrlProjDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["return 0; }"]
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(src, "w").write("\n".join(lines))
+        subprocess.run(["gcc", src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    c_layout = dict(l.split() for l in out.strip().splitlines())
+    for name, cls in structs.items():
+        assert int(c_layout[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(c_layout[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
+
+
+def test_product_has_no_cpu_path():
+    import torch
+    from geometry_rl_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.gae(torch.zeros(2, 3), torch.zeros(2, 4), torch.zeros(2, 3, dtype=torch.bool),
+                torch.zeros(2, 3, dtype=torch.bool), 0.99, 0.95)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "geometry_rl_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py") and f != "smoke.py":  # smoke.py is __graft_entry__.smoke()'s checker
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders

@@ -1,0 +1,126 @@
+"""CPU, world_size 2, gloo: the data-parallel host logic (geometry_rl_b200/parallel.py).  A minibatch sharded
+over two ranks must give the single-process statistics, critic loss and gradients.  The CUDA
+kernels are not involved: the DeepSets critic and the reduction helpers are torch code."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _critic(seed=0):
+    from geometry_rl_b200.modules.pyg_models.deepsets import DeepSets
+    torch.manual_seed(seed)
+    net = DeepSets(input_dim_node=15, output_dim=64, hidden_dim=64, norm=["layer_norm", "layer_norm"])
+    final = torch.nn.Linear(64, 1)
+    return net, final
+
+
+class _G:
+    node_types = ["a"]
+
+    def __init__(self, B):
+        self.B = B
+
+    def __len__(self):
+        return self.B
+
+
+def _critic_loss(net, final, x, target, old_v, mean_fn, groups=1):
+    v = final(net.one_step(_G(x.shape[0]), {"a": x.reshape(-1, x.shape[-1])}, norm_groups=groups))
+    l = (target - v).pow(2)
+    v_clip = old_v + (v - old_v).clamp(-0.2, 0.2)
+    return mean_fn(0.5 * torch.max(l, (target - v_clip).pow(2)))
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from geometry_rl_b200.modules.pyg_models.pyg_compat import GraphLayerNorm
+        from geometry_rl_b200.parallel import DataParallel
+        dp = DataParallel()
+        g = torch.Generator().manual_seed(5)
+        B, N = 8, 7
+        x = torch.randn(B, N, 15, generator=g)
+        target, old_v = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g)
+        adv = torch.randn(B, 1, generator=g) * 3 + 1
+        lw = torch.randn(B, generator=g)
+        sl = slice(rank * B // world, (rank + 1) * B // world)
+
+        # statistics
+        m, s = dp.mean_std_unbiased(adv[sl])
+        lse = dp.logsumexp(lw[sl])
+        # critic: sharded loss with global LayerNorm statistics + summed gradients
+        net, final = _critic()
+        for mod in net.modules():
+            if isinstance(mod, GraphLayerNorm):
+                mod.stats_reduce = dp.graph_norm_stats
+        loss = _critic_loss(net, final, x[sl], target[sl], old_v[sl], lambda t: t.sum() / (t.numel() * world))
+        loss.backward()
+        params = list(net.parameters()) + list(final.parameters())
+        n = dp.allreduce_grads(params)
+        loss_g = loss.detach().clone()
+        dist.all_reduce(loss_g)
+        # per-sample metrics
+        agg = dp.aggregate_metrics({"kl": lw[sl].abs()})
+        if rank == 0:
+            torch.save({"mean": m, "std": s, "lse": lse, "loss": loss_g, "grads": [p.grad.clone() for p in params],
+                        "n": n, "kl": agg["kl"], "kl_max": agg["kl_max"]}, out_path)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_step_equals_single_process(tmp_path):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out_path = str(tmp_path / "rank0.pt")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out_path)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    res = torch.load(out_path, weights_only=True)
+
+    g = torch.Generator().manual_seed(5)
+    B, N = 8, 7
+    x = torch.randn(B, N, 15, generator=g)
+    target, old_v = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g)
+    adv = torch.randn(B, 1, generator=g) * 3 + 1
+    lw = torch.randn(B, generator=g)
+    assert torch.allclose(res["mean"], adv.mean(), atol=1e-6)
+    assert torch.allclose(res["std"], adv.std(), atol=1e-5)
+    assert torch.allclose(res["lse"], lw.logsumexp(0), atol=1e-6)
+    assert torch.allclose(res["kl"], lw.abs().mean(), atol=1e-6) and torch.allclose(res["kl_max"], lw.abs().max())
+    net, final = _critic()
+    loss = _critic_loss(net, final, x, target, old_v, lambda t: t.mean())
+    loss.backward()
+    params = list(net.parameters()) + list(final.parameters())
+    assert res["n"] == sum(p.numel() for p in params)
+    assert torch.allclose(res["loss"], loss.detach(), rtol=1e-5, atol=1e-7)
+    for a, p in zip(res["grads"], params):
+        assert torch.allclose(a, p.grad, rtol=2e-4, atol=1e-7), float((a - p.grad).abs().max())
+
+
+def test_grouped_graph_layer_norm_equals_per_step_loop():
+    """GNNVFNet batches the T+1 critic calls; GraphLayerNorm(groups=T+1) keeps the loop's per-step statistics."""
+    net, final = _critic(1)
+    g = torch.Generator().manual_seed(2)
+    T, B, N = 4, 3, 5
+    x = torch.randn(T, B, N, 15, generator=g) * torch.arange(1, T + 1).view(T, 1, 1, 1)
+    loop = torch.stack([net.one_step(_G(B), {"a": x[t].reshape(-1, 15)}) for t in range(T)])
+    batched = net.one_step(_G(T * B), {"a": x.reshape(-1, 15)}, norm_groups=T).reshape(T, B, -1)
+    assert torch.allclose(loop, batched, rtol=1e-5, atol=1e-6)
+    assert not torch.allclose(loop, net.one_step(_G(T * B), {"a": x.reshape(-1, 15)}).reshape(T, B, -1), atol=1e-3)
