@@ -270,11 +270,13 @@ def run_ours(args):
 
     # ---- per-kernel CUDA-event pass (same steps, events around every C-ABI launch) ------------------------
     roofline = None
+    n_prof = min(args.steps, 5)
     if rank == 0:
         _lib.event_timing(True)
-        for i in range(min(args.steps, 5)):
-            lrn.update(dev_batches[i % N_ROTATE])
-        torch.cuda.synchronize()
+    for i in range(n_prof):  # every rank runs the steps (they contain collectives); only rank 0 records events
+        lrn.update(dev_batches[i % N_ROTATE])
+    torch.cuda.synchronize()
+    if rank == 0:
         per_kernel = _lib.event_timing(False)  # name -> list of (ms, n_src, n_dst, n_edges)
         tot = {k: sum(x[0] for x in v) for k, v in per_kernel.items()}
         step_kernel_ms = sum(tot.values())
@@ -286,10 +288,10 @@ def run_ours(args):
         achieved = ab / dur / 1e9 if dur > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": tot[top] / len(per_kernel[top]), "launches_per_step": len(per_kernel[top]) / min(args.steps, 5),
+                    "avg_launch_ms": tot[top] / len(per_kernel[top]), "launches_per_step": len(per_kernel[top]) / n_prof,
                     "algorithmic_bytes_per_launch": ab / len(per_kernel[top]),
                     "share_of_kernel_time": tot[top] / step_kernel_ms,
-                    "kernel_ms_per_step": {k: round(v / min(args.steps, 5), 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+                    "kernel_ms_per_step": {k: round(v / n_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

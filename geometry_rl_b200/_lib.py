@@ -40,7 +40,7 @@ class GrlConvDesc(C.Structure):
                 ("w2_c", _fp), ("b2", _fp), ("x1", _fp), ("out", _fp), ("accumulate_out", _i32),
                 ("grad_out", _fp), ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp),
                 ("grad_basis", _fp), ("accumulate_grad_basis", _i32), ("node_grad_partials", _fp),
-                ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32)]
+                ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp)]
 
 
 class GrlProjDesc(C.Structure):
@@ -67,10 +67,13 @@ SIGNATURES = {
     "grl_fbconv_node_fwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_node_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_edge_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_fbconv_node_fwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),
     "grl_trpl_fwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),
     "grl_trpl_bwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),
+    "grl_tc_selftest_gemm": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _fp]),
+    "grl_tc_debug_mma": (C.c_int, [_fp, C.c_int, _fp, C.c_int, _fp, C.c_int, C.c_int] + [C.c_uint32] * 8 + [_fp]),
 }
 
 _lib = None

@@ -1,0 +1,150 @@
+// tcgen05 / TMEM / mbarrier building blocks (sm_100a inline PTX) for the bf16 tensor-core path.
+//
+// Operand staging convention used by every tensor-core kernel in this library (no TMA, no swizzle: the A
+// operands are PRODUCED by threads — gathered rows, LayerNorm / GELU outputs — so they are written straight
+// into the layout the MMA reads):
+//   a K-major operand tile [R rows][K elements] of bf16 lives in shared memory as [K/8 chunks][R rows][8 bf16]
+//   i.e. 16-byte "core rows", 8 consecutive rows = one 128-byte core matrix,
+//        SBO (stride between 8-row groups)        = 128 B
+//        LBO (stride between the 16-byte K chunks) = R * 16 B
+//   One tcgen05.mma (kind::f16) consumes K = 16 (two chunks); the k-th step starts at base + k * 2 * LBO.
+// Accumulators: M = 128 rows <-> the 128 TMEM lanes, one fp32 column per output column.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace grl {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// ---- proxy / tcgen05 fences ---------------------------------------------------------------------
+// generic-proxy st.shared -> visible to the async proxy (the tensor core reads operands through it)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp executes these) -----------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, dense (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- MMA issue (ONE thread) ----------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread -> one arrival on `bar` when they have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T, operands in the chunked layout described at the top.
+// a_rows / b_rows = number of rows of the staged A / B tiles (LBO = rows * 16 B).
+template <int N, int K>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, int a_rows, uint32_t b_saddr, int b_rows,
+                                           bool accumulate_first) {
+  constexpr uint32_t idesc = idesc_bf16(128, N);
+#pragma unroll
+  for (int k = 0; k < K / 16; ++k) {
+    const uint64_t da = smem_desc(a_saddr + k * 2 * a_rows * 16, a_rows * 16, 128);
+    const uint64_t db = smem_desc(b_saddr + k * 2 * b_rows * 16, b_rows * 16, 128);
+    mma_bf16(tmem_d, da, db, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+  }
+}
+
+// ---- TMEM -> registers: 32 lanes x 32b, 16 consecutive columns per thread ---------------------------------
+// taddr = (lane_base << 16) | column; lane_base must be 32 * (warp_id % 4).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand staging helpers -----------------------------------------------------------------------------
+// address (in bf16 elements) of element (row, k) of a tile with `rows` rows in the chunked layout
+__device__ __forceinline__ int op_index(int rows, int row, int k) { return ((k >> 3) * rows + row) * 8 + (k & 7); }
+
+// pack 8 floats into 8 bf16 (16 bytes)
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c);
+  o.w = *reinterpret_cast<uint32_t*>(&d);
+  return o;
+}
+
+// Stage a [rows][K] fp32 row-major GLOBAL matrix (weights) as a bf16 operand tile. Whole CTA cooperates.
+__device__ __forceinline__ void stage_weight_bf16(__nv_bfloat16* dst, const float* __restrict__ src, int rows, int K, int ld) {
+  const int n_chunks = rows * (K >> 3);
+  for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
+    const int row = i % rows, kc = i / rows;
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + kc * 8));
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + kc * 8 + 4));
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    *reinterpret_cast<uint4*>(dst + ((size_t)kc * rows + row) * 8) = pack8(v);
+  }
+}
+
+}  // namespace tc
+}  // namespace grl

@@ -14,6 +14,22 @@ from . import _lib as L
 
 ROW = 16 * 64
 
+# Precision of the nn.Linear contractions inside the message-passing kernels (north_star):
+#   "fp32": FFMA kernels, parity 1e-5 against the reference's fp32 CPU results (default)
+#   "bf16": tcgen05 tensor-core kernels, bf16 operands / fp32 accumulation, parity 1e-2
+_PRECISION = "fp32"
+
+
+def set_precision(mode: str):
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
@@ -246,10 +262,17 @@ class FiberConvFn(torch.autograd.Function):
                           fiber_kernel=L.ptr(fk), wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
                           ln_b=L.ptr(lnb_c), w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_t=L.ptr(w2_t),
                           w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
-        L.call("grl_fbconv_edge_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
-        L.call("grl_fbconv_node_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+        shape = (es.n_src, es.n_dst, es.n_edges)
+        precision = _PRECISION
+        L.call("grl_fbconv_edge_fwd", C.byref(d), shape=shape)
+        if precision == "bf16":
+            w2_rm = _f32c(w2_d)
+            d.w2 = L.ptr(w2_rm)
+            L.call("grl_fbconv_node_fwd_tc", C.byref(d), shape=shape)
+        else:
+            L.call("grl_fbconv_node_fwd", C.byref(d), shape=shape)
         ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1)
-        ctx.es, ctx.homo = es, homo
+        ctx.es, ctx.homo, ctx.precision = es, homo, precision
         return out
 
     @staticmethod

@@ -173,6 +173,8 @@ typedef struct {
   int32_t n_partials_node;
   float* edge_grad_partials; /* [n_partials_edge][64*64] (kernel.weight)                        */
   int32_t n_partials_edge;
+  /* bf16 tensor-core path (the *_tc entry points): plain row-major weights, staged as bf16 operands */
+  const float* w2;           /* [64][256] row-major (nn.Linear.weight of the second node-MLP layer) */
 } GrlConvDesc;
 /* node partial layout: gW1[256][64] | gb1[256] | gW2[64][256] | gb2[64] | g_ln_g[64] | g_ln_b[64]
  *                      | g_bias[64] | g_fk[16][16][64] */
@@ -181,6 +183,10 @@ int grl_fbconv_edge_fwd(const GrlConvDesc* d, grl_stream_t stream); /* basis,x_s
 int grl_fbconv_node_fwd(const GrlConvDesc* d, grl_stream_t stream); /* x1,x_dst -> out             */
 int grl_fbconv_node_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_out -> grad_x1, node partials */
 int grl_fbconv_edge_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_x1 -> grad_x_src, grad_basis, edge partials */
+/* bf16 MLP path (north_star: "bf16 MLP path within 1e-2"): the same operators with the nn.Linear contractions
+ * on the 5th-generation tensor cores (tcgen05.mma kind::f16, bf16 operands, fp32 accumulators in TMEM);
+ * fibre convolution, LayerNorm, GELU, residuals and all segmented sums stay fp32. */
+int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream);
 
 /* out[i] = sum_p partials[p][i], fixed order (deterministic cross-CTA reduction). */
 int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,
@@ -218,6 +224,17 @@ typedef struct {
 } GrlProjDesc;
 int grl_trpl_fwd(const GrlProjDesc* d, grl_stream_t stream);
 int grl_trpl_bwd(const GrlProjDesc* d, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core building-block self-test: D[128][N] = bf16(A[128][K]) * bf16(B[N][K])^T, fp32 accumulate in
+ * TMEM (tcgen05.mma kind::f16).  (N,K) in {(64,16),(64,64),(256,64),(64,256)}.  Test hook only.
+ * ------------------------------------------------------------------------------------------ */
+int grl_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, grl_stream_t stream);
+/* Raw hook behind tests/test_gpu_tc.py's layout probes: the caller supplies the bf16 shared-memory images of
+ * both operands and every descriptor field (byte offsets, per-K-step advance, instruction descriptor). */
+int grl_tc_debug_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, float* D, int N, int n_ksteps,
+                     uint32_t lbo_a, uint32_t sbo_a, uint32_t adv_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t adv_b,
+                     uint32_t idesc, uint32_t desc_hi_bits, grl_stream_t stream);
 
 #ifdef __cplusplus
 }
