@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--minibatch", type=int, default=0, help="samples per GPU per step (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="nn.Linear contractions of the message-passing kernels: fp32 FFMA (parity 1e-5) or bf16 tcgen05 "
+                         "tensor cores (parity 1e-2)")
     return ap.parse_args()
 
 
@@ -113,6 +115,7 @@ def kernel_bytes(name, shape):
         "grl_edge_basis_bwd": E * (R + 32),
         "grl_fbconv_edge_fwd": E * R + n_src * R + n_dst * R + E * 8,
         "grl_fbconv_node_fwd": 3 * n_dst * R,
+        "grl_fbconv_node_fwd_tc": 3 * n_dst * R,
         "grl_fbconv_node_bwd": 3 * n_dst * R,
         "grl_fbconv_edge_bwd": 2 * E * R + 2 * n_src * R + n_dst * R + E * 12,
     }.get(name)
@@ -195,6 +198,8 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False  # strict fp32 everywhere (parity mode)
     torch.backends.cudnn.allow_tf32 = False
 
+    from geometry_rl_b200 import ops
+    ops.set_precision(args.precision)
     cfg = CONFIGS[args.config]
     B = args.minibatch or cfg.mini_batch_size
     actor, critic, projection, loss_module, adv_module = learner.build_agent(cfg, dev, seed=0)  # same init on all ranks
@@ -304,8 +309,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.config, "model": cfg.model, "minibatch_per_gpu": B, "global_minibatch": B * world,
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": args.config, "model": cfg.model, "mlp_precision": args.precision, "minibatch_per_gpu": B, "global_minibatch": B * world,
                        "parallelism": f"dp{world}", "l2": f"rotating {N_ROTATE} minibatches; per-step working set "
                        f"(latents {B * 49 * 4096 / 1e6:.0f} MB each) exceeds the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -68,6 +68,7 @@ SIGNATURES = {
     "grl_fbconv_node_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_edge_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_node_fwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),
     "grl_trpl_fwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),

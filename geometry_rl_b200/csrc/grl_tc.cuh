@@ -101,6 +101,46 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, in
   }
 }
 
+// Operand view for the generic issue loop: start address + (LBO, SBO, byte advance per K = 16 step).
+//   K-major  view of a [rows][cols] image (M/N = rows, K = cols): lbo = rows*16, sbo = 128,     adv = 2*rows*16
+//   MN-major view of the same image       (K = rows, M/N = cols): lbo = 128,     sbo = rows*16, adv = 256
+struct OpView {
+  uint32_t addr, lbo, sbo, adv;
+};
+__device__ __forceinline__ OpView view_k(uint32_t addr, int rows) { return OpView{addr, (uint32_t)rows * 16u, 128u, (uint32_t)rows * 32u}; }
+__device__ __forceinline__ OpView view_mn(uint32_t addr, int rows) { return OpView{addr, 128u, (uint32_t)rows * 16u, 256u}; }
+__host__ __device__ constexpr uint32_t idesc_bf16_ex(int M, int N, int a_mn, int b_mn) {
+  return idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+__device__ __forceinline__ void issue_mma(uint32_t tmem_d, const OpView& a, const OpView& b, uint32_t idesc, int ksteps,
+                                          bool accumulate_first) {
+#pragma unroll 1
+  for (int k = 0; k < ksteps; ++k) {
+    mma_bf16(tmem_d, smem_desc(a.addr + k * a.adv, a.lbo, a.sbo), smem_desc(b.addr + k * b.adv, b.lbo, b.sbo), idesc,
+             (k > 0 || accumulate_first) ? 1u : 0u);
+  }
+}
+
+// Sum over the 32 lanes of a warp of NV per-lane values by recursive halving: NV - 2 + ... shuffles instead of
+// 5 * NV.  On return lane l holds in v[0 .. NV/32) the totals of the ORIGINAL indices  i = l * (NV/32) + j
+// (NV must be a multiple of 32).  Fixed exchange pattern -> deterministic summation order.
+template <int NV>
+__device__ __forceinline__ void warp_colsum(float (&v)[NV], int lane) {
+  static_assert(NV % 32 == 0, "NV must be a multiple of 32");
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = NV >> (step + 1);       // values kept after this step
+    const int bit = 16 >> step;              // partner = lane ^ bit
+    const bool upper = (lane & bit) != 0;    // upper lanes keep the upper half of the current range
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+}
+
 // ---- TMEM -> registers: 32 lanes x 32b, 16 consecutive columns per thread ---------------------------------
 // taddr = (lane_base << 16) | column; lane_base must be 32 * (warp_id % 4).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {

@@ -271,13 +271,14 @@ class FiberConvFn(torch.autograd.Function):
             L.call("grl_fbconv_node_fwd_tc", C.byref(d), shape=shape)
         else:
             L.call("grl_fbconv_node_fwd", C.byref(d), shape=shape)
-        ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1)
+        ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1,
+                              _f32c(w2_d) if precision == "bf16" else w2_c)
         ctx.es, ctx.homo, ctx.precision = es, homo, precision
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1 = ctx.saved_tensors
+        x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1, w2_rm = ctx.saved_tensors
         es, homo = ctx.es, ctx.homo
         dev = x_src.device
         g_out = _f32c(g_out)
@@ -297,7 +298,11 @@ class FiberConvFn(torch.autograd.Function):
                           grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=L.ptr(g_basis),
                           accumulate_grad_basis=0, node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
-        L.call("grl_fbconv_node_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+        if ctx.precision == "bf16":
+            d.w2 = L.ptr(w2_rm)
+            L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+        else:
+            L.call("grl_fbconv_node_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         L.call("grl_fbconv_edge_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         g = _reduce(node_part)
         o = 0

@@ -187,6 +187,8 @@ int grl_fbconv_edge_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_x1 -
  * on the 5th-generation tensor cores (tcgen05.mma kind::f16, bf16 operands, fp32 accumulators in TMEM);
  * fibre convolution, LayerNorm, GELU, residuals and all segmented sums stay fp32. */
 int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream);
+/* grad_out -> grad_x1 + node partials (two launches: tensor-core MLP/LayerNorm backward, fp32 fibre backward) */
+int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);
 
 /* out[i] = sum_p partials[p][i], fixed order (deterministic cross-CTA reduction). */
 int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,

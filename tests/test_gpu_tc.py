@@ -59,3 +59,79 @@ def test_fiber_conv_bf16_tensor_core_path_within_1e_2(B, n_per):
     err = float((delta - ref).abs().max()) / float(ref.abs().max())
     assert err < 1e-2, f"bf16 node path rel err {err}"
     assert err > 0, "bf16 path returned the fp32 result bit-for-bit: tensor-core kernel not exercised"
+
+
+def _idesc(M, N, a_mn=0, b_mn=0):
+    return (1 << 4) | (1 << 7) | (1 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def _chunked(X):
+    """[rows][cols] -> the library's operand image [cols/8][rows][8] bf16."""
+    r, c = X.shape
+    return X.bfloat16().reshape(r, c // 8, 8).permute(1, 0, 2).contiguous().cuda()
+
+
+def _debug_mma(a_img, b_img, N, n_ksteps, a_desc, b_desc, idesc):
+    from geometry_rl_b200 import _lib as L
+    D = torch.full((128, N), float("nan"), device="cuda")
+    L.call("grl_tc_debug_mma", a_img.data_ptr(), a_img.numel() * 2, b_img.data_ptr(), b_img.numel() * 2, L.ptr(D), N,
+           n_ksteps, a_desc[0], a_desc[1], a_desc[2], b_desc[0], b_desc[1], b_desc[2], idesc, 0)
+    torch.cuda.synchronize()
+    return D.cpu()
+
+
+def test_tcgen05_transposed_operands_share_the_same_image():
+    """The [chunk][row][8] image of a [rows][cols] tile is BOTH a K-major operand (M/N = rows, K = cols:
+    LBO = rows*16, SBO = 128, 2*LBO per K step) and an MN-major operand (K = rows, M/N = cols: SBO = rows*16,
+    LBO = 128, 256 B per K step).  The backward kernels rely on this to form X^T Y weight gradients and the
+    W^T products without any transposed copies."""
+    g = torch.Generator().manual_seed(3)
+    rows = 128
+    X = torch.randn(rows, 128, generator=g)   # A^T: [k rows][m]
+    Y = torch.randn(rows, 64, generator=g)    # B^T: [k rows][n]
+    Xb, Yb = X.bfloat16().float(), Y.bfloat16().float()
+    mn = (128, rows * 16, 256)                # (LBO, SBO, advance per K step) of the MN-major view
+    # (1) weight-gradient form: D[m][n] = sum_rows X[row][m] Y[row][n]
+    D = _debug_mma(_chunked(X), _chunked(Y), 64, rows // 16, mn, mn, _idesc(128, 64, 1, 1))
+    ref = Xb.t() @ Yb
+    assert float((D - ref).abs().max() / ref.abs().max()) < 1e-5
+    # (2) activation x W form with W stored [k'][c] K-major-for-forward, read MN-major for the backward:
+    #     D[m][c] = sum_k' A[m][k'] W[k'][c],  A K-major (rows = m, K = k'), W image = chunked([k' rows][c cols])
+    A = torch.randn(128, 128, generator=g)
+    W = torch.randn(128, 64, generator=g)
+    kmaj = (128 * 16, 128, 2 * 128 * 16)
+    D = _debug_mma(_chunked(A), _chunked(W), 64, 128 // 16, kmaj, mn, _idesc(128, 64, 0, 1))
+    ref = A.bfloat16().float() @ W.bfloat16().float()
+    assert float((D - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("B,n_per", [(3, 7), (40, 49)])
+def test_fiber_conv_bf16_backward_within_1e_2(B, n_per):
+    """Every gradient of the fused convolution (inputs, edge basis, all 11 parameter tensors) from the bf16
+    tensor-core path vs the strict fp32 path: within 1e-2 of each tensor's max magnitude."""
+    from geometry_rl_b200 import ops
+    es, p = _conv_inputs(B, n_per, 3, 23)
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(p["x"].shape, generator=g).cuda()
+    names = ["x", "basis", "fk", "wk", "bias", "ln_g", "ln_b", "w1", "b1", "w2", "b2"]
+    grads = {}
+    for mode in ("fp32", "bf16"):
+        leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+        ops.set_precision(mode)
+        try:
+            out = ops.fiber_conv(leaves["x"], None, leaves["basis"], leaves["fk"], leaves["wk"], leaves["bias"], leaves["ln_g"],
+                                 leaves["ln_b"], leaves["w1"], leaves["b1"], leaves["w2"], leaves["b2"], es)
+            (out * w).sum().backward()
+        finally:
+            ops.set_precision("fp32")
+        grads[mode] = {k: leaves[k].grad.clone() for k in names}
+    torch.cuda.synchronize()
+    bad = []
+    for k in names:
+        a, b = grads["bf16"][k], grads["fp32"][k]
+        ref = b - w if k == "x" else b  # the identity part of d out / d x is exact in both paths
+        got = a - w if k == "x" else a
+        err = float((got - ref).abs().max()) / float(ref.abs().max())
+        if not err < 1e-2:
+            bad.append(f"{k}: rel err {err:.3e}")
+    assert not bad, "\n".join(bad)
