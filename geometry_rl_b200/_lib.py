@@ -29,7 +29,8 @@ class GrlEmbedDesc(C.Structure):
 class GrlBasisDesc(C.Structure):
     _fields_ = [("n_edges", _i32), ("dim", _i32), ("edge_src", _fp), ("edge_dst", _fp), ("pos_src", _fp),
                 ("pos_dst", _fp), ("ori", _fp), ("w1t", _fp), ("b1", _fp), ("w2t", _fp), ("b2", _fp), ("basis", _fp),
-                ("w2", _fp), ("grad_basis", _fp), ("grad_partials", _fp), ("n_partials", _i32)]
+                ("w2", _fp), ("grad_basis", _fp), ("grad_partials", _fp), ("n_partials", _i32),
+                ("basis_bf16", _fp), ("grad_basis_bf16", _fp)]
 
 
 class GrlConvDesc(C.Structure):
@@ -40,7 +41,8 @@ class GrlConvDesc(C.Structure):
                 ("w2_c", _fp), ("b2", _fp), ("x1", _fp), ("out", _fp), ("accumulate_out", _i32),
                 ("grad_out", _fp), ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp),
                 ("grad_basis", _fp), ("accumulate_grad_basis", _i32), ("node_grad_partials", _fp),
-                ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp)]
+                ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp),
+                ("basis_bf16", _fp), ("grad_basis_bf16", _fp)]
 
 
 class GrlProjDesc(C.Structure):
@@ -68,6 +70,8 @@ SIGNATURES = {
     "grl_fbconv_node_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_edge_bwd": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_node_fwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_edge_basis_fwd_tc": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
+    "grl_fbconv_edge_fwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),

@@ -1,0 +1,304 @@
+// Edge side of the message passing, bf16 tensor-core path (forward): edge basis MLP and the spatial half of the
+// fibre-bundle convolution.
+//   basis[e] = GELU(GELU(F[e] W1^T + b1) W2^T + b2)          F = 14 polynomial invariants of (i1, i2)
+//   x1[d]    = sum_{e in in(d)} (basis[e] Wk^T) * x_src[src(e)]
+// Reference lines as in grl_basis.cu / grl_conv_edge.cu (hepi.py:76-82,109-123; ponita/conv.py:71-87,116-149).
+// The three contractions run on tcgen05 (bf16 operands, fp32 accumulation in TMEM); the edge basis is stored in
+// HBM as bf16 [E][16][64] (2 KB per edge instead of 4); invariants, GELU, the message product and the
+// deterministic CSR-ordered segmented sum stay fp32.  Small per-CTA footprints (<= 64 KB smem, <= 128 TMEM
+// columns) so 2-3 CTAs share an SM and overlap each other's MMA / epilogue / gather phases.
+#include "grl_common.cuh"
+#include "grl_tc.cuh"
+
+namespace grl {
+
+// ---------------------------------------------------------------------------------------------------
+// (E1) edge basis forward
+// ---------------------------------------------------------------------------------------------------
+struct BasisTcSmem {
+  __nv_bfloat16 F[kTM * 16];    // [2 chunks][128 rows][8]
+  __nv_bfloat16 H1[kTM * kC];   // [8 chunks][128 rows][8]
+  __nv_bfloat16 W1b[kC * 16];   // [2 chunks][64 rows n][8 f]
+  __nv_bfloat16 W2b[kC * kC];   // [8 chunks][64 rows n][8 k]
+  float b1[kC], b2[kC];
+  uint64_t bar[2];
+  uint32_t tmem_base;
+};
+
+// 14 invariant features of (edge, orientation) -> two 16-byte chunks of the F operand image (features 14, 15 = 0)
+__device__ __forceinline__ void basis_features_tc(const GrlBasisDesc& d, int tile, __nv_bfloat16* __restrict__ F) {
+  const int r = threadIdx.x;
+  if (r < kTM) {
+    const int e = tile * kTE + (r >> 4), o = r & 15;
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = 0.f;
+    if (e < d.n_edges) {
+      const float* ps = d.pos_src + 3 * (size_t)d.edge_src[e];
+      const float* pd = d.pos_dst + 3 * (size_t)d.edge_dst[e];
+      const float rx = ps[0] - pd[0], ry = ps[1] - pd[1], rz = (d.dim == 3) ? ps[2] - pd[2] : 0.f;
+      const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+      const float i1 = (rx * ox + ry * oy) + rz * oz;
+      const float tx = rx - i1 * ox, ty = ry - i1 * oy, tz = rz - i1 * oz;
+      const float i2 = sqrtf((tx * tx + ty * ty) + tz * tz);
+      f[0] = i1; f[1] = i2;
+      f[2] = i1 * i1; f[3] = i1 * i2; f[4] = i2 * i1; f[5] = i2 * i2;
+      f[6] = f[2] * i1; f[7] = f[2] * i2; f[8] = f[3] * i1; f[9] = f[3] * i2;
+      f[10] = f[4] * i1; f[11] = f[4] * i2; f[12] = f[5] * i1; f[13] = f[5] * i2;
+    }
+    *reinterpret_cast<uint4*>(F + ((size_t)0 * kTM + r) * 8) = tc::pack8(f);
+    *reinterpret_cast<uint4*>(F + ((size_t)1 * kTM + r) * 8) = tc::pack8(f + 8);
+  }
+}
+
+// B operand images from the transposed fp32 weights the descriptor carries (w1t[f][n], w2t[k][n])
+__device__ __forceinline__ void stage_basis_weights(const GrlBasisDesc& d, __nv_bfloat16* W1b, __nv_bfloat16* W2b, float* b1,
+                                                    float* b2) {
+  for (int i = threadIdx.x; i < kC * 16; i += blockDim.x) {
+    const int n = i >> 4, f = i & 15;
+    W1b[tc::op_index(kC, n, f)] = __float2bfloat16(d.w1t[f * kC + n]);
+  }
+  for (int i = threadIdx.x; i < kC * kC; i += blockDim.x) {
+    const int n = i >> 6, k = i & 63;
+    W2b[tc::op_index(kC, n, k)] = __float2bfloat16(d.w2t[k * kC + n]);
+  }
+  if (threadIdx.x < kC) { b1[threadIdx.x] = d.b1[threadIdx.x]; b2[threadIdx.x] = d.b2[threadIdx.x]; }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const GrlBasisDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BasisTcSmem& s = *reinterpret_cast<BasisTcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
+  if (tid == 0) {
+    tc::mbar_init(&s.bar[0], 1);
+    tc::mbar_init(&s.bar[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 128);
+  stage_basis_weights(d, s.W1b, s.W2b, s.b1, s.b2);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t fa = tc::smem_u32(s.F), ha = tc::smem_u32(s.H1), w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.basis_bf16);
+  uint32_t parity = 0;
+  const int n_tiles = (d.n_edges + kTE - 1) / kTE;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    basis_features_tc(d, tile, s.F);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      tc::issue_mma(tmem, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
+      tc::mma_commit(&s.bar[0]);
+    }
+    tc::mbar_wait(&s.bar[0], parity);
+    tc::tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = gelu_f(v[e] + s.b1[c0 + e]);
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      tc::issue_mma(tmem + kC, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+      tc::mma_commit(&s.bar[1]);
+    }
+    tc::mbar_wait(&s.bar[1], parity);
+    tc::tc_fence_after();
+    const int e_idx = tile * kTE + (row >> 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + kC + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = gelu_f(v[e] + s.b2[c0 + e]);
+      if (e_idx < d.n_edges) {
+        __nv_bfloat16* p = out + (size_t)e_idx * kRow + (row & 15) * kC + c0;
+        *reinterpret_cast<uint4*>(p) = tc::pack8(v);
+        *reinterpret_cast<uint4*>(p + 8) = tc::pack8(v + 8);
+      }
+    }
+    tc::tc_fence_before();
+    parity ^= 1u;
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (E2) spatial convolution forward: kern = basis Wk^T on the tensor core, message product + CSR-ordered sum
+// ---------------------------------------------------------------------------------------------------
+struct EdgeFwdTcSmem {
+  __nv_bfloat16 BZ[kTM * kC];   // basis tile image [8 chunks][128 rows][8]
+  __nv_bfloat16 Wkb[kC * kC];   // [8 chunks][64 rows c][8 j]
+  float XS[kTileFloats];        // gathered x_src rows, then messages in place
+  int src[kTE], dst[kTE];
+  uint64_t bar;
+  uint32_t tmem_base;
+};
+constexpr int kNodesPerBlockTc = 16;
+
+// basis rows of `cnt` consecutive edges (bf16, row-major in HBM) -> operand image, 16-byte cp.async pieces
+__device__ __forceinline__ void stage_basis_image(__nv_bfloat16* __restrict__ img, const __nv_bfloat16* __restrict__ src, int cnt) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = threadIdx.x + kThreads * i;  // 16-byte piece 0..1023
+    const int r = f >> 3, c8 = f & 7;
+    __nv_bfloat16* dpt = img + ((size_t)c8 * kTM + r) * 8;
+    if ((r >> 4) < cnt) {
+      const unsigned sa = tc::smem_u32(dpt);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + (size_t)r * kC + 8 * c8) : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dpt) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const GrlConvDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  EdgeFwdTcSmem& s = *reinterpret_cast<EdgeFwdTcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
+  const int o = tid >> 4, cg = tid & 15;  // mapping of the segmented-sum phase
+  if (tid == 0) {
+    tc::mbar_init(&s.bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 64);
+  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t bz = tc::smem_u32(s.BZ), wk = tc::smem_u32(s.Wkb);
+  const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);
+  uint32_t parity = 0;
+  const int n_blocks = (d.n_dst + kNodesPerBlockTc - 1) / kNodesPerBlockTc;
+  for (int nb = blockIdx.x; nb < n_blocks; nb += gridDim.x) {
+    const int n0 = nb * kNodesPerBlockTc;
+    const int n1 = min(n0 + kNodesPerBlockTc, d.n_dst);
+    const int p0 = d.rowptr_dst[n0], p1 = d.rowptr_dst[n1];
+    int cur = n0;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = p0; base < p1; base += kTE) {
+      const int cnt = min(kTE, p1 - base);
+      __syncthreads();  // previous tile fully consumed
+      if (tid < kTE) {
+        s.src[tid] = (tid < cnt) ? d.edge_src[base + tid] : 0;
+        s.dst[tid] = (tid < cnt) ? d.edge_dst[base + tid] : 0;
+      }
+      stage_basis_image(s.BZ, basis + (size_t)base * kRow, cnt);
+      __syncthreads();  // s.src visible
+      stage_rows_gather(s.XS, d.x_src, s.src, cnt);
+      cp_async_commit();
+      cp_async_wait_all();
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc::tc_fence_after();
+        tc::issue_mma(tmem, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+        tc::mma_commit(&s.bar);
+      }
+      tc::mbar_wait(&s.bar, parity);
+      parity ^= 1u;
+      tc::tc_fence_after();
+      // messages in place: XS[row][c] *= kern[row][c]
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 32 * ch + 16 * i;
+        float v[16];
+        tc::tmem_ld16(lane_addr + c0, v);
+        float* xs = s.XS + row * kLDT + c0;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float4 x = ld4(xs + e);
+          x.x *= v[e]; x.y *= v[e + 1]; x.z *= v[e + 2]; x.w *= v[e + 3];
+          st4(xs + e, x);
+        }
+      }
+      tc::tc_fence_before();
+      __syncthreads();
+      // CSR-ordered segmented sum: thread (o, 4 channels) adds the edges of the tile sequentially
+#pragma unroll
+      for (int j = 0; j < kTE; ++j) {
+        if (j < cnt) {
+          const int dn = s.dst[j];
+          while (cur < dn) {
+            st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
+            sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            ++cur;
+          }
+          const float4 m = ld4(s.XS + (16 * j + o) * kLDT + 4 * cg);
+          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+        }
+      }
+    }
+    while (cur < n1) {
+      st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
+      sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      ++cur;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
+}  // namespace grl
+
+extern "C" {
+
+int grl_edge_basis_fwd_tc(const GrlBasisDesc* d, grl_stream_t stream) {
+  GRL_REQUIRE(d, GRL_EINVAL, "grl_edge_basis_fwd_tc: null descriptor");
+  if (d->n_edges == 0) return GRL_OK;
+  GRL_REQUIRE(d->n_edges > 0 && (d->dim == 2 || d->dim == 3), GRL_EINVAL, "grl_edge_basis_fwd_tc: n_edges=%d dim=%d",
+              d->n_edges, d->dim);
+  GRL_REQUIRE(d->edge_src && d->edge_dst && d->pos_src && d->pos_dst && d->ori && d->w1t && d->b1 && d->w2t && d->b2 &&
+                  d->basis_bf16, GRL_EINVAL, "grl_edge_basis_fwd_tc: null pointer");
+  static bool attr = false;
+  const int smem = (int)sizeof(grl::BasisTcSmem);
+  if (!attr) {
+    cudaFuncSetAttribute(grl::edge_basis_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  const int n_tiles = (d->n_edges + grl::kTE - 1) / grl::kTE;
+  int grid = 2 * grl::sm_count();
+  if (grid > n_tiles) grid = n_tiles;
+  grl::edge_basis_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_edge_basis_fwd_tc");
+}
+
+int grl_fbconv_edge_fwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
+  GRL_REQUIRE(d, GRL_EINVAL, "grl_fbconv_edge_fwd_tc: null descriptor");
+  GRL_REQUIRE(d->n_dst > 0 && d->n_src > 0 && d->n_edges >= 0, GRL_EINVAL, "grl_fbconv_edge_fwd_tc: bad sizes");
+  GRL_REQUIRE(d->rowptr_dst && d->x_src && d->wk && d->x1 && (d->n_edges == 0 || (d->edge_src && d->edge_dst && d->basis_bf16)),
+              GRL_EINVAL, "grl_fbconv_edge_fwd_tc: null pointer");
+  static bool attr = false;
+  const int smem = (int)sizeof(grl::EdgeFwdTcSmem);
+  if (!attr) {
+    cudaFuncSetAttribute(grl::fbconv_edge_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  const int n_blocks = (d->n_dst + grl::kNodesPerBlockTc - 1) / grl::kNodesPerBlockTc;
+  int grid = 2 * grl::sm_count();
+  if (grid > n_blocks) grid = n_blocks;
+  grl::fbconv_edge_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_fbconv_edge_fwd_tc");
+}
+
+}  // extern "C"

@@ -193,12 +193,15 @@ class EdgeBasisFn(torch.autograd.Function):
         w1t[:14] = w1.detach().t()
         w2t = w2.detach().t().contiguous()
         b1c, b2c = _f32c(b1.detach()), _f32c(b2.detach())
-        basis = torch.empty(es.n_edges, 16, 64, dtype=torch.float32, device=dev)
+        bf16 = _PRECISION == "bf16"
+        basis = torch.empty(es.n_edges, 16, 64, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
         d = L.GrlBasisDesc(n_edges=es.n_edges, dim=dim, edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst),
                            pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
-                           w2t=L.ptr(w2t), b2=L.ptr(b2c), basis=L.ptr(basis))
+                           w2t=L.ptr(w2t), b2=L.ptr(b2c), basis=None if bf16 else L.ptr(basis),
+                           basis_bf16=L.ptr(basis) if bf16 else None)
         if es.n_edges > 0:
-            L.call("grl_edge_basis_fwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+            L.call("grl_edge_basis_fwd_tc" if bf16 else "grl_edge_basis_fwd", C.byref(d),
+                   shape=(es.n_src, es.n_dst, es.n_edges))
         ctx.save_for_backward(pos_src, pos_dst, w1t, b1c, w2t, b2c, _f32c(w2.detach()), ori3)
         ctx.es, ctx.dim = es, dim
         return basis
@@ -212,7 +215,7 @@ class EdgeBasisFn(torch.autograd.Function):
             z = torch.zeros
             return (None, None, z(64, 14, device=dev), z(64, device=dev), z(64, 64, device=dev), z(64, device=dev),
                     None, None, None)
-        g_basis = _f32c(g_basis)
+        g_basis = _f32c(g_basis)  # (bf16 path: up-converted until the tensor-core basis backward consumes bf16 directly)
         n_p = _n_partials((es.n_edges + 7) // 8)
         partials = torch.empty(n_p, L.BASIS_GRAD_FLOATS, dtype=torch.float32, device=dev)
         d = L.GrlBasisDesc(n_edges=es.n_edges, dim=dim, edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst),
@@ -241,7 +244,10 @@ class FiberConvFn(torch.autograd.Function):
         homo = x_dst is None
         x_src = _f32c(x_src)
         xd = x_src if homo else _f32c(x_dst)
-        basis, fk = _f32c(basis), _f32c(fk)
+        precision = _PRECISION
+        basis_in_dtype = basis.dtype
+        basis = basis.contiguous() if (precision == "bf16" and basis.dtype == torch.bfloat16) else _f32c(basis)
+        fk = _f32c(fk)
         dev = x_src.device
         assert x_src.shape[0] == es.n_src and xd.shape[0] == es.n_dst, "latent rows do not match the edge set"
         assert tuple(x_src.shape[1:]) == (16, 64) and tuple(w1.shape) == (256, 64) and tuple(w2.shape) == (64, 256)
@@ -258,13 +264,14 @@ class FiberConvFn(torch.autograd.Function):
         out = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=dev)
         d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
                           edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), rowptr_src=L.ptr(es.rowptr_src),
-                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), x_dst=L.ptr(xd), basis=L.ptr(basis),
+                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), x_dst=L.ptr(xd),
+                          basis=L.ptr(basis) if basis.dtype == torch.float32 else None,
+                          basis_bf16=L.ptr(basis) if basis.dtype == torch.bfloat16 else None,
                           fiber_kernel=L.ptr(fk), wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
                           ln_b=L.ptr(lnb_c), w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_t=L.ptr(w2_t),
                           w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
         shape = (es.n_src, es.n_dst, es.n_edges)
-        precision = _PRECISION
-        L.call("grl_fbconv_edge_fwd", C.byref(d), shape=shape)
+        L.call("grl_fbconv_edge_fwd_tc" if basis.dtype == torch.bfloat16 else "grl_fbconv_edge_fwd", C.byref(d), shape=shape)
         if precision == "bf16":
             w2_rm = _f32c(w2_d)
             d.w2 = L.ptr(w2_rm)
@@ -273,7 +280,7 @@ class FiberConvFn(torch.autograd.Function):
             L.call("grl_fbconv_node_fwd", C.byref(d), shape=shape)
         ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1,
                               _f32c(w2_d) if precision == "bf16" else w2_c)
-        ctx.es, ctx.homo, ctx.precision = es, homo, precision
+        ctx.es, ctx.homo, ctx.precision, ctx.basis_in_dtype = es, homo, precision, basis_in_dtype
         return out
 
     @staticmethod
@@ -284,6 +291,9 @@ class FiberConvFn(torch.autograd.Function):
         g_out = _f32c(g_out)
         g_x1 = torch.empty_like(x1)
         g_xsrc = torch.empty_like(x_src)
+        basis_bf16 = basis.dtype == torch.bfloat16
+        if basis_bf16:
+            basis = basis.float()  # interim: the fp32 edge backward kernel reads fp32 basis rows
         g_basis = torch.empty_like(basis)
         n_pn = _n_partials((es.n_dst + 7) // 8)
         n_pe = _n_partials((es.n_src + 15) // 16)
@@ -316,6 +326,8 @@ class FiberConvFn(torch.autograd.Function):
         gfk = g[o:o + 16 * 16 * 64].view(16, 16, 64)
         gwk = _reduce(edge_part).view(64, 64)
         g_xdst = None if homo else g_out
+        if g_basis.dtype != ctx.basis_in_dtype:
+            g_basis = g_basis.to(ctx.basis_in_dtype)
         return g_xsrc, g_xdst, g_basis, gfk, gwk, gbias, glng, glnb, gw1, gb1, gw2, gb2, None
 
 

@@ -128,6 +128,9 @@ typedef struct {
   const float* grad_basis;   /* [E][16][64]                                                     */
   float* grad_partials;      /* [n_partials][GRL_BASIS_GRAD_FLOATS]                             */
   int32_t n_partials;
+  /* bf16 tensor-core path: the basis and its gradient are stored as bf16 [E][16][64] (2 KB per edge) */
+  void* basis_bf16;
+  const void* grad_basis_bf16;
 } GrlBasisDesc;
 /* partial layout: gW1[64][16] | gb1[64] | gW2[64][64] | gb2[64] */
 #define GRL_BASIS_GRAD_FLOATS (64 * 16 + 64 + 64 * 64 + 64)
@@ -175,6 +178,8 @@ typedef struct {
   int32_t n_partials_edge;
   /* bf16 tensor-core path (the *_tc entry points): plain row-major weights, staged as bf16 operands */
   const float* w2;           /* [64][256] row-major (nn.Linear.weight of the second node-MLP layer) */
+  const void* basis_bf16;    /* [E][16][64] bf16 (edge order)                                       */
+  void* grad_basis_bf16;     /* [E][16][64] bf16                                                    */
 } GrlConvDesc;
 /* node partial layout: gW1[256][64] | gb1[256] | gW2[64][256] | gb2[64] | g_ln_g[64] | g_ln_b[64]
  *                      | g_bias[64] | g_fk[16][16][64] */
@@ -186,6 +191,8 @@ int grl_fbconv_edge_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_x1 -
 /* bf16 MLP path (north_star: "bf16 MLP path within 1e-2"): the same operators with the nn.Linear contractions
  * on the 5th-generation tensor cores (tcgen05.mma kind::f16, bf16 operands, fp32 accumulators in TMEM);
  * fibre convolution, LayerNorm, GELU, residuals and all segmented sums stay fp32. */
+int grl_edge_basis_fwd_tc(const GrlBasisDesc* d, grl_stream_t stream);   /* positions -> basis_bf16        */
+int grl_fbconv_edge_fwd_tc(const GrlConvDesc* d, grl_stream_t stream);   /* basis_bf16, x_src -> x1        */
 int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream);
 /* grad_out -> grad_x1 + node partials (two launches: tensor-core MLP/LayerNorm backward, fp32 fibre backward) */
 int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);

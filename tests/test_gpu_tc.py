@@ -135,3 +135,39 @@ def test_fiber_conv_bf16_backward_within_1e_2(B, n_per):
         if not err < 1e-2:
             bad.append(f"{k}: rel err {err:.3e}")
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("name", ["hepi_rigid_insertion", "hepi_cloth_hanging", "hepi_rope_shaping", "empn_rigid_pushing"])
+def test_policy_body_bf16_path_matches_reference_fixture_within_1e_2(name):
+    """The whole policy body on the bf16 tensor-core path (bf16 edge basis, tcgen05 contractions) against the
+    fixtures recorded from the UNMODIFIED reference: outputs and every parameter gradient within 1e-2 of the
+    tensor's max magnitude (north_star: "bf16 MLP path within 1e-2")."""
+    from geometry_rl_b200 import ops
+    from geometry_rl_b200.synthetic import CONFIGS
+    from tests import gpu_helpers as G
+    from tests.helpers import load_golden
+    rec = load_golden(name)
+    cfg = CONFIGS[rec["config"]]
+    net = G.make_policy_body(cfg)
+    net.load_state_dict(rec["state_dict"], strict=True)
+    net.train()
+    data = G.make_data(cfg, policy=True)
+    graph, u = data.build_data(*G.obs_args(cfg, rec["obs"], policy=True), train=True)
+    ops.set_precision("bf16")
+    try:
+        out, hidden = net.one_step(graph, u)
+        loss = (out * rec["w_out"].cuda()).sum() + (hidden * rec["w_hid"].cuda()).sum()
+        loss.backward()
+    finally:
+        ops.set_precision("fp32")
+    assert G.rel(out, rec["out"]) < 1e-2, G.err_report("out", out, rec["out"])
+    assert G.rel(hidden, rec["hidden"]) < 1e-2, G.err_report("hidden", hidden, rec["hidden"])
+    assert G.rel(out, rec["out"]) > 1e-7, "bit-identical to fp32: the bf16 kernels did not run"
+    params = dict(net.named_parameters())
+    bad = []
+    for k, gref in rec["grads"].items():
+        if gref is None:
+            continue
+        if G.rel(params[k].grad, gref) >= 1e-2:
+            bad.append(G.err_report(k, params[k].grad, gref))
+    assert not bad, "\n".join(bad)
