@@ -1,0 +1,456 @@
+// Edge side of the message passing, bf16 tensor-core path (backward).
+//
+// (E3) fbconv_edge_bwd_tc_kernel — src-sorted tiles of 8 edges:
+//        kern    = basis Wk^T                         (tcgen05)
+//        g_xsrc[s] = init[s] + sum_{e in out(s)} g_x1[dst(e)] * kern[e]       (fp32, src-CSR order, no atomics)
+//        g_kern  = g_x1[dst(e)] * x_src[src(e)]
+//        g_basis = g_kern Wk                          (tcgen05, Wk image read MN-major)  -> bf16 in HBM
+//        gWk    += g_kern^T basis                     (tcgen05, accumulated in TMEM over all tiles of the CTA)
+// (E4) edge_basis_bwd_tc_kernel — edge-order tiles: recompute F, pre1, H1, pre2, then
+//        gP2 = g_basis * GELU'(pre2);  gW2 += gP2^T H1;  gH1 = gP2 W2;  gP1 = gH1 * GELU'(pre1);  gW1 += gP1^T F
+//
+// The 64 x 64 (and 64 x 16) weight gradients are formed with M = 128 MMAs by reading a 128-column operand image
+// made of two ADJACENT 64-column images [X | G]: lanes 64..127 of the accumulator then hold G^T Y (lanes 0..63
+// hold X^T Y and are ignored).  Reference: autograd of ponita/conv.py:84-87,116-149 and hepi.py:76-82,109-123.
+#include "grl_common.cuh"
+#include "grl_tc.cuh"
+
+namespace grl {
+
+__device__ __forceinline__ void cp_async16_any(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = tc::smem_u32(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (E3)
+// ---------------------------------------------------------------------------------------------------
+struct EdgeBwdTcSmem {
+  __nv_bfloat16 BZ[kTM * kC];   // basis rows gathered by edge id   [8 chunks][128][8]
+  __nv_bfloat16 GK[kTM * kC];   // g_kern, MUST directly follow BZ ([BZ | GK] is read as one 128-column image)
+  __nv_bfloat16 Wkb[kC * kC];   // [8 chunks][64 rows c][8 j]
+  float GX[kTileFloats];        // g_x1 rows gathered by dst, then g_x1 * kern in place
+  float XS[kTileFloats];        // x_src rows gathered by src
+  int eid[kTE], src[kTE], dst[kTE];
+  uint64_t bar[2];
+  uint32_t tmem_base;
+};
+constexpr int kSrcNodesPerBlockTc = 16;
+
+__global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc_kernel(const GrlConvDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  EdgeBwdTcSmem& s = *reinterpret_cast<EdgeBwdTcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
+  const int o = tid >> 4, cg = tid & 15;
+  if (tid == 0) {
+    tc::mbar_init(&s.bar[0], 1);
+    tc::mbar_init(&s.bar[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 256);
+  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t bz = tc::smem_u32(s.BZ), gk = tc::smem_u32(s.GK), wk = tc::smem_u32(s.Wkb);
+  const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);
+  __nv_bfloat16* g_basis = reinterpret_cast<__nv_bfloat16*>(d.grad_basis_bf16);
+  uint32_t par0 = 0, par1 = 0;
+  bool first = true;
+
+  const int n_blocks = (d.n_src + kSrcNodesPerBlockTc - 1) / kSrcNodesPerBlockTc;
+  for (int nb = blockIdx.x; nb < n_blocks; nb += gridDim.x) {
+    const int n0 = nb * kSrcNodesPerBlockTc;
+    const int n1 = min(n0 + kSrcNodesPerBlockTc, d.n_src);
+    const int q0 = d.rowptr_src[n0], q1 = d.rowptr_src[n1];
+    int cur = n0;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&](int node) {
+      const size_t off = (size_t)node * kRow + o * kC + 4 * cg;
+      if (d.grad_x_src_init) {
+        const float4 b = ldg4(d.grad_x_src_init + off);
+        sum.x += b.x; sum.y += b.y; sum.z += b.z; sum.w += b.w;
+      }
+      st4(d.grad_x_src + off, sum);
+      sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    for (int base = q0; base < q1; base += kTE) {
+      const int cnt = min(kTE, q1 - base);
+      __syncthreads();
+      if (tid < kTE) {
+        const int e = (tid < cnt) ? d.src_eid[base + tid] : 0;
+        s.eid[tid] = e;
+        s.src[tid] = (tid < cnt) ? d.edge_src[e] : 0;
+        s.dst[tid] = (tid < cnt) ? d.edge_dst[e] : 0;
+      }
+      __syncthreads();
+      // basis rows (bf16) by edge id -> operand image
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int f = tid + kThreads * i;
+        const int r = f >> 3, c8 = f & 7, j = r >> 4;
+        __nv_bfloat16* dpt = s.BZ + ((size_t)c8 * kTM + r) * 8;
+        if (j < cnt) cp_async16_any(dpt, basis + (size_t)s.eid[j] * kRow + (r & 15) * kC + 8 * c8);
+        else *reinterpret_cast<uint4*>(dpt) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      stage_rows_gather(s.GX, d.grad_x1, s.dst, cnt);
+      stage_rows_gather(s.XS, d.x_src, s.src, cnt);
+      cp_async_commit();
+      cp_async_wait_all();
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc::tc_fence_after();
+        tc::issue_mma(tmem, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+        tc::mma_commit(&s.bar[0]);
+      }
+      tc::mbar_wait(&s.bar[0], par0);
+      par0 ^= 1u;
+      tc::tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 32 * ch + 16 * i;
+        float v[16], gkv[16];
+        tc::tmem_ld16(lane_addr + c0, v);
+        float* gx = s.GX + row * kLDT + c0;
+        const float* xs = s.XS + row * kLDT + c0;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 gm = ld4(gx + e), x = ld4(xs + e);
+          st4(gx + e, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
+          gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
+        }
+        *reinterpret_cast<uint4*>(s.GK + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
+        *reinterpret_cast<uint4*>(s.GK + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc::tc_fence_after();
+        // g_basis = g_kern Wk   (Wk image [c rows][j cols] read MN-major: K = c, N = j)
+        tc::issue_mma(tmem + 64, tc::view_k(gk, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
+        // lanes 64..127: gWk[c][j] += sum_rows g_kern[row][c] basis[row][j]   ([BZ | GK] as one 128-column image)
+        tc::issue_mma(tmem + 128, tc::view_mn(bz, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, !first);
+        tc::mma_commit(&s.bar[1]);
+      }
+      first = false;
+      // src-CSR segmented sum of g_x1 * kern while the tensor core works
+#pragma unroll
+      for (int j = 0; j < kTE; ++j) {
+        if (j < cnt) {
+          const int sn = s.src[j];
+          while (cur < sn) { flush(cur); ++cur; }
+          const float4 m = ld4(s.GX + (16 * j + o) * kLDT + 4 * cg);
+          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+        }
+      }
+      tc::mbar_wait(&s.bar[1], par1);
+      par1 ^= 1u;
+      tc::tc_fence_after();
+      {
+        const int j = row >> 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 32 * ch + 16 * i;
+          float v[16];
+          tc::tmem_ld16(lane_addr + 64 + c0, v);
+          if (j < cnt) {
+            __nv_bfloat16* p = g_basis + (size_t)s.eid[j] * kRow + (row & 15) * kC + c0;
+            *reinterpret_cast<uint4*>(p) = tc::pack8(v);
+            *reinterpret_cast<uint4*>(p + 8) = tc::pack8(v + 8);
+          }
+        }
+      }
+      tc::tc_fence_before();
+    }
+    while (cur < n1) { flush(cur); ++cur; }
+  }
+  // gWk partial of this CTA: lanes 64..127 = rows c, columns j
+  __syncthreads();
+  tc::tc_fence_after();
+  float* P = d.edge_grad_partials + (size_t)blockIdx.x * kWFloats;
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int c0 = 32 * ch + 16 * i;
+    float v[16];
+    if (first) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = 0.f;
+    } else {
+      tc::tmem_ld16(lane_addr + 128 + c0, v);
+    }
+    if (row >= 64) {
+      float* p = P + (size_t)(row - 64) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (E4)
+// ---------------------------------------------------------------------------------------------------
+struct BasisBwdTcSmem {
+  __nv_bfloat16 F[kTM * 16];    // [2 chunks][128][8]
+  __nv_bfloat16 H1[kTM * kC];   // [8 chunks][128][8]
+  __nv_bfloat16 GP2[kTM * kC];  // MUST follow H1   ([H1 | GP2] -> gW2)
+  __nv_bfloat16 GP1[kTM * kC];  // MUST follow GP2  ([GP2 | GP1] -> gW1)
+  __nv_bfloat16 W1b[kC * 16];
+  __nv_bfloat16 W2b[kC * kC];
+  float b1[kC], b2[kC];
+  float acc_gb1[4][kC], acc_gb2[4][kC];
+  uint64_t bar[4];
+  uint32_t tmem_base;
+};
+
+// shared with grl_edge_tc.cu (same translation-unit-local copies)
+__device__ __forceinline__ void basis_features_tc2(const GrlBasisDesc& d, int tile, __nv_bfloat16* __restrict__ F) {
+  const int r = threadIdx.x;
+  if (r < kTM) {
+    const int e = tile * kTE + (r >> 4), o = r & 15;
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = 0.f;
+    if (e < d.n_edges) {
+      const float* ps = d.pos_src + 3 * (size_t)d.edge_src[e];
+      const float* pd = d.pos_dst + 3 * (size_t)d.edge_dst[e];
+      const float rx = ps[0] - pd[0], ry = ps[1] - pd[1], rz = (d.dim == 3) ? ps[2] - pd[2] : 0.f;
+      const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+      const float i1 = (rx * ox + ry * oy) + rz * oz;
+      const float tx = rx - i1 * ox, ty = ry - i1 * oy, tz = rz - i1 * oz;
+      const float i2 = sqrtf((tx * tx + ty * ty) + tz * tz);
+      f[0] = i1; f[1] = i2;
+      f[2] = i1 * i1; f[3] = i1 * i2; f[4] = i2 * i1; f[5] = i2 * i2;
+      f[6] = f[2] * i1; f[7] = f[2] * i2; f[8] = f[3] * i1; f[9] = f[3] * i2;
+      f[10] = f[4] * i1; f[11] = f[4] * i2; f[12] = f[5] * i1; f[13] = f[5] * i2;
+    }
+    *reinterpret_cast<uint4*>(F + ((size_t)0 * kTM + r) * 8) = tc::pack8(f);
+    *reinterpret_cast<uint4*>(F + ((size_t)1 * kTM + r) * 8) = tc::pack8(f + 8);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) edge_basis_bwd_tc_kernel(const GrlBasisDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BasisBwdTcSmem& s = *reinterpret_cast<BasisBwdTcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&s.bar[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 256);
+  for (int i = tid; i < kC * 16; i += kThreads) {
+    const int n = i >> 4, f = i & 15;
+    s.W1b[tc::op_index(kC, n, f)] = __float2bfloat16(d.w1t[f * kC + n]);
+  }
+  for (int i = tid; i < kC * kC; i += kThreads) {
+    const int n = i >> 6, k = i & 63;
+    s.W2b[tc::op_index(kC, n, k)] = __float2bfloat16(d.w2t[k * kC + n]);
+  }
+  if (tid < kC) { s.b1[tid] = d.b1[tid]; s.b2[tid] = d.b2[tid]; }
+  for (int i = tid; i < 4 * kC; i += kThreads) { (&s.acc_gb1[0][0])[i] = 0.f; (&s.acc_gb2[0][0])[i] = 0.f; }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t fa = tc::smem_u32(s.F), ha = tc::smem_u32(s.H1), g2a = tc::smem_u32(s.GP2), g1a = tc::smem_u32(s.GP1);
+  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b);
+  const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(d.grad_basis_bf16);
+  uint32_t parity = 0;
+  bool first = true;
+  const int n_tiles = (d.n_edges + kTE - 1) / kTE;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    basis_features_tc2(d, tile, s.F);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {  // pre1 = F W1^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
+      tc::mma_commit(&s.bar[0]);
+    }
+    tc::mbar_wait(&s.bar[0], parity);
+    tc::tc_fence_after();
+    float dG1[32];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float pre = v[e] + s.b1[c0 + e];
+        dG1[16 * i + e] = gelu_grad_f(pre);
+        v[e] = gelu_f(pre);
+      }
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {  // pre2 = H1 W2^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem + 64, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+      tc::mma_commit(&s.bar[1]);
+    }
+    tc::mbar_wait(&s.bar[1], parity);
+    tc::tc_fence_after();
+    {
+      const int e_idx = tile * kTE + (row >> 4);
+      float gp2[32];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 32 * ch + 16 * i;
+        float v[16];
+        tc::tmem_ld16(lane_addr + 64 + c0, v);
+        uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
+        if (e_idx < d.n_edges) {
+          const uint4* p = reinterpret_cast<const uint4*>(gb + (size_t)e_idx * kRow + (row & 15) * kC + c0);
+          g0 = __ldg(p);
+          g1 = __ldg(p + 1);
+        }
+        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
+        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __bfloat1622float2(h0[e]), b = __bfloat1622float2(h1[e]);
+          gp2[16 * i + 2 * e] = a.x * gelu_grad_f(v[2 * e] + s.b2[c0 + 2 * e]);
+          gp2[16 * i + 2 * e + 1] = a.y * gelu_grad_f(v[2 * e + 1] + s.b2[c0 + 2 * e + 1]);
+          gp2[16 * i + 8 + 2 * e] = b.x * gelu_grad_f(v[8 + 2 * e] + s.b2[c0 + 8 + 2 * e]);
+          gp2[16 * i + 8 + 2 * e + 1] = b.y * gelu_grad_f(v[8 + 2 * e + 1] + s.b2[c0 + 8 + 2 * e + 1]);
+        }
+        *reinterpret_cast<uint4*>(s.GP2 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i);
+        *reinterpret_cast<uint4*>(s.GP2 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i + 8);
+      }
+      tc::warp_colsum<32>(gp2, lane);
+      s.acc_gb2[q][32 * ch + lane] += gp2[0];
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      // gH1 = gP2 W2   (W2 image [n rows][k cols] read MN-major: K = n, N = k)
+      tc::issue_mma(tmem, tc::view_k(g2a, kTM), tc::view_mn(w2, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
+      // lanes 64..127: gW2[n][k] += sum_rows gP2[row][n] H1[row][k]      ([H1 | GP2] as one 128-column image)
+      tc::issue_mma(tmem + 128, tc::view_mn(ha, kTM), tc::view_mn(ha, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, !first);
+      tc::mma_commit(&s.bar[2]);
+    }
+    tc::mbar_wait(&s.bar[2], parity);
+    tc::tc_fence_after();
+    {
+      float gp1[32];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c0 = 32 * ch + 16 * i;
+        float v[16];
+        tc::tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) gp1[16 * i + e] = v[e] * dG1[16 * i + e];
+        *reinterpret_cast<uint4*>(s.GP1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gp1 + 16 * i);
+        *reinterpret_cast<uint4*>(s.GP1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gp1 + 16 * i + 8);
+      }
+      tc::warp_colsum<32>(gp1, lane);
+      s.acc_gb1[q][32 * ch + lane] += gp1[0];
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      // lanes 64..127: gW1[n][f] += sum_rows gP1[row][n] F[row][f]       ([GP2 | GP1] as one 128-column image)
+      tc::issue_mma(tmem + 192, tc::view_mn(g2a, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, !first);
+      tc::mma_commit(&s.bar[3]);
+    }
+    tc::mbar_wait(&s.bar[3], parity);
+    tc::tc_fence_after();
+    tc::tc_fence_before();
+    first = false;
+    parity ^= 1u;
+  }
+  // partial slot: gW1[64][16] | gb1[64] | gW2[64][64] | gb2[64]
+  __syncthreads();
+  tc::tc_fence_after();
+  float* P = d.grad_partials + (size_t)blockIdx.x * GRL_BASIS_GRAD_FLOATS;
+  {
+    float v[16];
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const int c0 = 32 * ch + 16 * i;
+      if (first) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+      } else {
+        tc::tmem_ld16(lane_addr + 128 + c0, v);
+      }
+      if (row >= 64) {
+        float* p = P + 64 * 16 + 64 + (size_t)(row - 64) * kC + c0;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+      }
+    }
+    if (!first) tc::tmem_ld16(lane_addr + 192, v);
+    if (row >= 64 && ch == 0) {
+      float* p = P + (size_t)(row - 64) * 16;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+  }
+  if (tid < kC) {
+    P[64 * 16 + tid] = ((s.acc_gb1[0][tid] + s.acc_gb1[1][tid]) + s.acc_gb1[2][tid]) + s.acc_gb1[3][tid];
+    P[64 * 16 + 64 + kWFloats + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace grl
+
+extern "C" {
+
+int grl_fbconv_edge_bwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
+  GRL_REQUIRE(d, GRL_EINVAL, "grl_fbconv_edge_bwd_tc: null descriptor");
+  GRL_REQUIRE(d->n_dst > 0 && d->n_src > 0 && d->n_edges >= 0, GRL_EINVAL, "grl_fbconv_edge_bwd_tc: bad sizes");
+  GRL_REQUIRE(d->rowptr_src && d->x_src && d->wk && d->grad_x1 && d->grad_x_src && d->edge_grad_partials &&
+                  (d->n_edges == 0 || (d->src_eid && d->edge_src && d->edge_dst && d->basis_bf16 && d->grad_basis_bf16)),
+              GRL_EINVAL, "grl_fbconv_edge_bwd_tc: null pointer");
+  GRL_REQUIRE(d->n_partials_edge > 0, GRL_EINVAL, "grl_fbconv_edge_bwd_tc: n_partials_edge must be > 0");
+  static bool attr = false;
+  const int smem = (int)sizeof(grl::EdgeBwdTcSmem);
+  if (!attr) {
+    cudaFuncSetAttribute(grl::fbconv_edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  grl::fbconv_edge_bwd_tc_kernel<<<d->n_partials_edge, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_fbconv_edge_bwd_tc");
+}
+
+int grl_edge_basis_bwd_tc(const GrlBasisDesc* d, grl_stream_t stream) {
+  GRL_REQUIRE(d, GRL_EINVAL, "grl_edge_basis_bwd_tc: null descriptor");
+  GRL_REQUIRE(d->n_edges > 0 && (d->dim == 2 || d->dim == 3), GRL_EINVAL, "grl_edge_basis_bwd_tc: n_edges=%d dim=%d",
+              d->n_edges, d->dim);
+  GRL_REQUIRE(d->edge_src && d->edge_dst && d->pos_src && d->pos_dst && d->ori && d->w1t && d->b1 && d->w2t && d->b2 &&
+                  d->grad_basis_bf16 && d->grad_partials, GRL_EINVAL, "grl_edge_basis_bwd_tc: null pointer");
+  GRL_REQUIRE(d->n_partials > 0, GRL_EINVAL, "grl_edge_basis_bwd_tc: n_partials must be > 0");
+  static bool attr = false;
+  const int smem = (int)sizeof(grl::BasisBwdTcSmem);
+  if (!attr) {
+    cudaFuncSetAttribute(grl::edge_basis_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  grl::edge_basis_bwd_tc_kernel<<<d->n_partials, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_edge_basis_bwd_tc");
+}
+
+}  // extern "C"

@@ -146,8 +146,8 @@ def _reduce(partials: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def _n_partials(n_units: int) -> int:
-    return max(1, min(n_units, L.sm_count()))
+def _n_partials(n_units: int, per_sm: int = 1) -> int:
+    return max(1, min(n_units, per_sm * L.sm_count()))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,14 +215,15 @@ class EdgeBasisFn(torch.autograd.Function):
             z = torch.zeros
             return (None, None, z(64, 14, device=dev), z(64, device=dev), z(64, 64, device=dev), z(64, device=dev),
                     None, None, None)
-        g_basis = _f32c(g_basis)  # (bf16 path: up-converted until the tensor-core basis backward consumes bf16 directly)
-        n_p = _n_partials((es.n_edges + 7) // 8)
+        bf16 = g_basis.dtype == torch.bfloat16
+        g_basis = g_basis.contiguous() if bf16 else _f32c(g_basis)
+        n_p = _n_partials((es.n_edges + 7) // 8, 2 if bf16 else 1)
         partials = torch.empty(n_p, L.BASIS_GRAD_FLOATS, dtype=torch.float32, device=dev)
         d = L.GrlBasisDesc(n_edges=es.n_edges, dim=dim, edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst),
                            pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
-                           w2t=L.ptr(w2t), b2=L.ptr(b2c), w2=L.ptr(w2), grad_basis=L.ptr(g_basis),
-                           grad_partials=L.ptr(partials), n_partials=n_p)
-        L.call("grl_edge_basis_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+                           w2t=L.ptr(w2t), b2=L.ptr(b2c), w2=L.ptr(w2), grad_basis=None if bf16 else L.ptr(g_basis),
+                           grad_basis_bf16=L.ptr(g_basis) if bf16 else None, grad_partials=L.ptr(partials), n_partials=n_p)
+        L.call("grl_edge_basis_bwd_tc" if bf16 else "grl_edge_basis_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
         g = _reduce(partials)
         gw1 = g[:1024].view(64, 16)[:, :14].contiguous()
         gb1 = g[1024:1088]
@@ -292,28 +293,29 @@ class FiberConvFn(torch.autograd.Function):
         g_x1 = torch.empty_like(x1)
         g_xsrc = torch.empty_like(x_src)
         basis_bf16 = basis.dtype == torch.bfloat16
-        if basis_bf16:
-            basis = basis.float()  # interim: the fp32 edge backward kernel reads fp32 basis rows
         g_basis = torch.empty_like(basis)
         n_pn = _n_partials((es.n_dst + 7) // 8)
-        n_pe = _n_partials((es.n_src + 15) // 16)
+        n_pe = _n_partials((es.n_src + 15) // 16, 2 if basis_bf16 else 1)
         node_part = torch.empty(n_pn, L.NODE_GRAD_FLOATS, dtype=torch.float32, device=dev)
         edge_part = torch.empty(n_pe, L.EDGE_GRAD_FLOATS, dtype=torch.float32, device=dev)
         d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
                           edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), rowptr_src=L.ptr(es.rowptr_src),
-                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), basis=L.ptr(basis), fiber_kernel=L.ptr(fk),
+                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), basis=None if basis_bf16 else L.ptr(basis),
+                          basis_bf16=L.ptr(basis) if basis_bf16 else None, fiber_kernel=L.ptr(fk),
                           wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c), ln_b=L.ptr(lnb_c),
                           w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_c=L.ptr(w2_c), x1=L.ptr(x1),
                           grad_out=L.ptr(g_out), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),
-                          grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=L.ptr(g_basis),
+                          grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=None if basis_bf16 else L.ptr(g_basis),
+                          grad_basis_bf16=L.ptr(g_basis) if basis_bf16 else None,
                           accumulate_grad_basis=0, node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
+        shape = (es.n_src, es.n_dst, es.n_edges)
         if ctx.precision == "bf16":
             d.w2 = L.ptr(w2_rm)
-            L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+            L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=shape)
         else:
-            L.call("grl_fbconv_node_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
-        L.call("grl_fbconv_edge_bwd", C.byref(d), shape=(es.n_src, es.n_dst, es.n_edges))
+            L.call("grl_fbconv_node_bwd", C.byref(d), shape=shape)
+        L.call("grl_fbconv_edge_bwd_tc" if basis_bf16 else "grl_fbconv_edge_bwd", C.byref(d), shape=shape)
         g = _reduce(node_part)
         o = 0
         gw1 = g[o:o + 256 * 64].view(256, 64); o += 256 * 64

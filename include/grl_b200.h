@@ -194,6 +194,8 @@ int grl_fbconv_edge_bwd(const GrlConvDesc* d, grl_stream_t stream); /* grad_x1 -
 int grl_edge_basis_fwd_tc(const GrlBasisDesc* d, grl_stream_t stream);   /* positions -> basis_bf16        */
 int grl_fbconv_edge_fwd_tc(const GrlConvDesc* d, grl_stream_t stream);   /* basis_bf16, x_src -> x1        */
 int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream);
+int grl_fbconv_edge_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);   /* grad_x1 -> grad_x_src, grad_basis_bf16, edge partials */
+int grl_edge_basis_bwd_tc(const GrlBasisDesc* d, grl_stream_t stream);   /* grad_basis_bf16 -> basis_fn partials */
 /* grad_out -> grad_x1 + node partials (two launches: tensor-core MLP/LayerNorm backward, fp32 fibre backward) */
 int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);
 
