@@ -116,6 +116,11 @@ def kernel_bytes(name, shape):
         "grl_fbconv_edge_fwd": E * R + n_src * R + n_dst * R + E * 8,
         "grl_fbconv_node_fwd": 3 * n_dst * R,
         "grl_fbconv_node_fwd_tc": 3 * n_dst * R,
+        # bf16 path: basis / grad_basis rows are 2 KB (R / 2)
+        "grl_edge_basis_fwd_tc": E * (R // 2 + 32),
+        "grl_edge_basis_bwd_tc": E * (R // 2 + 32),
+        "grl_fbconv_edge_fwd_tc": E * R // 2 + n_src * R + n_dst * R + E * 8,
+        "grl_fbconv_edge_bwd_tc": 2 * E * R // 2 + 2 * n_src * R + n_dst * R + E * 12,
         "grl_fbconv_node_bwd": 3 * n_dst * R,
         "grl_fbconv_node_bwd_tc": 5 * n_dst * R,  # x1, grad_out read, g_x2 write + (fibre kernel) g_x2 re-read, g_x1 write
         "grl_fbconv_edge_bwd": 2 * E * R + 2 * n_src * R + n_dst * R + E * 12,

@@ -216,9 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
         tc::tmem_ld16(lane_addr + kColD + c0, v);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float pre = v[e] + s.b1[128 * h2 + c0 + e];
-          dG[16 * i + e] = gelu_grad_f(pre);
-          v[e] = gelu_f(pre);
+          gelu_fast(v[e] + s.b1[128 * h2 + c0 + e], v[e], dG[16 * i + e]);
         }
         *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
         *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
@@ -304,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
       const float m2 = (s.rs[1][0][row] + s.rs[1][1][row]) * (1.0f / 64.0f);
       const float rstd = s.rstd[row];
       const int node = n0 + (row >> 4);
-      float* gdst = d.grad_x1 + (size_t)node * kRow + (row & 15) * kC + 32 * ch;  // holds g_x2 until kernel (2)
+      float* gdst = d.grad_x2 + (size_t)node * kRow + (row & 15) * kC + 32 * ch;  // consumed by kernel (2)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float o[4];
@@ -367,52 +365,65 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-// (2) fibre convolution backward, fp32.  Thread (channel c, orientation quarter oq): fk[4 o][16 p] and the
-// g_fk accumulators stay in registers; g_x2 is read from d.grad_x1 (written by kernel (1)) and overwritten
-// with g_x1 in place — every (node, c) column is read completely by its 4 threads before any of them writes,
-// enforced by the block barrier between the read and the write phase of each node.
-__global__ void __launch_bounds__(kThreads, 1) fbconv_fiber_bwd_kernel(const GrlConvDesc d) {
-  const int tid = threadIdx.x, c = tid & 63, oq = tid >> 6;
-  float fk[4][kO], gfk[4][kO];
+// (2) fibre convolution backward, fp32.  512 threads: thread (channel c, orientation pair op) keeps fk[2 o][16 p] and
+// the g_fk accumulators in registers, reads the g_x2 column of a node from d.grad_x2 (written by kernel (1)) and
+// writes g_x1; the next node's column is prefetched into registers while the current one is processed.
+constexpr int kFiberThreads = 512;
+__global__ void __launch_bounds__(kFiberThreads, 1) fbconv_fiber_bwd_kernel(const GrlConvDesc d) {
+  const int tid = threadIdx.x, c = tid & 63, op = tid >> 6;
+  float fk[2][kO], gfk[2][kO];
 #pragma unroll
-  for (int oi = 0; oi < 4; ++oi)
+  for (int oi = 0; oi < 2; ++oi)
 #pragma unroll
     for (int p = 0; p < kO; ++p) {
-      fk[oi][p] = __ldg(d.fiber_kernel + ((size_t)((4 * oq + oi) * kO + p)) * kC + c) * 0.0625f;
+      fk[oi][p] = __ldg(d.fiber_kernel + ((size_t)((2 * op + oi) * kO + p)) * kC + c) * 0.0625f;
       gfk[oi][p] = 0.f;
     }
   float gbias = 0.f;
-  for (int n = blockIdx.x; n < d.n_dst; n += gridDim.x) {
-    float* g = d.grad_x1 + (size_t)n * kRow + c;
-    const float* x = d.x1 + (size_t)n * kRow + c;
-    float g2[kO];
+  float g2[kO], x1v[2];
+  int n = blockIdx.x;
+  if (n < d.n_dst) {
 #pragma unroll
-    for (int p = 0; p < kO; ++p) g2[p] = g[p * kC];
-    float x1v[4];
+    for (int p = 0; p < kO; ++p) g2[p] = __ldg(d.grad_x2 + (size_t)n * kRow + p * kC + c);
+    x1v[0] = __ldg(d.x1 + (size_t)n * kRow + (2 * op) * kC + c);
+    x1v[1] = __ldg(d.x1 + (size_t)n * kRow + (2 * op + 1) * kC + c);
+  }
+  for (; n < d.n_dst; n += gridDim.x) {
+    const int nn = n + gridDim.x;
+    float g2n[kO], x1n[2];
+    if (nn < d.n_dst) {
 #pragma unroll
-    for (int oi = 0; oi < 4; ++oi) x1v[oi] = __ldg(x + (4 * oq + oi) * kC);
-    __syncthreads();  // all four orientation quarters have read the g_x2 column before it is overwritten
+      for (int p = 0; p < kO; ++p) g2n[p] = __ldg(d.grad_x2 + (size_t)nn * kRow + p * kC + c);
+      x1n[0] = __ldg(d.x1 + (size_t)nn * kRow + (2 * op) * kC + c);
+      x1n[1] = __ldg(d.x1 + (size_t)nn * kRow + (2 * op + 1) * kC + c);
+    }
 #pragma unroll
-    for (int oi = 0; oi < 4; ++oi) {
+    for (int oi = 0; oi < 2; ++oi) {
       float a = 0.f;
 #pragma unroll
       for (int p = 0; p < kO; ++p) {
         a = fmaf(g2[p], fk[oi][p], a);
         gfk[oi][p] = fmaf(x1v[oi], g2[p], gfk[oi][p]);
       }
-      g[(4 * oq + oi) * kC] = a;
+      d.grad_x1[(size_t)n * kRow + (2 * op + oi) * kC + c] = a;
     }
-    if (oq == 0) {
+    if (op == 0) {
 #pragma unroll
       for (int p = 0; p < kO; ++p) gbias += g2[p];
+    }
+    if (nn < d.n_dst) {
+#pragma unroll
+      for (int p = 0; p < kO; ++p) g2[p] = g2n[p];
+      x1v[0] = x1n[0];
+      x1v[1] = x1n[1];
     }
   }
   float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
 #pragma unroll
-  for (int oi = 0; oi < 4; ++oi)
+  for (int oi = 0; oi < 2; ++oi)
 #pragma unroll
-    for (int p = 0; p < kO; ++p) P[kPGFK + ((size_t)((4 * oq + oi) * kO + p)) * kC + c] = gfk[oi][p] * 0.0625f;
-  if (oq == 0) P[kPGBIAS + c] = gbias;
+    for (int p = 0; p < kO; ++p) P[kPGFK + ((size_t)((2 * op + oi) * kO + p)) * kC + c] = gfk[oi][p] * 0.0625f;
+  if (op == 0) P[kPGBIAS + c] = gbias;
 }
 
 }  // namespace grl
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_fiber_bwd_kernel(const Grl
 extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d && d->n_dst > 0, GRL_EINVAL, "grl_fbconv_node_bwd_tc: bad descriptor");
   GRL_REQUIRE(d->x1 && d->fiber_kernel && d->bias && d->ln_g && d->ln_b && d->w1 && d->b1 && d->w2 && d->grad_out &&
-                  d->grad_x1 && d->node_grad_partials && d->n_partials_node > 0, GRL_EINVAL,
+                  d->grad_x1 && d->grad_x2 && d->node_grad_partials && d->n_partials_node > 0, GRL_EINVAL,
               "grl_fbconv_node_bwd_tc: null pointer");
   static bool attr = false;
   const int smem = (int)sizeof(grl::NodeBwdTcSmem);
@@ -431,6 +442,6 @@ extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream)
   grl::fbconv_node_bwd_tc_kernel<<<d->n_partials_node, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   int rc = grl::check_launch("grl_fbconv_node_bwd_tc (mlp)");
   if (rc != GRL_OK) return rc;
-  grl::fbconv_fiber_bwd_kernel<<<d->n_partials_node, grl::kThreads, 0, (cudaStream_t)stream>>>(*d);
+  grl::fbconv_fiber_bwd_kernel<<<d->n_partials_node, grl::kFiberThreads, 0, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_node_bwd_tc (fibre)");
 }

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_fwd_tc_kernel(const G
         float v[16];
         tc::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + c0, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = gelu_f(v[e] + s.b1[c0 + e]);
+        for (int e = 0; e < 16; ++e) v[e] = gelu_fast(v[e] + s.b1[c0 + e]);
         *reinterpret_cast<uint4*>(s.u.A2 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
         *reinterpret_cast<uint4*>(s.u.A2 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
       }

@@ -288,9 +288,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_bwd_tc_kernel(const Gr
       tc::tmem_ld16(lane_addr + c0, v);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const float pre = v[e] + s.b1[c0 + e];
-        dG1[16 * i + e] = gelu_grad_f(pre);
-        v[e] = gelu_f(pre);
+        gelu_fast(v[e] + s.b1[c0 + e], v[e], dG1[16 * i + e]);
       }
       *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
       *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
@@ -324,10 +322,15 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_bwd_tc_kernel(const Gr
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 a = __bfloat1622float2(h0[e]), b = __bfloat1622float2(h1[e]);
-          gp2[16 * i + 2 * e] = a.x * gelu_grad_f(v[2 * e] + s.b2[c0 + 2 * e]);
-          gp2[16 * i + 2 * e + 1] = a.y * gelu_grad_f(v[2 * e + 1] + s.b2[c0 + 2 * e + 1]);
-          gp2[16 * i + 8 + 2 * e] = b.x * gelu_grad_f(v[8 + 2 * e] + s.b2[c0 + 8 + 2 * e]);
-          gp2[16 * i + 8 + 2 * e + 1] = b.y * gelu_grad_f(v[8 + 2 * e + 1] + s.b2[c0 + 8 + 2 * e + 1]);
+          float y_, d0, d1, d2, d3;
+          gelu_fast(v[2 * e] + s.b2[c0 + 2 * e], y_, d0);
+          gelu_fast(v[2 * e + 1] + s.b2[c0 + 2 * e + 1], y_, d1);
+          gelu_fast(v[8 + 2 * e] + s.b2[c0 + 8 + 2 * e], y_, d2);
+          gelu_fast(v[8 + 2 * e + 1] + s.b2[c0 + 8 + 2 * e + 1], y_, d3);
+          gp2[16 * i + 2 * e] = a.x * d0;
+          gp2[16 * i + 2 * e + 1] = a.y * d1;
+          gp2[16 * i + 8 + 2 * e] = b.x * d2;
+          gp2[16 * i + 8 + 2 * e + 1] = b.y * d3;
         }
         *reinterpret_cast<uint4*>(s.GP2 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i);
         *reinterpret_cast<uint4*>(s.GP2 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i + 8);

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
       float v[16];
       tc::tmem_ld16(lane_addr + c0, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = gelu_f(v[e] + s.b1[c0 + e]);
+      for (int e = 0; e < 16; ++e) v[e] = gelu_fast(v[e] + s.b1[c0 + e]);
       *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
       *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
     }
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
       float v[16];
       tc::tmem_ld16(lane_addr + kC + c0, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = gelu_f(v[e] + s.b2[c0 + e]);
+      for (int e = 0; e < 16; ++e) v[e] = gelu_fast(v[e] + s.b2[c0 + e]);
       if (e_idx < d.n_edges) {
         __nv_bfloat16* p = out + (size_t)e_idx * kRow + (row & 15) * kC + c0;
         *reinterpret_cast<uint4*>(p) = tc::pack8(v);

@@ -8,16 +8,26 @@ namespace grl {
 
 constexpr int kMaxF = 16;
 
-__device__ __forceinline__ void embed_features(const GrlEmbedDesc& d, int n, int o, float (&feat)[kMaxF]) {
+constexpr int kEmbTile = 16;  // nodes staged per CTA iteration
+
+// Stage scalars [T][S] and vectors [T][V][3] of `cnt` consecutive nodes into shared memory (coalesced).
+__device__ __forceinline__ void embed_stage(const GrlEmbedDesc& d, int n0, int cnt, float* __restrict__ sc, float* __restrict__ vc) {
+  const int S = d.n_scalars, V3 = 3 * d.n_vectors;
+  for (int i = threadIdx.x; i < cnt * S; i += kThreads) sc[i] = d.scalars[(size_t)n0 * S + i];
+  for (int i = threadIdx.x; i < cnt * V3; i += kThreads) vc[i] = d.vectors[(size_t)n0 * V3 + i];
+}
+
+// features of (staged node j, orientation o): scalars, then <v, ori_o> for every vector
+__device__ __forceinline__ void embed_features(const GrlEmbedDesc& d, const float* __restrict__ sc, const float* __restrict__ vc,
+                                               int j, float ox, float oy, float oz, float (&feat)[kMaxF]) {
   const int S = d.n_scalars, V = d.n_vectors;
-  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
 #pragma unroll
   for (int f = 0; f < kMaxF; ++f) {
     float v = 0.f;
     if (f < S) {
-      v = d.scalars[(size_t)n * S + f];
+      v = sc[j * S + f];
     } else if (f < S + V) {
-      const float* p = d.vectors + ((size_t)n * V + (f - S)) * 3;
+      const float* p = vc + (j * V + (f - S)) * 3;
       v = (p[0] * ox + p[1] * oy) + ((d.dim == 3) ? p[2] * oz : 0.f);
     }
     feat[f] = v;
@@ -26,47 +36,66 @@ __device__ __forceinline__ void embed_features(const GrlEmbedDesc& d, int n, int
 
 __global__ void __launch_bounds__(kThreads) embed_fwd_kernel(const GrlEmbedDesc d) {
   __shared__ __align__(16) float Wt[kMaxF * kC];  // Wt[f][c] = W[c][f]
+  __shared__ float sc[kEmbTile * kMaxF], vc[kEmbTile * kMaxF * 3];
   const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
   const int F = d.n_scalars + d.n_vectors;
   for (int i = tid; i < kMaxF * kC; i += kThreads) {
     const int f = i / kC, c = i % kC;
     Wt[i] = (f < F) ? d.weight[c * F + f] : 0.f;
   }
-  __syncthreads();
-  for (int n = blockIdx.x; n < d.n_nodes; n += gridDim.x) {
-    float feat[kMaxF];
-    embed_features(d, n, o, feat);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+  const int n_tiles = (d.n_nodes + kEmbTile - 1) / kEmbTile;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n0 = t * kEmbTile, cnt = min(kEmbTile, d.n_nodes - n0);
+    __syncthreads();
+    embed_stage(d, n0, cnt, sc, vc);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      float feat[kMaxF];
+      embed_features(d, sc, vc, j, ox, oy, oz, feat);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int f = 0; f < kMaxF; ++f) {
-      const float4 w = ld4(Wt + f * kC + 4 * cg);
-      a.x = fmaf(feat[f], w.x, a.x);
-      a.y = fmaf(feat[f], w.y, a.y);
-      a.z = fmaf(feat[f], w.z, a.z);
-      a.w = fmaf(feat[f], w.w, a.w);
+      for (int f = 0; f < kMaxF; ++f) {
+        const float4 w = ld4(Wt + f * kC + 4 * cg);
+        a.x = fmaf(feat[f], w.x, a.x);
+        a.y = fmaf(feat[f], w.y, a.y);
+        a.z = fmaf(feat[f], w.z, a.z);
+        a.w = fmaf(feat[f], w.w, a.w);
+      }
+      st4(d.x + (size_t)(n0 + j) * kRow + o * kC + 4 * cg, a);
     }
-    st4(d.x + (size_t)n * kRow + o * kC + 4 * cg, a);
   }
 }
 
 // gW[c][f] = sum_{n,o} grad_x[n][o][c] feat[n][o][f]; per-CTA partial, cross-o reduction through smem.
-__global__ void __launch_bounds__(kThreads) embed_bwd_kernel(const GrlEmbedDesc d) {
+__global__ void __launch_bounds__(kThreads, 2) embed_bwd_kernel(const GrlEmbedDesc d) {
   __shared__ __align__(16) float red[kO * kC];
+  __shared__ float sc[kEmbTile * kMaxF], vc[kEmbTile * kMaxF * 3];
   const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
   const int F = d.n_scalars + d.n_vectors;
+  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
   float g[kMaxF][4];
 #pragma unroll
   for (int f = 0; f < kMaxF; ++f) g[f][0] = g[f][1] = g[f][2] = g[f][3] = 0.f;
-  for (int n = blockIdx.x; n < d.n_nodes; n += gridDim.x) {
-    float feat[kMaxF];
-    embed_features(d, n, o, feat);
-    const float4 gx = ldg4(d.grad_x + (size_t)n * kRow + o * kC + 4 * cg);
+  const int n_tiles = (d.n_nodes + kEmbTile - 1) / kEmbTile;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int n0 = t * kEmbTile, cnt = min(kEmbTile, d.n_nodes - n0);
+    __syncthreads();
+    embed_stage(d, n0, cnt, sc, vc);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const float4 gx = ldg4(d.grad_x + (size_t)(n0 + j) * kRow + o * kC + 4 * cg);
+      float feat[kMaxF];
+      embed_features(d, sc, vc, j, ox, oy, oz, feat);
 #pragma unroll
-    for (int f = 0; f < kMaxF; ++f) {
-      g[f][0] = fmaf(gx.x, feat[f], g[f][0]);
-      g[f][1] = fmaf(gx.y, feat[f], g[f][1]);
-      g[f][2] = fmaf(gx.z, feat[f], g[f][2]);
-      g[f][3] = fmaf(gx.w, feat[f], g[f][3]);
+      for (int f = 0; f < kMaxF; ++f) {
+        g[f][0] = fmaf(gx.x, feat[f], g[f][0]);
+        g[f][1] = fmaf(gx.y, feat[f], g[f][1]);
+        g[f][2] = fmaf(gx.z, feat[f], g[f][2]);
+        g[f][3] = fmaf(gx.w, feat[f], g[f][3]);
+      }
     }
   }
   float* P = d.grad_weight_partials + (size_t)blockIdx.x * kC * F;
@@ -105,8 +134,9 @@ int grl_embed_fwd(const GrlEmbedDesc* d, grl_stream_t stream) {
   const int rc = check_embed(d, "grl_embed_fwd");
   if (rc != GRL_OK) return rc;
   GRL_REQUIRE(d->weight && d->x, GRL_EINVAL, "grl_embed_fwd: null pointer");
-  int grid = 8 * grl::sm_count();
-  if (grid > d->n_nodes) grid = d->n_nodes;
+  const int n_tiles = (d->n_nodes + grl::kEmbTile - 1) / grl::kEmbTile;
+  int grid = 6 * grl::sm_count();
+  if (grid > n_tiles) grid = n_tiles;
   grl::embed_fwd_kernel<<<grid, grl::kThreads, 0, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_embed_fwd");
 }

@@ -173,7 +173,7 @@ class EmbedFn(torch.autograd.Function):
         scalars, vectors, ori3 = ctx.saved_tensors
         N, S, V, dim = ctx.meta
         gx = _f32c(gx)
-        n_p = _n_partials(N)
+        n_p = _n_partials((N + 15) // 16, 2)
         partials = torch.empty(n_p, 64 * (S + V), dtype=torch.float32, device=gx.device)
         d = L.GrlEmbedDesc(n_nodes=N, n_scalars=S, n_vectors=V, dim=dim, scalars=L.ptr(scalars), vectors=L.ptr(vectors),
                            ori=L.ptr(ori3), grad_x=L.ptr(gx), grad_weight_partials=L.ptr(partials), n_partials=n_p)
@@ -311,7 +311,8 @@ class FiberConvFn(torch.autograd.Function):
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
         shape = (es.n_src, es.n_dst, es.n_edges)
         if ctx.precision == "bf16":
-            d.w2 = L.ptr(w2_rm)
+            g_x2 = torch.empty_like(x1)
+            d.w2, d.grad_x2 = L.ptr(w2_rm), L.ptr(g_x2)
             L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=shape)
         else:
             L.call("grl_fbconv_node_bwd", C.byref(d), shape=shape)

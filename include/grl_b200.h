@@ -180,6 +180,7 @@ typedef struct {
   const float* w2;           /* [64][256] row-major (nn.Linear.weight of the second node-MLP layer) */
   const void* basis_bf16;    /* [E][16][64] bf16 (edge order)                                       */
   void* grad_basis_bf16;     /* [E][16][64] bf16                                                    */
+  float* grad_x2;            /* [n_dst][16][64] workspace: gradient w.r.t. the pre-LayerNorm tensor   */
 } GrlConvDesc;
 /* node partial layout: gW1[256][64] | gb1[256] | gW2[64][256] | gb2[64] | g_ln_g[64] | g_ln_b[64]
  *                      | g_bias[64] | g_fk[16][16][64] */
