@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--minibatch", type=int, default=0, help="samples per GPU per step (default: the config's)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--single-precision", action="store_true", help="skip the second (other precision) measurement")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="nn.Linear contractions of the message-passing kernels: fp32 FFMA (parity 1e-5) or bf16 tcgen05 "
                          "tensor cores (parity 1e-2)")
     return ap.parse_args()
@@ -181,31 +183,19 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=True):
+    """Build a fresh agent for `precision`, time `steps` updates device-resident and end-to-end, and (rank 0)
+    time every kernel with CUDA events.  Returns a dict of results (meaningful on rank 0)."""
     import torch.distributed as dist
-    from geometry_rl_b200 import _lib, learner
+    from geometry_rl_b200 import _lib, learner, ops
     from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs
     from geometry_rl_b200.smoke import to_device
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    _lib.load()
-    dp = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-        from geometry_rl_b200.parallel import DataParallel
-        dp = DataParallel()
-    torch.backends.cuda.matmul.allow_tf32 = False  # strict fp32 everywhere (parity mode)
-    torch.backends.cudnn.allow_tf32 = False
-
-    from geometry_rl_b200 import ops
-    ops.set_precision(args.precision)
+    # strict mode: fp32 everywhere.  bf16 mode: the library GEMMs of the DeepSets critic / heads may use TF32, as the
+    # reference itself does on GPU (examples/torchrl/train.py:29-30)
+    torch.backends.cuda.matmul.allow_tf32 = precision == "bf16"
+    torch.backends.cudnn.allow_tf32 = precision == "bf16"
+    ops.set_precision(precision)
     cfg = CONFIGS[args.config]
     B = args.minibatch or cfg.mini_batch_size
     actor, critic, projection, loss_module, adv_module = learner.build_agent(cfg, dev, seed=0)  # same init on all ranks
@@ -243,8 +233,17 @@ def run_ours(args):
         return float(t[0])
 
     # ---- device-resident timing ----------------------------------------------------------------------
+    use_graph = (dp is None) and not args.no_graph
+    launches_per_step = None
+    if use_graph:
+        c0 = _lib.launch_count
+        lrn.capture(dev_batches[0], warmup=max(args.warmup, 3))
+        launches_per_step = (_lib.launch_count - c0) // (max(args.warmup, 3) + 1)
+        step = lrn.update_graphed
+    else:
+        step = lrn.update
     for i in range(args.warmup):
-        lrn.update(dev_batches[i % N_ROTATE])
+        step(dev_batches[i % N_ROTATE])
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -253,15 +252,16 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed steps
     e0.record()
-    for i in range(args.steps):
-        out = lrn.update(dev_batches[i % N_ROTATE])
+    for i in range(steps):
+        out = step(dev_batches[i % N_ROTATE])
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
-    launches = _lib.launch_count - launches0
+    launches = launches_per_step * steps if use_graph else _lib.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1))
-    value = B * world * args.steps / (ms * 1e-3)
+    res = {"precision": precision, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+           "clocks": clocks, "gpu_launches": launches, "cuda_graph": use_graph, "B": B, "model": cfg.model}
 
     # ---- end to end: pinned host minibatch -> H2D -> step -> loss scalar D2H, every step ----------------
     barrier()
@@ -269,40 +269,75 @@ def run_ours(args):
     t_wall = time.perf_counter()
     s0.record()
     loss_host = 0.0
-    for i in range(args.steps):
-        mb = {k: t.to(dev, non_blocking=True) for k, t in host_batches[i % N_ROTATE].items()}
-        out = lrn.update(mb)
+    for i in range(steps):
+        if use_graph:  # pinned host -> the graph's static input buffers (H2D), replay, read the loss back
+            out = step(host_batches[i % N_ROTATE])
+        else:
+            out = step({k: t.to(dev, non_blocking=True) for k, t in host_batches[i % N_ROTATE].items()})
         loss_host = float(out["actor_loss"].item())  # device -> host read of the step's result
     s1.record()
     barrier()
     e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), (time.perf_counter() - t_wall) * 1e3 if dp is None else 0.0))
-    e2e = {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
-           "d2h_bytes_per_step": 4, "last_actor_loss": loss_host}
+    res["e2e"] = {"value": B * world * steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                  "d2h_bytes_per_step": 4, "last_actor_loss": loss_host}
 
-    # ---- per-kernel CUDA-event pass (same steps, events around every C-ABI launch) ------------------------
-    roofline = None
-    n_prof = min(args.steps, 5)
-    if rank == 0:
-        _lib.event_timing(True)
-    for i in range(n_prof):  # every rank runs the steps (they contain collectives); only rank 0 records events
-        lrn.update(dev_batches[i % N_ROTATE])
-    torch.cuda.synchronize()
-    if rank == 0:
-        per_kernel = _lib.event_timing(False)  # name -> list of (ms, n_src, n_dst, n_edges)
-        tot = {k: sum(x[0] for x in v) for k, v in per_kernel.items()}
-        step_kernel_ms = sum(tot.values())
-        top = max(tot, key=tot.get)
-        peak, peak_src = measured_peaks()
-        # average over the launches of the dominant kernel: algorithmic bytes of each launch / its duration
-        ab = sum(kernel_bytes(top, x[1:]) or 0 for x in per_kernel[top])
-        dur = tot[top] * 1e-3
-        achieved = ab / dur / 1e9 if dur > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": tot[top] / len(per_kernel[top]), "launches_per_step": len(per_kernel[top]) / n_prof,
-                    "algorithmic_bytes_per_launch": ab / len(per_kernel[top]),
-                    "share_of_kernel_time": tot[top] / step_kernel_ms,
-                    "kernel_ms_per_step": {k: round(v / n_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+    # ---- per-kernel CUDA-event pass (same steps, eager, events around every C-ABI launch) -------------------
+    res["roofline"] = None
+    if with_profile:
+        n_prof = min(steps, 5)
+        if rank == 0:
+            _lib.event_timing(True)
+        for i in range(n_prof):  # every rank runs the steps (they contain collectives); only rank 0 records events
+            lrn.update(dev_batches[i % N_ROTATE])
+        torch.cuda.synchronize()
+        if rank == 0:
+            per_kernel = _lib.event_timing(False)  # name -> list of (ms, n_src, n_dst, n_edges)
+            tot = {k: sum(x[0] for x in v) for k, v in per_kernel.items()}
+            step_kernel_ms = sum(tot.values())
+            top = max(tot, key=tot.get)
+            peak, peak_src = measured_peaks()
+            # average over the launches of the dominant kernel: algorithmic bytes of each launch / its duration
+            ab = sum(kernel_bytes(top, x[1:]) or 0 for x in per_kernel[top])
+            dur = tot[top] * 1e-3
+            achieved = ab / dur / 1e9 if dur > 0 else 0.0
+            res["roofline"] = {
+                "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": tot[top] / len(per_kernel[top]),
+                "launches_per_step": len(per_kernel[top]) / n_prof, "algorithmic_bytes_per_launch": ab / len(per_kernel[top]),
+                "share_of_kernel_time": tot[top] / step_kernel_ms,
+                "kernel_ms_per_step": {k: round(v / n_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+    del lrn, actor, critic, loss_module, dev_batches, host_batches
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from geometry_rl_b200 import _lib
+    from geometry_rl_b200.synthetic import CONFIGS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    dp = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        from geometry_rl_b200.parallel import DataParallel
+        dp = DataParallel()
+    cfg = CONFIGS[args.config]
+
+    main_res = measure(args, args.precision, dev, dp, rank, world, local, args.steps)
+    # the other precision mode of the same path, measured in the same run (fewer steps; no per-kernel pass)
+    other = "fp32" if args.precision == "bf16" else "bf16"
+    other_res = None
+    if not args.single_precision and cfg.model != "transformer":
+        other_res = measure(args, other, dev, dp, rank, world, local, min(args.steps, 5), with_profile=False)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -312,15 +347,26 @@ def run_ours(args):
                          f"restatement of the reference step, fp64 KL dual solve instead of ITPAL), {sec:.2f} s/step"}
 
     if rank == 0:
+        B = main_res["B"]
         line = {
-            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": main_res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": args.config, "model": cfg.model, "mlp_precision": args.precision, "minibatch_per_gpu": B, "global_minibatch": B * world,
+            "config": {"workload": args.config, "model": cfg.model, "mlp_precision": args.precision,
+                       "parity": "1e-5 vs reference fp32" if args.precision == "fp32" else
+                                 "1e-2 vs reference fp32 (north_star bf16 MLP path: bf16 tcgen05 operands, fp32 accumulation; "
+                                 "latents, LayerNorm, segmented sums, projection, losses fp32)",
+                       "cuda_graph": main_res["cuda_graph"], "minibatch_per_gpu": B, "global_minibatch": B * world,
                        "parallelism": f"dp{world}", "l2": f"rotating {N_ROTATE} minibatches; per-step working set "
                        f"(latents {B * 49 * 4096 / 1e6:.0f} MB each) exceeds the 126 MB L2"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
+            "roofline": main_res["roofline"], "cpu_baseline": cpu,
         }
+        if other_res is not None:
+            line["other_precision"] = {"mlp_precision": other, "dtype": "f32" if other == "fp32" else "bf16",
+                                       "value": other_res["value"], "unit": "samples/s", "ms_per_step": other_res["ms_per_step"],
+                                       "steps": other_res["steps"], "e2e": other_res["e2e"]["value"],
+                                       "parity": "1e-5 vs reference fp32" if other == "fp32" else "1e-2 vs reference fp32"}
         print(json.dumps(line))
     if dp is not None:
         dist.destroy_process_group()

@@ -31,9 +31,8 @@ class TRPLLoss(nn.Module):
         self.loss_critic_type = loss_critic_type
         self.normalize_advantage = normalize_advantage
         self.separate_losses = separate_losses
-        if clip_value is not None:
-            clip_value = torch.tensor(float(clip_value))
-        self.register_buffer("clip_value", clip_value)
+        # plain float (the reference registers a 0-dim buffer and moves it to the device on every call, trpl.py:219)
+        self.clip_value = None if clip_value is None else float(clip_value)
         self.trust_region_coef = trust_region_coef
         self.register_buffer("clip_epsilon", torch.tensor(clip_epsilon))
         self.projection = projection
@@ -52,8 +51,8 @@ class TRPLLoss(nn.Module):
         state_value = self.critic_network.module(*[td_get(td, k) for k in self.critic_network.in_keys])
         loss_value = distance_loss(target_return, state_value, loss_function=self.loss_critic_type)
         if self.clip_value is not None:
-            loss_value, _ = _clip_value_loss(old_state_value, state_value, self.clip_value.to(state_value.device),
-                                             target_return, loss_value, self.loss_critic_type)
+            loss_value, _ = _clip_value_loss(old_state_value, state_value, self.clip_value, target_return, loss_value,
+                                             self.loss_critic_type)
         return self.critic_coef * loss_value
 
     # ---- actor (trpl.py:231-253) ---------------------------------------------------------------------

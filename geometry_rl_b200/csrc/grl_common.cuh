@@ -48,10 +48,19 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
-// GELU (erf form) and its derivative for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7) sharing ONE exponential with the Gaussian pdf: 2 MUFU (ex2, rcp) + ~14 FP32 ops per element
-// instead of erff + expf.  The strict fp32 kernels keep erff.
+// GELU and its derivative for the bf16 tensor-core path.  The epilogues of those kernels are instruction-bound
+// on the activation (ncu: 75 % of the issued instructions of the node kernels), and their results are rounded
+// to bf16 operands (relative step 3.9e-3) right afterwards, so the default is the tanh form evaluated with ONE
+// MUFU.TANH:  gelu(x) ~ 0.5 x (1 + tanh(k (x + c x^3))),  |error| <= 4.8e-4 on gelu, 8.7e-4 on gelu' (6 + 5 FP32
+// ops).  -DGRL_TC_EXACT_GELU selects the erf form by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, one shared
+// exponential, 2 MUFU + ~14 FP32 ops).  The strict fp32 kernels always use erff.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
+#ifdef GRL_TC_EXACT_GELU
   const float u = __expf(-0.5f * x * x);                                   // exp(-z^2), z = |x| / sqrt(2)
   const float t = __fdividef(1.0f, fmaf(0.23164189f, fabsf(x), 1.0f));     // 1 / (1 + p z), p / sqrt(2) folded in
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
@@ -62,11 +71,25 @@ __device__ __forceinline__ void gelu_fast(float x, float& y, float& dy) {
   const float cdf = x >= 0.f ? 1.0f - tail : tail;
   y = x * cdf;
   dy = fmaf(x * u, 0.39894228040143267794f, cdf);
+#else
+  constexpr float k = 0.7978845608028654f, kc = 0.7978845608028654f * 0.044715f;
+  const float t2 = x * x;
+  const float th = tanh_approx(x * fmaf(t2, kc, k));
+  const float hx = 0.5f * x;
+  y = fmaf(hx, th, hx);
+  dy = fmaf(hx * fmaf(-th, th, 1.0f), fmaf(t2, 3.0f * kc, k), fmaf(th, 0.5f, 0.5f));
+#endif
 }
 __device__ __forceinline__ float gelu_fast(float x) {
+#ifdef GRL_TC_EXACT_GELU
   float y, dy;
   gelu_fast(x, y, dy);
   return y;
+#else
+  constexpr float k = 0.7978845608028654f, kc = 0.7978845608028654f * 0.044715f;
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(x * fmaf(x * x, kc, k)), hx);
+#endif
 }
 
 // ---- cp.async (LDGSTS) ----------------------------------------------------------------------

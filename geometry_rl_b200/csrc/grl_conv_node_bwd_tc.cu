@@ -215,8 +215,12 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
         float v[16];
         tc::tmem_ld16(lane_addr + kColD + c0, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          gelu_fast(v[e] + s.b1[128 * h2 + c0 + e], v[e], dG[16 * i + e]);
+        for (int e = 0; e < 16; e += 4) {
+          const float4 bb = ld4(s.b1 + 128 * h2 + c0 + e);
+          gelu_fast(v[e] + bb.x, v[e], dG[16 * i + e]);
+          gelu_fast(v[e + 1] + bb.y, v[e + 1], dG[16 * i + e + 1]);
+          gelu_fast(v[e + 2] + bb.z, v[e + 2], dG[16 * i + e + 2]);
+          gelu_fast(v[e + 3] + bb.w, v[e + 3], dG[16 * i + e + 3]);
         }
         *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
         *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
@@ -365,11 +369,32 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-// (2) fibre convolution backward, fp32.  512 threads: thread (channel c, orientation pair op) keeps fk[2 o][16 p] and
-// the g_fk accumulators in registers, reads the g_x2 column of a node from d.grad_x2 (written by kernel (1)) and
-// writes g_x1; the next node's column is prefetched into registers while the current one is processed.
+// (2) fibre convolution backward, fp32: a pure streaming pass (reads g_x2 and x1, writes g_x1: 12 KB per node).
+// 512 threads; thread (channel c, orientation pair op) keeps fk[2 o][16 p] and its g_fk accumulators in registers.
+// Tiles of 4 nodes are staged with 16-byte cp.async into a double-buffered shared-memory ring (64 KB in flight per
+// SM) so the HBM latency is covered without relying on occupancy.
 constexpr int kFiberThreads = 512;
+constexpr int kFibTile = 4;
+struct FiberBwdSmem {
+  float G[2][kFibTile * kRow];
+  float X[2][kFibTile * kRow];
+};
+
+__device__ __forceinline__ void fiber_stage(FiberBwdSmem& s, int buf, const GrlConvDesc& d, int tile) {
+  const int n0 = tile * kFibTile;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = threadIdx.x + kFiberThreads * i;  // float4 index over [2 arrays][4 nodes][256 float4]
+    const int arr = f >> 10, idx = f & 1023, node = n0 + (idx >> 8);
+    float* dst = (arr ? s.X[buf] : s.G[buf]) + 4 * idx;
+    if (node < d.n_dst) cp_async16(dst, (arr ? d.x1 : d.grad_x2) + (size_t)n0 * kRow + 4 * idx);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(kFiberThreads, 1) fbconv_fiber_bwd_kernel(const GrlConvDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FiberBwdSmem& s = *reinterpret_cast<FiberBwdSmem*>(smem_raw);
   const int tid = threadIdx.x, c = tid & 63, op = tid >> 6;
   float fk[2][kO], gfk[2][kO];
 #pragma unroll
@@ -380,43 +405,41 @@ __global__ void __launch_bounds__(kFiberThreads, 1) fbconv_fiber_bwd_kernel(cons
       gfk[oi][p] = 0.f;
     }
   float gbias = 0.f;
-  float g2[kO], x1v[2];
-  int n = blockIdx.x;
-  if (n < d.n_dst) {
+  const int n_tiles = (d.n_dst + kFibTile - 1) / kFibTile;
+  int tile = blockIdx.x, buf = 0;
+  if (tile < n_tiles) fiber_stage(s, 0, d, tile);
+  cp_async_commit();
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int nt = tile + gridDim.x;
+    if (nt < n_tiles) fiber_stage(s, buf ^ 1, d, nt);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
 #pragma unroll
-    for (int p = 0; p < kO; ++p) g2[p] = __ldg(d.grad_x2 + (size_t)n * kRow + p * kC + c);
-    x1v[0] = __ldg(d.x1 + (size_t)n * kRow + (2 * op) * kC + c);
-    x1v[1] = __ldg(d.x1 + (size_t)n * kRow + (2 * op + 1) * kC + c);
-  }
-  for (; n < d.n_dst; n += gridDim.x) {
-    const int nn = n + gridDim.x;
-    float g2n[kO], x1n[2];
-    if (nn < d.n_dst) {
+    for (int j = 0; j < kFibTile; ++j) {
+      const int node = tile * kFibTile + j;
+      const float* G = s.G[buf] + j * kRow + c;
+      const float* X = s.X[buf] + j * kRow + c;
+      float g2[kO];
 #pragma unroll
-      for (int p = 0; p < kO; ++p) g2n[p] = __ldg(d.grad_x2 + (size_t)nn * kRow + p * kC + c);
-      x1n[0] = __ldg(d.x1 + (size_t)nn * kRow + (2 * op) * kC + c);
-      x1n[1] = __ldg(d.x1 + (size_t)nn * kRow + (2 * op + 1) * kC + c);
-    }
+      for (int p = 0; p < kO; ++p) g2[p] = G[p * kC];
 #pragma unroll
-    for (int oi = 0; oi < 2; ++oi) {
-      float a = 0.f;
+      for (int oi = 0; oi < 2; ++oi) {
+        const float x1v = X[(2 * op + oi) * kC];
+        float a = 0.f;
 #pragma unroll
-      for (int p = 0; p < kO; ++p) {
-        a = fmaf(g2[p], fk[oi][p], a);
-        gfk[oi][p] = fmaf(x1v[oi], g2[p], gfk[oi][p]);
+        for (int p = 0; p < kO; ++p) {
+          a = fmaf(g2[p], fk[oi][p], a);
+          gfk[oi][p] = fmaf(x1v, g2[p], gfk[oi][p]);
+        }
+        if (node < d.n_dst) d.grad_x1[(size_t)node * kRow + (2 * op + oi) * kC + c] = a;
       }
-      d.grad_x1[(size_t)n * kRow + (2 * op + oi) * kC + c] = a;
-    }
-    if (op == 0) {
+      if (op == 0) {
 #pragma unroll
-      for (int p = 0; p < kO; ++p) gbias += g2[p];
+        for (int p = 0; p < kO; ++p) gbias += g2[p];
+      }
     }
-    if (nn < d.n_dst) {
-#pragma unroll
-      for (int p = 0; p < kO; ++p) g2[p] = g2n[p];
-      x1v[0] = x1n[0];
-      x1v[1] = x1n[1];
-    }
+    __syncthreads();  // everyone done with `buf` before the next iteration's prefetch overwrites it
   }
   float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
 #pragma unroll
@@ -442,6 +465,12 @@ extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream)
   grl::fbconv_node_bwd_tc_kernel<<<d->n_partials_node, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   int rc = grl::check_launch("grl_fbconv_node_bwd_tc (mlp)");
   if (rc != GRL_OK) return rc;
-  grl::fbconv_fiber_bwd_kernel<<<d->n_partials_node, grl::kFiberThreads, 0, (cudaStream_t)stream>>>(*d);
+  static bool attr2 = false;
+  const int smem2 = (int)sizeof(grl::FiberBwdSmem);
+  if (!attr2) {
+    cudaFuncSetAttribute(grl::fbconv_fiber_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    attr2 = true;
+  }
+  grl::fbconv_fiber_bwd_kernel<<<d->n_partials_node, grl::kFiberThreads, smem2, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_node_bwd_tc (fibre)");
 }

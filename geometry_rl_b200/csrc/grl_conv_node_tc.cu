@@ -168,7 +168,13 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_fwd_tc_kernel(const G
         float v[16];
         tc::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + c0, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = gelu_fast(v[e] + s.b1[c0 + e]);
+        for (int e = 0; e < 16; e += 4) {
+          const float4 bb = ld4(s.b1 + c0 + e);
+          v[e] = gelu_fast(v[e] + bb.x);
+          v[e + 1] = gelu_fast(v[e + 1] + bb.y);
+          v[e + 2] = gelu_fast(v[e + 2] + bb.z);
+          v[e + 3] = gelu_fast(v[e + 3] + bb.w);
+        }
         *reinterpret_cast<uint4*>(s.u.A2 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
         *reinterpret_cast<uint4*>(s.u.A2 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
       }

@@ -108,9 +108,11 @@ class Learner:
     def __init__(self, cfg: PathConfig, actor, critic, loss_module, dp=None, fused_adam: bool = True):
         self.cfg, self.actor, self.critic, self.loss_module, self.dp = cfg, actor, critic, loss_module, dp
         fused = fused_adam and next(actor.parameters()).is_cuda
-        self.actor_optim = torch.optim.Adam(actor.parameters(), lr=cfg.lr, eps=1e-5, fused=fused)
-        self.critic_optim = torch.optim.Adam(critic.parameters(), lr=cfg.lr, eps=1e-5, fused=fused)
+        # capturable: the step counter lives on the device, so the whole update can be replayed from a CUDA graph
+        self.actor_optim = torch.optim.Adam(actor.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
+        self.critic_optim = torch.optim.Adam(critic.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
         self.num_network_updates = 0
+        self._graph = None
         if dp is not None:
             dp.attach(loss_module)
 
@@ -135,3 +137,29 @@ class Learner:
         self.actor_optim.zero_grad()
         self.critic_optim.zero_grad()
         return loss
+
+
+    # ---- CUDA-graph replay of the whole update (launch-bound glue: ~500 launches per step) -----------------------
+    def capture(self, example_batch, warmup: int = 3):
+        """Capture `update` on static copies of `example_batch` (same shapes for every later batch).  The warm-up
+        iterations are REAL updates (they also run the one-time calibration and build the topology cache)."""
+        if self.dp is not None:
+            raise RuntimeError("graph capture of the data-parallel step is not enabled (NCCL calls stay eager)")
+        self._static = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.update(self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.update(self._static)
+        return self
+
+    def update_graphed(self, batch):
+        for k, v in self._static.items():
+            v.copy_(batch[k], non_blocking=True)
+        self._graph.replay()
+        self.num_network_updates += 1
+        return self._graph_out

@@ -24,6 +24,9 @@ class FiberBundleConv(torch.nn.Module):
         self.fiber_kernel = Linear(attr_dim, int(in_channels * out_channels / groups), bias=False)
         self.bias = torch.nn.Parameter(torch.zeros(out_channels))
         self.register_buffer("callibrated", torch.tensor(False))
+        # host-side latch of `callibrated` (reading the device buffer every forward would be a GPU sync per conv)
+        self._cal_latch = False
+        self._register_load_state_dict_pre_hook(lambda *a, **k: setattr(self, "_cal_latch", False))
         self.vmap_aggr = None
         self.args = "sum"
         self.node_mlp = Sequential(LayerNorm(in_channels), Linear(in_channels, out_channels * widening_factor),
@@ -42,7 +45,7 @@ class FiberBundleConv(torch.nn.Module):
             homo = True
         fk = F.linear(fiber_attr, self.fiber_kernel.weight)  # [o, p, c]  (conv.py:88-90 "boc,opc->bpc")
         pending = None
-        if self.training and not bool(self.callibrated):
+        if self.training and not self._is_callibrated():
             pending = self._callibration_factors(x_src, x_dst, edge_attr, fk, edge_set)
         mlp = self.node_mlp
         out = ops.fiber_conv(x_src, None if homo else x_dst, edge_attr, fk, self.kernel.weight, self.bias, mlp[0].weight,
@@ -53,6 +56,11 @@ class FiberBundleConv(torch.nn.Module):
             self.fiber_kernel.weight.data = self.fiber_kernel.weight.data * pending[1]
             self.callibrated = ~self.callibrated
         return (x_src, out)
+
+    def _is_callibrated(self) -> bool:
+        if not self._cal_latch:
+            self._cal_latch = bool(self.callibrated)
+        return self._cal_latch
 
     @torch.no_grad()
     def _callibration_factors(self, x_src, x_dst, edge_attr, fk, edge_set):

@@ -91,6 +91,14 @@ class SeparableFiberBundleConv(nn.Module):
         self.attention = attention
         self.bias = nn.Parameter(torch.zeros(out_channels))
         self.register_buffer("callibrated", torch.tensor(False))
+        # host-side latch of `callibrated` (reading the device buffer every forward would be a GPU sync per layer)
+        self._cal_latch = False
+        self._register_load_state_dict_pre_hook(lambda *a, **k: setattr(self, "_cal_latch", False))
+
+    def is_callibrated(self) -> bool:
+        if not self._cal_latch:
+            self._cal_latch = bool(self.callibrated)
+        return self._cal_latch
 
 
 class SeparableFiberBundleConvNext(nn.Module):
@@ -112,7 +120,7 @@ class SeparableFiberBundleConvNext(nn.Module):
         fk = F.linear(fiber_kernel_basis, c.fiber_kernel.weight)  # [p, o, c] (ponita.py:166 "boc,poc->bpc")
         fk_op = fk.transpose(0, 1).contiguous()  # kernel layout [o][p][c]
         pending = None
-        if self.training and not bool(c.callibrated):
+        if self.training and not c.is_callibrated():
             pending = self._callibration_factors(x, kernel_basis, fk_op, edge_set)
         out = ops.fiber_conv(x, None, kernel_basis, fk_op, c.kernel.weight, c.bias, self.norm.weight, self.norm.bias,
                              self.linear_1.weight, self.linear_1.bias, self.linear_2.weight, self.linear_2.bias, edge_set)
