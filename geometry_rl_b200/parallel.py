@@ -85,6 +85,17 @@ class DataParallel:
             out[f"{k}_max"] = maxs[i]
         return out
 
+    def global_losses(self, out: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Logging view of a sharded TRPLLoss output: every `loss_*` entry is this rank's share (local sum / global
+        count, so that summed gradients are the global-mean gradients); their sum over ranks is the reference's value."""
+        keys = [k for k in out if k.startswith("loss_") or k == "actor_loss"]
+        t = torch.stack([out[k].detach() for k in keys])
+        self.all_reduce(t)
+        res = dict(out)
+        for i, k in enumerate(keys):
+            res[k] = t[i]
+        return res
+
     # ---- gradient exchange -----------------------------------------------------------------------------
     def allreduce_grads(self, params: Iterable[torch.nn.Parameter]):
         """ONE flat fp32 bucket, summed (losses already divide by the global count)."""
