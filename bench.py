@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dp-graph", action="store_true", help="also replay the data-parallel step (NCCL included) from a CUDA graph")
     ap.add_argument("--single-precision", action="store_true", help="skip the second (other precision) measurement")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="nn.Linear contractions of the message-passing kernels: fp32 FFMA (parity 1e-5) or bf16 tcgen05 "
@@ -233,7 +234,7 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
         return float(t[0])
 
     # ---- device-resident timing ----------------------------------------------------------------------
-    use_graph = (dp is None) and not args.no_graph
+    use_graph = not args.no_graph and (dp is None or args.dp_graph)
     launches_per_step = None
     if use_graph:
         c0 = _lib.launch_count

@@ -140,17 +140,30 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// (E2) spatial convolution forward: kern = basis Wk^T on the tensor core, message product + CSR-ordered sum
+// (E2) spatial convolution forward: kern = basis Wk^T on the tensor core, message product + CSR-ordered sum.
+// Persistent CTAs own CONTIGUOUS dst-node ranges holding equal shares of the edges (binary search in rowptr), so
+// the edge tiles of a CTA are consecutive 8-edge groups of the CSR: tile t+1's basis rows and gathered x_src rows
+// are fetched with cp.async into the other half of a 2-stage ring while tile t is multiplied and reduced, and the
+// edge indices are prefetched two tiles ahead in registers.
 // ---------------------------------------------------------------------------------------------------
 struct EdgeFwdTcSmem {
-  __nv_bfloat16 BZ[kTM * kC];   // basis tile image [8 chunks][128 rows][8]
-  __nv_bfloat16 Wkb[kC * kC];   // [8 chunks][64 rows c][8 j]
-  float XS[kTileFloats];        // gathered x_src rows, then messages in place
-  int src[kTE], dst[kTE];
+  __nv_bfloat16 BZ[2][kTM * kC];  // basis tile images [8 chunks][128 rows][8]
+  float XS[2][kTileFloats];       // gathered x_src rows, then messages in place
+  __nv_bfloat16 Wkb[kC * kC];     // [8 chunks][64 rows c][8 j]
+  int src[4][kTE], dst[4][kTE];   // 4-deep index ring: slot (t & 3) holds the edges of tile t
   uint64_t bar;
   uint32_t tmem_base;
 };
-constexpr int kNodesPerBlockTc = 16;
+
+// first node n in [0, n_nodes] with rowptr[n] >= target
+__device__ __forceinline__ int node_lower_bound(const int32_t* __restrict__ rowptr, int n_nodes, long long target) {
+  int lo = 0, hi = n_nodes;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)__ldg(rowptr + mid) < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 
 // basis rows of `cnt` consecutive edges (bf16, row-major in HBM) -> operand image, 16-byte cp.async pieces
 __device__ __forceinline__ void stage_basis_image(__nv_bfloat16* __restrict__ img, const __nv_bfloat16* __restrict__ src, int cnt) {
@@ -180,81 +193,102 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
   }
   if (warp == 0) tc::tmem_alloc(&s.tmem_base, 64);
   tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
+  // this CTA's node range: equal edge shares
+  const long long E = d.n_edges;
+  const int n_lo = blockIdx.x == 0 ? 0 : node_lower_bound(d.rowptr_dst, d.n_dst, E * blockIdx.x / gridDim.x);
+  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_dst : node_lower_bound(d.rowptr_dst, d.n_dst, E * (blockIdx.x + 1) / gridDim.x);
+  const int p0 = d.rowptr_dst[n_lo], p1 = d.rowptr_dst[n_hi];
+  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
+  const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);
+
+  // edge indices of tile t live in registers of threads 0..7 until they are published to s.src / s.dst
+  auto load_idx = [&](int t, int& es, int& ed) {
+    es = 0; ed = 0;
+    const int e = p0 + t * kTE + tid;
+    if (tid < kTE && t < n_tiles && e < p1) { es = __ldg(d.edge_src + e); ed = __ldg(d.edge_dst + e); }
+  };
+  auto stage = [&](int t, int buf) {  // requires index slot (t & 3) to be visible
+    const int cnt = min(kTE, p1 - (p0 + t * kTE));
+    stage_basis_image(s.BZ[buf], basis + (size_t)(p0 + t * kTE) * kRow, cnt);
+    stage_rows_gather(s.XS[buf], d.x_src, s.src[t & 3], cnt);
+  };
+  int es_a, ed_a, es_b, ed_b;  // a: tile t+2 (published in iteration t), b: tile t+3
+  load_idx(0, es_a, ed_a);
+  if (tid < kTE) { s.src[0][tid] = es_a; s.dst[0][tid] = ed_a; }
+  load_idx(1, es_a, ed_a);
+  if (tid < kTE) { s.src[1][tid] = es_a; s.dst[1][tid] = ed_a; }
+  load_idx(2, es_a, ed_a);
+  load_idx(3, es_b, ed_b);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t bz = tc::smem_u32(s.BZ), wk = tc::smem_u32(s.Wkb);
-  const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);
+  const uint32_t wk = tc::smem_u32(s.Wkb);
+  if (n_tiles > 0) stage(0, 0);
+  cp_async_commit();
+
   uint32_t parity = 0;
-  const int n_blocks = (d.n_dst + kNodesPerBlockTc - 1) / kNodesPerBlockTc;
-  for (int nb = blockIdx.x; nb < n_blocks; nb += gridDim.x) {
-    const int n0 = nb * kNodesPerBlockTc;
-    const int n1 = min(n0 + kNodesPerBlockTc, d.n_dst);
-    const int p0 = d.rowptr_dst[n0], p1 = d.rowptr_dst[n1];
-    int cur = n0;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = p0; base < p1; base += kTE) {
-      const int cnt = min(kTE, p1 - base);
-      __syncthreads();  // previous tile fully consumed
-      if (tid < kTE) {
-        s.src[tid] = (tid < cnt) ? d.edge_src[base + tid] : 0;
-        s.dst[tid] = (tid < cnt) ? d.edge_dst[base + tid] : 0;
-      }
-      stage_basis_image(s.BZ, basis + (size_t)base * kRow, cnt);
-      __syncthreads();  // s.src visible
-      stage_rows_gather(s.XS, d.x_src, s.src, cnt);
-      cp_async_commit();
-      cp_async_wait_all();
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        tc::issue_mma(tmem, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-        tc::mma_commit(&s.bar);
-      }
-      tc::mbar_wait(&s.bar, parity);
-      parity ^= 1u;
+  int cur = n_lo;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < n_tiles; ++t) {
+    const int buf = t & 1;
+    const int cnt = min(kTE, p1 - (p0 + t * kTE));
+    // publish the indices of tile t+2: slot (t+2)&3 was last read by tile t-2, two barriers ago
+    if (tid < kTE) { s.src[(t + 2) & 3][tid] = es_a; s.dst[(t + 2) & 3][tid] = ed_a; }
+    es_a = es_b; ed_a = ed_b;
+    load_idx(t + 4, es_b, ed_b);
+    __syncthreads();  // everyone is done reducing tile t-1: its data buffers (buf ^ 1) may be overwritten
+    if (t + 1 < n_tiles) stage(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();  // tile t has landed (this thread's copies); the barrier below makes it CTA-wide
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
       tc::tc_fence_after();
-      // messages in place: XS[row][c] *= kern[row][c]
+      tc::issue_mma(tmem, tc::view_k(tc::smem_u32(s.BZ[buf]), kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+      tc::mma_commit(&s.bar);
+    }
+    tc::mbar_wait(&s.bar, parity);
+    parity ^= 1u;
+    tc::tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 32 * ch + 16 * i;
-        float v[16];
-        tc::tmem_ld16(lane_addr + c0, v);
-        float* xs = s.XS + row * kLDT + c0;
+    for (int i = 0; i < 2; ++i) {  // messages in place: XS[row][c] *= kern[row][c]
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + c0, v);
+      float* xs = s.XS[buf] + row * kLDT + c0;
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          float4 x = ld4(xs + e);
-          x.x *= v[e]; x.y *= v[e + 1]; x.z *= v[e + 2]; x.w *= v[e + 3];
-          st4(xs + e, x);
-        }
-      }
-      tc::tc_fence_before();
-      __syncthreads();
-      // CSR-ordered segmented sum: thread (o, 4 channels) adds the edges of the tile sequentially
-#pragma unroll
-      for (int j = 0; j < kTE; ++j) {
-        if (j < cnt) {
-          const int dn = s.dst[j];
-          while (cur < dn) {
-            st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
-            sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            ++cur;
-          }
-          const float4 m = ld4(s.XS + (16 * j + o) * kLDT + 4 * cg);
-          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
-        }
+      for (int e = 0; e < 16; e += 4) {
+        float4 x = ld4(xs + e);
+        x.x *= v[e]; x.y *= v[e + 1]; x.z *= v[e + 2]; x.w *= v[e + 3];
+        st4(xs + e, x);
       }
     }
-    while (cur < n1) {
-      st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
-      sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      ++cur;
+    tc::tc_fence_before();
+    __syncthreads();
+    // CSR-ordered segmented sum: thread (o, 4 channels) adds the edges of the tile sequentially
+#pragma unroll
+    for (int j = 0; j < kTE; ++j) {
+      if (j < cnt) {
+        const int dn = s.dst[t & 3][j];
+        while (cur < dn) {
+          st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
+          sum = make_float4(0.f, 0.f, 0.f, 0.f);
+          ++cur;
+        }
+        const float4 m = ld4(s.XS[buf] + (16 * j + o) * kLDT + 4 * cg);
+        sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+      }
     }
   }
+  while (cur < n_hi) {
+    st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
+    sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    ++cur;
+  }
+  cp_async_wait_all();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
@@ -294,9 +328,8 @@ int grl_fbconv_edge_fwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
     cudaFuncSetAttribute(grl::fbconv_edge_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  const int n_blocks = (d->n_dst + grl::kNodesPerBlockTc - 1) / grl::kNodesPerBlockTc;
   int grid = 2 * grl::sm_count();
-  if (grid > n_blocks) grid = n_blocks;
+  if (grid > d->n_dst) grid = d->n_dst;
   grl::fbconv_edge_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_edge_fwd_tc");
 }

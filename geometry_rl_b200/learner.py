@@ -143,8 +143,8 @@ class Learner:
     def capture(self, example_batch, warmup: int = 3):
         """Capture `update` on static copies of `example_batch` (same shapes for every later batch).  The warm-up
         iterations are REAL updates (they also run the one-time calibration and build the topology cache)."""
-        if self.dp is not None:
-            raise RuntimeError("graph capture of the data-parallel step is not enabled (NCCL calls stay eager)")
+        # data-parallel: the NCCL all-reduces of the step are captured too (torch's ProcessGroupNCCL records them on the
+        # capture stream); every rank must capture and replay in lock-step
         self._static = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
