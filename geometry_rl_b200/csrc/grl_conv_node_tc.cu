@@ -12,6 +12,8 @@
 //   E  one thread issues GEMM2 (16 x tcgen05.mma, N = 64)                                        -> TMEM cols 256..319
 //   F  all warps: tcgen05.ld, + b2 + x_dst                                                        -> out (HBM)
 // The next tile's x1 is prefetched with cp.async while phase F streams the residual / output.
+#include <stdlib.h>
+
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
 
@@ -232,21 +234,286 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_fwd_tc_kernel(const G
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// v2: two independent tile pipelines per SM.
+// The v1 kernel above is issue / latency bound (ncu: smsp__issue_active 33 %, 8 warps per SM, every phase fenced
+// by a CTA barrier).  Here one 512-thread CTA per SM runs TWO 256-thread groups that walk alternate tiles with
+// their own buffers, mbarriers, TMEM columns and named barriers, sharing only the weight images, so one group's
+// MMA / TMEM / global-memory waits are covered by the other group's CUDA-core phases.  Further changes:
+//   * operands are fp16 (LayerNorm and GELU outputs are O(1); 11-bit mantissa instead of bf16's 8),
+//   * b1 rides in the contraction: K = 80 with y[:, 64:66] = 1 and W1[:, 64:66] = (hi, lo) fp16 split of b1,
+//   * GELU is evaluated two elements per instruction (HFMA2 / MUFU.TANH.F16, grl_tc.cuh gelu_h2),
+//   * D2 (GEMM2 accumulator) re-uses the first 64 TMEM columns of D1, so a group needs 256 columns.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kNF2Threads = 512;
+constexpr int kK1 = 80;  // GEMM1 contraction length: 64 channels + 2 bias columns + 14 zero columns
+
+struct NodeFwd2Group {
+  union {
+    struct {
+      float X1[kTM * kC];    // x1 tile, dense rows (phase A reads one row per warp: conflict-free)
+      float X2[kTM * kLDX];  // fibre conv output (phase B reads thread-pair-per-row: stride 72)
+    } x;
+    __half A1[kTM * kK1];    // y: [10 chunks][128 rows][8]   (aliases X1, dead after phase A)
+    __half A2[kTM * kH];     // hidden: [32 chunks][128 rows][8]   (aliases X1 + X2, dead after GEMM1)
+  } u;
+};
+
+struct NodeFwd2Smem {
+  __half W1h[kH * kK1];      // [10 chunks][256 rows][8]; chunk 8 = (b1 hi, b1 lo, 0 ...), chunk 9 = 0
+  __half W2h[kC * kH];       // [32 chunks][64 rows][8]
+  NodeFwd2Group g[2];
+  float b2[kC], bias[kC], lng[kC], lnb[kC];
+  uint64_t bar[2][2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void stage_x1_dense(float* __restrict__ X1, const float* __restrict__ src, int cnt, int gt) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = gt + 256 * i;  // float4 index 0..2047 of the [128][64] tile
+    float* d = X1 + 4 * f;
+    if ((f >> 8) < cnt) cp_async16(d, src + 4 * f);
+    else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <bool kAcc>
+__global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(const GrlConvDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NodeFwd2Smem& s = *reinterpret_cast<NodeFwd2Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int grp = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
+  NodeFwd2Group& G = s.g[grp];
+  const int bar_id = 1 + grp;
+
+  // ---- one-time setup (whole CTA) --------------------------------------------------------------------
+  if (tid == 0) {
+    tc::mbar_init(&s.bar[0][0], 1);
+    tc::mbar_init(&s.bar[0][1], 1);
+    tc::mbar_init(&s.bar[1][0], 1);
+    tc::mbar_init(&s.bar[1][1], 1);
+    tc::fence_mbar_init();
+  }
+  if (tid < 32) tc::tmem_alloc(&s.tmem_base, 512);
+  tc::stage_weight_f16(s.W1h, d.w1, kH, kC, kC);   // chunks 0..7 of W1h
+  tc::stage_weight_f16(s.W2h, d.w2, kC, kH, kH);
+  for (int n = tid; n < kH; n += kNF2Threads) {    // chunks 8 (bias split) and 9 (zero)
+    const float b = d.b1[n];
+    const __half hi = __float2half_rn(b);
+    const __half lo = __float2half_rn(b - __half2float(hi));
+    const __half z = __float2half_rn(0.f);
+    const __half2 h[4] = {__halves2half2(hi, lo), __halves2half2(z, z), __halves2half2(z, z), __halves2half2(z, z)};
+    *reinterpret_cast<uint4*>(s.W1h + ((size_t)8 * kH + n) * 8) = tc::pack_h8(h);
+    *reinterpret_cast<uint4*>(s.W1h + ((size_t)9 * kH + n) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < kC) { s.b2[tid] = d.b2[tid]; s.bias[tid] = d.bias[tid]; s.lng[tid] = d.ln_g[tid]; s.lnb[tid] = d.ln_b[tid]; }
+  // fibre kernel slice of this thread: channel fc, output orientations p = 4 pq .. 4 pq + 3, all 16 inputs o
+  const int fc = gt & 63, pq = gt >> 6;
+  float fk[kO][4];
+#pragma unroll
+  for (int o = 0; o < kO; ++o)
+#pragma unroll
+    for (int pi = 0; pi < 4; ++pi) fk[o][pi] = __ldg(d.fiber_kernel + ((size_t)(o * kO + 4 * pq + pi)) * kC + fc) * 0.0625f;
+
+  const int n_tiles = (d.n_dst + kTE - 1) / kTE;
+  const int tile_stride = 2 * gridDim.x;
+  int tile = 2 * blockIdx.x + grp;
+  if (tile < n_tiles) {
+    stage_x1_dense(G.u.x.X1, d.x1 + (size_t)tile * kTE * kRow, min(kTE, d.n_dst - tile * kTE), gt);
+    cp_async_commit();
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base + 256u * grp;
+  const uint32_t a1_addr = tc::smem_u32(G.u.A1), a2_addr = tc::smem_u32(G.u.A2);
+  const uint32_t w1_addr = tc::smem_u32(s.W1h), w2_addr = tc::smem_u32(s.W2h);
+  const int q = gw & 3, hh = gw >> 2;
+  const int row = 32 * q + lane;
+  const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  uint32_t parity = 0;
+
+  for (; tile < n_tiles; tile += tile_stride) {
+    const int n0 = tile * kTE;
+    cp_async_wait_all();
+    tc::group_sync(bar_id, 256);  // X1 of this tile visible to the group
+
+    // ---- A: fibre convolution + bias -------------------------------------------------------------
+    {
+      const float bias_c = s.bias[fc];
+#pragma unroll 2
+      for (int j = 0; j < kTE; ++j) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int o = 0; o < kO; ++o) {
+          const float x = G.u.x.X1[(16 * j + o) * kC + fc];
+          a0 = fmaf(x, fk[o][0], a0);
+          a1 = fmaf(x, fk[o][1], a1);
+          a2 = fmaf(x, fk[o][2], a2);
+          a3 = fmaf(x, fk[o][3], a3);
+        }
+        float* o2 = G.u.x.X2 + (16 * j + 4 * pq) * kLDX + fc;
+        o2[0 * kLDX] = a0 + bias_c;
+        o2[1 * kLDX] = a1 + bias_c;
+        o2[2 * kLDX] = a2 + bias_c;
+        o2[3 * kLDX] = a3 + bias_c;
+      }
+    }
+    tc::group_sync(bar_id, 256);
+
+    // ---- B: LayerNorm over the 64 channels of a row; thread pair (row r, half h) -> fp16 operand A1 ------
+    {
+      const int r = gt >> 1, h = gt & 1;
+      float4 v[8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = ld4(G.u.x.X2 + r * kLDX + 4 * (2 * i + h));
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      const float mean = sum * (1.0f / 64.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      const float rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = 4 * (2 * i + h);  // channels c..c+3 = half `h` of 16-byte chunk i
+        const float4 g = ld4(s.lng + c), b = ld4(s.lnb + c);
+        const __half2 p0 = __floats2half2_rn(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
+        const __half2 p1 = __floats2half2_rn(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+        *reinterpret_cast<uint2*>(G.u.A1 + ((size_t)i * kTM + r) * 8 + 4 * h) = pk;
+      }
+      // chunk 8 = (1, 1, 0 ...) multiplies the (hi, lo) bias columns of W1h; chunk 9 = 0
+      *reinterpret_cast<uint4*>(G.u.A1 + ((size_t)(8 + h) * kTM + r) * 8) = make_uint4(h == 0 ? 0x3C003C00u : 0u, 0u, 0u, 0u);
+    }
+    // ---- C: GEMM1  D1[128 x 256] = [y | 1 1 0..] [W1 | b1_hi b1_lo 0..]^T ------------------------------
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    tc::group_sync(bar_id, 256);
+    if (gt == 0) {
+      tc::tc_fence_after();
+      tc::issue_mma(tmem, tc::view_k(a1_addr, kTM), tc::view_k(w1_addr, kH), tc::idesc_f16_ex(128, kH, 0, 0, 0, 0), kK1 / 16, false);
+      tc::mma_commit(&s.bar[grp][0]);
+    }
+    // ---- D: hidden = GELU(D1) -> A2 (aliases X1 / X2 / A1, which nobody reads any more) ----------------
+    tc::mbar_wait(&s.bar[grp][0], parity);
+    tc::tc_fence_after();
+    {
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int c0 = 128 * hh + 16 * i;
+        float v[16];
+        tc::tmem_ld16(lane_addr + c0, v);
+        __half2 h0[4], h1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h0[e] = tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]));
+          h1[e] = tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]));
+        }
+        *reinterpret_cast<uint4*>(G.u.A2 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack_h8(h0);
+        *reinterpret_cast<uint4*>(G.u.A2 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack_h8(h1);
+      }
+    }
+    // ---- E: GEMM2  D2[128 x 64] = hidden W2^T  (into the first 64 columns of D1: every D1 read is done) ----
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    tc::group_sync(bar_id, 256);
+    if (gt == 0) {
+      tc::tc_fence_after();
+      tc::issue_mma(tmem, tc::view_k(a2_addr, kTM), tc::view_k(w2_addr, kC), tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), kH / 16, false);
+      tc::mma_commit(&s.bar[grp][1]);
+    }
+    // x_dst of this thread's two 16-column pieces: issued BEFORE the wait so the DRAM round trip hides behind GEMM2
+    // (ncu r02: with the loads inside the epilogue, 45 % of the stall samples sat on their first use)
+    const int node = n0 + (row >> 4);
+    const bool live = node < d.n_dst;
+    const size_t off = (size_t)(live ? node : 0) * kRow + (row & 15) * kC + 32 * hh;
+    float4 xd[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xd[e] = ldg4(d.x_dst + off + 4 * e);
+    if (kAcc) {  // HeteroConv group "sum": out already holds the other edge type's result
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 old = ldg4(d.out + off + 4 * e);
+        xd[e].x += old.x; xd[e].y += old.y; xd[e].z += old.z; xd[e].w += old.w;
+      }
+    }
+    tc::mbar_wait(&s.bar[grp][1], parity);
+    tc::tc_fence_after();
+    // A2 (= X1 / X2) is free again: prefetch the group's next tile while the epilogue streams out
+    {
+      const int nt = tile + tile_stride;
+      if (nt < n_tiles) {
+        stage_x1_dense(G.u.x.X1, d.x1 + (size_t)nt * kTE * kRow, min(kTE, d.n_dst - nt * kTE), gt);
+        cp_async_commit();
+      }
+    }
+    // ---- F: out = x_dst + D2 + b2 -------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float v[16];
+      tc::tmem_ld16(lane_addr + 32 * hh + 16 * i, v);
+      if (live) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 bb = ld4(s.b2 + 32 * hh + 16 * i + 4 * e);
+          const float4 x = xd[4 * i + e];
+          st4(d.out + off + 16 * i + 4 * e, make_float4(x.x + (v[4 * e] + bb.x), x.y + (v[4 * e + 1] + bb.y),
+                                                       x.z + (v[4 * e + 2] + bb.z), x.w + (v[4 * e + 3] + bb.w)));
+        }
+      }
+    }
+    tc::tc_fence_before();  // TMEM reads of this tile ordered before the group's next MMAs (after its next barrier)
+    parity ^= 1u;
+  }
+  cp_async_wait_all();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tc::tmem_dealloc(s.tmem_base, 512);
+}
+
 }  // namespace grl
 
 extern "C" int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d && d->n_dst > 0, GRL_EINVAL, "grl_fbconv_node_fwd_tc: bad descriptor");
   GRL_REQUIRE(d->x1 && d->fiber_kernel && d->bias && d->ln_g && d->ln_b && d->w1 && d->b1 && d->w2 && d->b2 && d->x_dst &&
                   d->out, GRL_EINVAL, "grl_fbconv_node_fwd_tc: null pointer");
-  static bool attr = false;
-  const int smem = (int)sizeof(grl::NodeTcSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::fbconv_node_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
   const int n_tiles = (d->n_dst + grl::kTE - 1) / grl::kTE;
+  static const bool use_v1 = getenv("GRL_NODE_FWD_V1") != nullptr;
+  if (use_v1) {
+    static bool attr = false;
+    const int smem = (int)sizeof(grl::NodeTcSmem);
+    if (!attr) {
+      cudaFuncSetAttribute(grl::fbconv_node_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr = true;
+    }
+    int grid = grl::sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    grl::fbconv_node_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+    return grl::check_launch("grl_fbconv_node_fwd_tc");
+  }
+  static bool attr2 = false;
+  const int smem2 = (int)sizeof(grl::NodeFwd2Smem);
+  if (!attr2) {
+    cudaFuncSetAttribute(grl::fbconv_node_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    cudaFuncSetAttribute(grl::fbconv_node_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    attr2 = true;
+  }
   int grid = grl::sm_count();
-  if (grid > n_tiles) grid = n_tiles;
-  grl::fbconv_node_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  if (2 * grid > n_tiles) grid = (n_tiles + 1) / 2;
+  if (d->accumulate_out) grl::fbconv_node_fwd_tc2_kernel<true><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d);
+  else grl::fbconv_node_fwd_tc2_kernel<false><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_node_fwd_tc");
 }

@@ -17,51 +17,68 @@ __device__ __forceinline__ void embed_stage(const GrlEmbedDesc& d, int n0, int c
   for (int i = threadIdx.x; i < cnt * V3; i += kThreads) vc[i] = d.vectors[(size_t)n0 * V3 + i];
 }
 
-// features of (staged node j, orientation o): scalars, then <v, ori_o> for every vector
+// Features of (staged node j, orientation o) -> feat[j][o][0..15] in shared memory (entries >= S + V are zero).
+// One (j, o) pair per thread: the 16 channel-group threads of an orientation then share the row by broadcast
+// loads instead of each recomputing it.
 __device__ __forceinline__ void embed_features(const GrlEmbedDesc& d, const float* __restrict__ sc, const float* __restrict__ vc,
-                                               int j, float ox, float oy, float oz, float (&feat)[kMaxF]) {
+                                               int cnt, float* __restrict__ feat) {
   const int S = d.n_scalars, V = d.n_vectors;
+  const int j = threadIdx.x >> 4, o = threadIdx.x & 15;
+  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+  float f[kMaxF];
 #pragma unroll
-  for (int f = 0; f < kMaxF; ++f) {
+  for (int i = 0; i < kMaxF; ++i) {
     float v = 0.f;
-    if (f < S) {
-      v = sc[j * S + f];
-    } else if (f < S + V) {
-      const float* p = vc + (j * V + (f - S)) * 3;
-      v = (p[0] * ox + p[1] * oy) + ((d.dim == 3) ? p[2] * oz : 0.f);
+    if (j < cnt) {
+      if (i < S) {
+        v = sc[j * S + i];
+      } else if (i < S + V) {
+        const float* p = vc + (j * V + (i - S)) * 3;
+        v = (p[0] * ox + p[1] * oy) + ((d.dim == 3) ? p[2] * oz : 0.f);
+      }
     }
-    feat[f] = v;
+    f[i] = v;
   }
+  float* dst = feat + (j * kO + o) * kMaxF;
+#pragma unroll
+  for (int i = 0; i < kMaxF; i += 4) st4(dst + i, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
 }
 
-__global__ void __launch_bounds__(kThreads) embed_fwd_kernel(const GrlEmbedDesc d) {
-  __shared__ __align__(16) float Wt[kMaxF * kC];  // Wt[f][c] = W[c][f]
+__global__ void __launch_bounds__(kThreads, 2) embed_fwd_kernel(const GrlEmbedDesc d) {
+  __shared__ __align__(16) float feat[kEmbTile * kO * kMaxF];
   __shared__ float sc[kEmbTile * kMaxF], vc[kEmbTile * kMaxF * 3];
   const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
-  const int F = d.n_scalars + d.n_vectors;
-  for (int i = tid; i < kMaxF * kC; i += kThreads) {
-    const int f = i / kC, c = i % kC;
-    Wt[i] = (f < F) ? d.weight[c * F + f] : 0.f;
-  }
-  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+  const int F = d.n_scalars + d.n_vectors, Fq = (F + 3) >> 2;
+  float w[kMaxF][4];  // w[f][i] = W[4 cg + i][f]
+#pragma unroll
+  for (int f = 0; f < kMaxF; ++f)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[f][i] = (f < F) ? __ldg(d.weight + (size_t)(4 * cg + i) * F + f) : 0.f;
   const int n_tiles = (d.n_nodes + kEmbTile - 1) / kEmbTile;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int n0 = t * kEmbTile, cnt = min(kEmbTile, d.n_nodes - n0);
     __syncthreads();
     embed_stage(d, n0, cnt, sc, vc);
     __syncthreads();
+    embed_features(d, sc, vc, cnt, feat);
+    __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
-      float feat[kMaxF];
-      embed_features(d, sc, vc, j, ox, oy, oz, feat);
+      const float* fr = feat + (j * kO + o) * kMaxF;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int f = 0; f < kMaxF; ++f) {
-        const float4 w = ld4(Wt + f * kC + 4 * cg);
-        a.x = fmaf(feat[f], w.x, a.x);
-        a.y = fmaf(feat[f], w.y, a.y);
-        a.z = fmaf(feat[f], w.z, a.z);
-        a.w = fmaf(feat[f], w.w, a.w);
+      for (int qd = 0; qd < kMaxF / 4; ++qd) {
+        if (qd < Fq) {
+          const float4 fv = ld4(fr + 4 * qd);
+          const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            a.x = fmaf(fe[e], w[4 * qd + e][0], a.x);
+            a.y = fmaf(fe[e], w[4 * qd + e][1], a.y);
+            a.z = fmaf(fe[e], w[4 * qd + e][2], a.z);
+            a.w = fmaf(fe[e], w[4 * qd + e][3], a.w);
+          }
+        }
       }
       st4(d.x + (size_t)(n0 + j) * kRow + o * kC + 4 * cg, a);
     }
@@ -70,11 +87,10 @@ __global__ void __launch_bounds__(kThreads) embed_fwd_kernel(const GrlEmbedDesc 
 
 // gW[c][f] = sum_{n,o} grad_x[n][o][c] feat[n][o][f]; per-CTA partial, cross-o reduction through smem.
 __global__ void __launch_bounds__(kThreads, 2) embed_bwd_kernel(const GrlEmbedDesc d) {
-  __shared__ __align__(16) float red[kO * kC];
+  __shared__ __align__(16) float feat[kEmbTile * kO * kMaxF];  // re-used as the reduction buffer at the end
   __shared__ float sc[kEmbTile * kMaxF], vc[kEmbTile * kMaxF * 3];
   const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
-  const int F = d.n_scalars + d.n_vectors;
-  const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
+  const int F = d.n_scalars + d.n_vectors, Fq = (F + 3) >> 2;
   float g[kMaxF][4];
 #pragma unroll
   for (int f = 0; f < kMaxF; ++f) g[f][0] = g[f][1] = g[f][2] = g[f][3] = 0.f;
@@ -84,21 +100,30 @@ __global__ void __launch_bounds__(kThreads, 2) embed_bwd_kernel(const GrlEmbedDe
     __syncthreads();
     embed_stage(d, n0, cnt, sc, vc);
     __syncthreads();
+    embed_features(d, sc, vc, cnt, feat);
+    __syncthreads();
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
       const float4 gx = ldg4(d.grad_x + (size_t)(n0 + j) * kRow + o * kC + 4 * cg);
-      float feat[kMaxF];
-      embed_features(d, sc, vc, j, ox, oy, oz, feat);
+      const float* fr = feat + (j * kO + o) * kMaxF;
 #pragma unroll
-      for (int f = 0; f < kMaxF; ++f) {
-        g[f][0] = fmaf(gx.x, feat[f], g[f][0]);
-        g[f][1] = fmaf(gx.y, feat[f], g[f][1]);
-        g[f][2] = fmaf(gx.z, feat[f], g[f][2]);
-        g[f][3] = fmaf(gx.w, feat[f], g[f][3]);
+      for (int qd = 0; qd < kMaxF / 4; ++qd) {
+        if (qd < Fq) {
+          const float4 fv = ld4(fr + 4 * qd);
+          const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            g[4 * qd + e][0] = fmaf(gx.x, fe[e], g[4 * qd + e][0]);
+            g[4 * qd + e][1] = fmaf(gx.y, fe[e], g[4 * qd + e][1]);
+            g[4 * qd + e][2] = fmaf(gx.z, fe[e], g[4 * qd + e][2]);
+            g[4 * qd + e][3] = fmaf(gx.w, fe[e], g[4 * qd + e][3]);
+          }
+        }
       }
     }
   }
   float* P = d.grad_weight_partials + (size_t)blockIdx.x * kC * F;
+  float* red = feat;  // [16 o][64 c]
 #pragma unroll
   for (int f = 0; f < kMaxF; ++f) {
     if (f < F) {

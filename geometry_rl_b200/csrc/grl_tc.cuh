@@ -11,6 +11,7 @@
 // Accumulators: M = 128 rows <-> the 128 TMEM lanes, one fp32 column per output column.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -69,6 +70,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor: D fp32, A/B bf16, both K-major, dense (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 takes fp16 or bf16 per operand (format bits 7-9 for A, 10-12 for B: 0 = fp16, 1 = bf16)
+__host__ __device__ constexpr uint32_t idesc_f16_ex(int M, int N, int a_mn, int b_mn, int a_bf16, int b_bf16) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- MMA issue (ONE thread) ----------------------------------------------------------------------------
@@ -156,6 +163,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- named barrier for a sub-group of the CTA (id 1..15, `count` threads, multiple of 32) -----------------------
+__device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// ---- packed fp16 GELU (tanh form) for the activation epilogues ------------------------------------------------
+// The epilogues are issue-bound on the activation; HFMA2 / MUFU.TANH.F16 evaluate two elements per instruction and
+// the result is an fp16 MMA operand anyway (11-bit mantissa: finer than the bf16 operands of the other contractions).
+__device__ __forceinline__ __half2 tanh_h2(__half2 x) {
+  uint32_t r;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&x)));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+  const __half2 k = __floats2half2_rn(0.7978845608028654f, 0.7978845608028654f);
+  const __half2 kc = __floats2half2_rn(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const __half2 half = __floats2half2_rn(0.5f, 0.5f);
+  const __half2 t = tanh_h2(__hmul2(x, __hfma2(__hmul2(x, x), kc, k)));
+  const __half2 hx = __hmul2(x, half);
+  return __hfma2(hx, t, hx);
+}
+// value and derivative: dy = 0.5 (1 + t) + 0.5 x (1 - t^2) (k + 3 kc x^2)
+__device__ __forceinline__ void gelu_h2(__half2 x, __half2& y, __half2& dy) {
+  const __half2 k = __floats2half2_rn(0.7978845608028654f, 0.7978845608028654f);
+  const __half2 kc = __floats2half2_rn(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const __half2 k3 = __floats2half2_rn(3.0f * 0.7978845608028654f * 0.044715f, 3.0f * 0.7978845608028654f * 0.044715f);
+  const __half2 half = __floats2half2_rn(0.5f, 0.5f), one = __floats2half2_rn(1.0f, 1.0f);
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 t = tanh_h2(__hmul2(x, __hfma2(x2, kc, k)));
+  const __half2 hx = __hmul2(x, half);
+  y = __hfma2(hx, t, hx);
+  dy = __hfma2(__hmul2(hx, __hfma2(__hneg2(t), t, one)), __hfma2(x2, k3, k), __hfma2(t, half, half));
+}
+__device__ __forceinline__ uint4 pack_h8(const __half2 (&h)[4]) {
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&h[0]);
+  o.y = *reinterpret_cast<const uint32_t*>(&h[1]);
+  o.z = *reinterpret_cast<const uint32_t*>(&h[2]);
+  o.w = *reinterpret_cast<const uint32_t*>(&h[3]);
+  return o;
+}
+
 // ---- operand staging helpers -----------------------------------------------------------------------------
 // address (in bf16 elements) of element (row, k) of a tile with `rows` rows in the chunked layout
 __device__ __forceinline__ int op_index(int rows, int row, int k) { return ((k >> 3) * rows + row) * 8 + (k & 7); }
@@ -183,6 +230,19 @@ __device__ __forceinline__ void stage_weight_bf16(__nv_bfloat16* dst, const floa
     const float4 hi = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + kc * 8 + 4));
     const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     *reinterpret_cast<uint4*>(dst + ((size_t)kc * rows + row) * 8) = pack8(v);
+  }
+}
+
+// fp16 variant of stage_weight_bf16 (same [K/8][rows][8] image)
+__device__ __forceinline__ void stage_weight_f16(__half* dst, const float* __restrict__ src, int rows, int K, int ld) {
+  const int n_chunks = rows * (K >> 3);
+  for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
+    const int row = i % rows, kc = i / rows;
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + kc * 8));
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld + kc * 8 + 4));
+    const __half2 h[4] = {__floats2half2_rn(lo.x, lo.y), __floats2half2_rn(lo.z, lo.w), __floats2half2_rn(hi.x, hi.y),
+                          __floats2half2_rn(hi.z, hi.w)};
+    *reinterpret_cast<uint4*>(dst + ((size_t)kc * rows + row) * 8) = pack_h8(h);
   }
 }
 

@@ -61,14 +61,14 @@ def test_fiber_conv_bf16_tensor_core_path_within_1e_2(B, n_per):
     assert err > 0, "bf16 path returned the fp32 result bit-for-bit: tensor-core kernel not exercised"
 
 
-def _idesc(M, N, a_mn=0, b_mn=0):
-    return (1 << 4) | (1 << 7) | (1 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+def _idesc(M, N, a_mn=0, b_mn=0, a_bf16=1, b_bf16=1):
+    return (1 << 4) | (a_bf16 << 7) | (b_bf16 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
 
 
-def _chunked(X):
-    """[rows][cols] -> the library's operand image [cols/8][rows][8] bf16."""
+def _chunked(X, dtype=torch.bfloat16):
+    """[rows][cols] -> the library's operand image [cols/8][rows][8] (bf16 or fp16)."""
     r, c = X.shape
-    return X.bfloat16().reshape(r, c // 8, 8).permute(1, 0, 2).contiguous().cuda()
+    return X.to(dtype).reshape(r, c // 8, 8).permute(1, 0, 2).contiguous().cuda()
 
 
 def _debug_mma(a_img, b_img, N, n_ksteps, a_desc, b_desc, idesc):
@@ -102,6 +102,23 @@ def test_tcgen05_transposed_operands_share_the_same_image():
     kmaj = (128 * 16, 128, 2 * 128 * 16)
     D = _debug_mma(_chunked(A), _chunked(W), 64, 128 // 16, kmaj, mn, _idesc(128, 64, 0, 1))
     ref = A.bfloat16().float() @ W.bfloat16().float()
+    assert float((D - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("a_bf16,b_bf16", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("N,K", [(64, 64), (80, 80), (256, 80)])
+def test_tcgen05_kind_f16_operand_formats(a_bf16, b_bf16, N, K):
+    """kind::f16 with fp16 operands (the forward node kernel stages LayerNorm / GELU outputs as fp16; gradients stay
+    bf16) and N = 80 / K = 80 shapes (bias folded into the contraction as an extra K chunk, bias gradient as an extra
+    N chunk).  A and B must share one format: measured on B200, fp16 x bf16 raises an illegal-instruction error."""
+    g = torch.Generator().manual_seed(17 + N)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ta = torch.bfloat16 if a_bf16 else torch.float16
+    tb = torch.bfloat16 if b_bf16 else torch.float16
+    D = _debug_mma(_chunked(A, ta), _chunked(B, tb), N, K // 16, (128 * 16, 128, 2 * 128 * 16), (N * 16, 128, 2 * N * 16),
+                   _idesc(128, N, 0, 0, a_bf16, b_bf16))
+    ref = A.to(ta).float() @ B.to(tb).float().t()
     assert float((D - ref).abs().max() / ref.abs().max()) < 1e-5
 
 
