@@ -42,7 +42,7 @@ class GrlConvDesc(C.Structure):
                 ("grad_out", _fp), ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp),
                 ("grad_basis", _fp), ("accumulate_grad_basis", _i32), ("node_grad_partials", _fp),
                 ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp),
-                ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp)]
+                ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp), ("grad_amax", _fp)]
 
 
 class GrlProjDesc(C.Structure):
@@ -75,6 +75,7 @@ SIGNATURES = {
     "grl_fbconv_edge_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_edge_basis_bwd_tc": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
     "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_absmax": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),
     "grl_trpl_fwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),

@@ -338,6 +338,11 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
 
   for (; tile < n_tiles; tile += tile_stride) {
     const int n0 = tile * kTE;
+    if (gt == 0) {  // L2 prefetch: this tile's residual rows (read before the GEMM2 wait) and the group's next x1 tile
+      tc::prefetch_l2(d.x_dst + (size_t)n0 * kRow, (uint32_t)min(kTE, d.n_dst - n0) * kRow * 4u);
+      const int nt = tile + tile_stride;
+      if (nt < n_tiles) tc::prefetch_l2(d.x1 + (size_t)nt * kTE * kRow, (uint32_t)min(kTE, d.n_dst - nt * kTE) * kRow * 4u);
+    }
     cp_async_wait_all();
     tc::group_sync(bar_id, 256);  // X1 of this tile visible to the group
 

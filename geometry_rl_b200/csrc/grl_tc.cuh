@@ -163,6 +163,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- L2 prefetch of a contiguous global range (bytes: multiple of 16) issued by ONE thread -----------------------
+// Pulls a tile that will be read a few microseconds later (by LDG or cp.async) into L2, so that the later access pays
+// an L2 hit instead of a DRAM round trip; no shared memory or registers are tied up while the data is in flight.
+__device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ---- named barrier for a sub-group of the CTA (id 1..15, `count` threads, multiple of 32) -----------------------
 __device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -219,6 +226,30 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   o.z = *reinterpret_cast<uint32_t*>(&c);
   o.w = *reinterpret_cast<uint32_t*>(&d);
   return o;
+}
+
+// pack 8 floats into 8 fp16 (16 bytes)
+__device__ __forceinline__ uint4 pack8_h(const float* v) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  const __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&a);
+  o.y = *reinterpret_cast<const uint32_t*>(&b);
+  o.z = *reinterpret_cast<const uint32_t*>(&c);
+  o.w = *reinterpret_cast<const uint32_t*>(&d);
+  return o;
+}
+
+// Gradient scale for fp16 gradient operands: gradients are multiplied by a power of two chosen from the tensor's
+// absolute maximum (grl_absmax) so that max |g * scale| lies in [32, 64): every element within 2^-20 of the maximum
+// keeps fp16's 11-bit mantissa (bf16 keeps 8), products stay far below 65504, and the power of two is removed
+// exactly in the epilogues.  amax_bits = bit pattern of the (non-negative) maximum; 0 / inf / nan -> scale 1.
+__device__ __forceinline__ float grad_scale_from_amax(uint32_t amax_bits) {
+  const int e = (int)((amax_bits >> 23) & 0xFFu);      // biased exponent: amax in [2^(e-127), 2^(e-126))
+  if (e == 0 || e == 255) return 1.0f;
+  int k = 127 + 5 - (e - 127);                         // scale = 2^(5 - (e - 127))  ->  amax * scale in [32, 64)
+  k = k < 1 ? 1 : (k > 254 ? 254 : k);
+  return __uint_as_float((uint32_t)k << 23);
 }
 
 // Stage a [rows][K] fp32 row-major GLOBAL matrix (weights) as a bf16 operand tile. Whole CTA cooperates.

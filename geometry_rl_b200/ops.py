@@ -5,6 +5,7 @@ autograd graph.  All arithmetic on latents / edges happens inside libgrl_b200.so
 eager fallback — tensors must live on a CUDA device.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -18,6 +19,8 @@ ROW = 16 * 64
 #   "fp32": FFMA kernels, parity 1e-5 against the reference's fp32 CPU results (default)
 #   "bf16": tcgen05 tensor-core kernels, bf16 operands / fp32 accumulation, parity 1e-2
 _PRECISION = "fp32"
+# debugging aid for error attribution: which halves of the bf16 path use the tensor-core kernels ("node", "edge")
+_TC_PARTS = set(os.environ.get("GRL_TC_PARTS", "node,edge").split(","))
 
 
 def set_precision(mode: str):
@@ -193,7 +196,7 @@ class EdgeBasisFn(torch.autograd.Function):
         w1t[:14] = w1.detach().t()
         w2t = w2.detach().t().contiguous()
         b1c, b2c = _f32c(b1.detach()), _f32c(b2.detach())
-        bf16 = _PRECISION == "bf16"
+        bf16 = _PRECISION == "bf16" and "edge" in _TC_PARTS
         basis = torch.empty(es.n_edges, 16, 64, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
         d = L.GrlBasisDesc(n_edges=es.n_edges, dim=dim, edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst),
                            pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1t=L.ptr(w1t), b1=L.ptr(b1c),
@@ -245,7 +248,7 @@ class FiberConvFn(torch.autograd.Function):
         homo = x_dst is None
         x_src = _f32c(x_src)
         xd = x_src if homo else _f32c(x_dst)
-        precision = _PRECISION
+        precision = _PRECISION if "node" in _TC_PARTS else "fp32"
         basis_in_dtype = basis.dtype
         basis = basis.contiguous() if (precision == "bf16" and basis.dtype == torch.bfloat16) else _f32c(basis)
         fk = _f32c(fk)
@@ -312,7 +315,9 @@ class FiberConvFn(torch.autograd.Function):
         shape = (es.n_src, es.n_dst, es.n_edges)
         if ctx.precision == "bf16":
             g_x2 = torch.empty_like(x1)
-            d.w2, d.grad_x2 = L.ptr(w2_rm), L.ptr(g_x2)
+            amax = torch.empty(1, dtype=torch.int32, device=dev)  # bit pattern of max |grad_out| (fp16 gradient scale)
+            L.call("grl_absmax", L.ptr(g_out), g_out.numel(), L.ptr(amax), shape=shape)
+            d.w2, d.grad_x2, d.grad_amax = L.ptr(w2_rm), L.ptr(g_x2), L.ptr(amax)
             L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=shape)
         else:
             L.call("grl_fbconv_node_bwd", C.byref(d), shape=shape)

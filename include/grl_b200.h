@@ -181,6 +181,8 @@ typedef struct {
   const void* basis_bf16;    /* [E][16][64] bf16 (edge order)                                       */
   void* grad_basis_bf16;     /* [E][16][64] bf16                                                    */
   float* grad_x2;            /* [n_dst][16][64] workspace: gradient w.r.t. the pre-LayerNorm tensor   */
+  const uint32_t* grad_amax; /* grl_absmax(grad_out): the tensor-core backward stages gradients as fp16 scaled by a
+                                power of two derived from it (max |g| -> [32, 64)); NULL = scale 1          */
 } GrlConvDesc;
 /* node partial layout: gW1[256][64] | gb1[256] | gW2[64][256] | gb2[64] | g_ln_g[64] | g_ln_b[64]
  *                      | g_bias[64] | g_fk[16][16][64] */
@@ -199,6 +201,9 @@ int grl_fbconv_edge_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);   /* grad
 int grl_edge_basis_bwd_tc(const GrlBasisDesc* d, grl_stream_t stream);   /* grad_basis_bf16 -> basis_fn partials */
 /* grad_out -> grad_x1 + node partials (two launches: tensor-core MLP/LayerNorm backward, fp32 fibre backward) */
 int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);
+
+/* *out_bits = bit pattern of max_i |x[i]| (NaNs ignored); feeds GrlConvDesc.grad_amax.  x must be 16-byte aligned. */
+int grl_absmax(const float* x, int64_t n, uint32_t* out_bits, grl_stream_t stream);
 
 /* out[i] = sum_p partials[p][i], fixed order (deterministic cross-CTA reduction). */
 int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,
