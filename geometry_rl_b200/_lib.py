@@ -42,7 +42,7 @@ class GrlConvDesc(C.Structure):
                 ("grad_out", _fp), ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp),
                 ("grad_basis", _fp), ("accumulate_grad_basis", _i32), ("node_grad_partials", _fp),
                 ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp),
-                ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp), ("grad_amax", _fp)]
+                ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp), ("x2", _fp), ("grad_amax", _fp)]
 
 
 class GrlProjDesc(C.Structure):

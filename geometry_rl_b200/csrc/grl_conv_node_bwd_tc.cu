@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
 //   * GELU and GELU' are evaluated two elements per instruction in packed fp16 (gelu_h2); h and dG stay packed.
 //   * grad_out is loaded into registers at the top of the tile (used after the fibre phase); the next tile's x1 /
 //     grad_out are pulled into L2 one tile ahead.
-//   * fibre recompute: thread = (channel, pair of output orientations), fk[16][2] stays in registers.
+//   * no fibre recompute: the forward kernel saves the pre-LayerNorm tensor x2 (GrlConvDesc.x2) and this kernel
+//     streams it back with cp.async (the fibre phase was 20 % of the stall samples of the recomputing version);
+//   * half 0 never waits on its gY / dW MMAs: the tensor pipe retires MMAs in issue order, so the next wait covers them.
 // TMEM columns: D 0..127 | gY 128..191 | dW1 192..351 (2 x 80) | dW2^T 352..479 (2 x 64).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kNB2Threads = 512;
@@ -396,10 +398,7 @@ struct NodeBwd2Smem {
   __half A1[kTM * kKb];     // y: [10 chunks][128 rows][8]; chunk 8 = (1, 1, 0 ...), chunk 9 = 0 (written once)
   __half GZh[kTM * kC];     // scaled grad_out [8 chunks][128 rows][8]
   union {
-    struct {
-      float X1[kTM * kC];       // x1 tile, dense rows (phase A only)
-      float X2[kTM * kLDX2];    // pre-LayerNorm x2 (phases A, B)
-    } x;
+    float X2[kTM * kLDX2];      // pre-LayerNorm x2 tile (saved by the forward kernel), phase B only
     struct {
       __half A2h[kTM * 128];    // h           half: [16 chunks][128 rows][8]
       __half AP[kTM * 128];     // scaled gPre half: [16 chunks][128 rows][8]
@@ -465,30 +464,21 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
   }
   const float gscale = d.grad_amax ? tc::grad_scale_from_amax(__ldg(d.grad_amax)) : 1.0f;
   const float inv_gscale = 1.0f / gscale;  // exact: gscale is a power of two
-  // fibre kernel slice: channel fc, output orientations 2 pp, 2 pp + 1, all 16 inputs (pre-scaled by 1/16)
-  const int fc = tid & 63, pp = tid >> 6;
-  float fk[kO][2];
-#pragma unroll
-  for (int o = 0; o < kO; ++o) {
-    fk[o][0] = __ldg(d.fiber_kernel + ((size_t)(o * kO + 2 * pp)) * kC + fc) * 0.0625f;
-    fk[o][1] = __ldg(d.fiber_kernel + ((size_t)(o * kO + 2 * pp + 1)) * kC + fc) * 0.0625f;
-  }
-
   const int n_tiles = (d.n_dst + kTE - 1) / kTE;
   int tile = blockIdx.x;
-  auto stage_x1 = [&](int t) {
+  auto stage_x2 = [&](int t) {  // x2 rows of tile t -> X2 (row stride kLDX2), 16-byte cp.async pieces
     const int cnt = min(kTE, d.n_dst - t * kTE);
-    const float* src = d.x1 + (size_t)t * kTE * kRow;
+    const float* src = d.x2 + (size_t)t * kTE * kRow;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int f = tid + kNB2Threads * i;  // float4 index 0..2047 of the dense [128][64] tile
-      float* dp = s.u.x.X1 + 4 * f;
+      const int f = tid + kNB2Threads * i;  // float4 index 0..2047 of the [128][64] tile
+      float* dp = s.u.X2 + (f >> 4) * kLDX2 + 4 * (f & 15);
       if ((f >> 8) < cnt) cp_async16(dp, src + 4 * f);
       else *reinterpret_cast<float4*>(dp) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   if (tile < n_tiles) {
-    stage_x1(tile);
+    stage_x2(tile);
     cp_async_commit();
   }
   tc::fence_async_smem();
@@ -507,7 +497,7 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
     const int node = n0 + (row >> 4);
     const bool live = node < d.n_dst;
     const size_t roff = (size_t)(live ? node : 0) * kRow + (row & 15) * kC + 16 * cg;  // this thread's 16 channels
-    // grad_out of this thread (used after the fibre phase): in flight during phase A
+    // grad_out of this thread: in flight while the x2 tile lands
     float4 gzv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) gzv[i] = live ? ldg4(d.grad_out + roff + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -515,30 +505,11 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
       const int nt = tile + gridDim.x;
       if (nt < n_tiles) {
         const uint32_t bytes = (uint32_t)min(kTE, d.n_dst - nt * kTE) * kRow * 4u;
-        tc::prefetch_l2(d.x1 + (size_t)nt * kTE * kRow, bytes);
+        tc::prefetch_l2(d.x2 + (size_t)nt * kTE * kRow, bytes);
         tc::prefetch_l2(d.grad_out + (size_t)nt * kTE * kRow, bytes);
       }
     }
     cp_async_wait_all();
-    __syncthreads();
-
-    // ---- A: fibre convolution + bias: X1 -> X2 ------------------------------------------------------
-    {
-      const float bias_c = s.bias[fc];
-#pragma unroll 2
-      for (int j = 0; j < kTE; ++j) {
-        float c0 = 0.f, c1 = 0.f;
-#pragma unroll
-        for (int o = 0; o < kO; ++o) {
-          const float x = s.u.x.X1[(16 * j + o) * kC + fc];
-          c0 = fmaf(x, fk[o][0], c0);
-          c1 = fmaf(x, fk[o][1], c1);
-        }
-        float* o2 = s.u.x.X2 + (16 * j + 2 * pp) * kLDX2 + fc;
-        o2[0] = c0 + bias_c;
-        o2[kLDX2] = c1 + bias_c;
-      }
-    }
     __syncthreads();
 
     // ---- B: LayerNorm forward (thread = row x 16-channel group cg) + scaled grad_out -> fp16 operand -------
@@ -548,7 +519,7 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 v = ld4(s.u.x.X2 + row * kLDX2 + 16 * cg + 4 * i);
+        const float4 v = ld4(s.u.X2 + row * kLDX2 + 16 * cg + 4 * i);
         xh[4 * i] = v.x; xh[4 * i + 1] = v.y; xh[4 * i + 2] = v.z; xh[4 * i + 3] = v.w;
         sum += (v.x + v.y) + (v.z + v.w);
       }
@@ -622,10 +593,10 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
         // gH' = gZ' W2[:, half]   (W2h read MN-major: N = k', K = n)
         tc::issue_mma(tmem + kCol2D, tc::view_k(gz, kTM), tc::view_mn(w2 + (16 * h2) * (kC * 16), kC),
                       tc::idesc_f16_ex(128, 128, 0, 1, 0, 0), kC / 16, false);
+        tc::mma_commit(&s.bar[1]);  // the epilogue below only needs gH': dW2 runs underneath it
         // dW2'^T[k'][n] += h^T gZ'   (both MN-major, K = tile rows)
         tc::issue_mma(tmem + kCol2DW2 + 64 * h2, tc::view_mn(a2, kTM), tc::view_mn(gz, kTM),
                       tc::idesc_f16_ex(128, 64, 1, 1, 0, 0), kTM / 16, !first_tile);
-        tc::mma_commit(&s.bar[1]);
       }
       tc::mbar_wait(&s.bar[1], par1);
       par1 ^= 1u;
@@ -657,18 +628,20 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
         // [dW1' | gb1'][k'][c] += gPre'^T [y | 1 1 0..]
         tc::issue_mma(tmem + kCol2DW1 + kKb * h2, tc::view_mn(ap, kTM), tc::view_mn(a1, kTM),
                       tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0), kTM / 16, !first_tile);
-        tc::mma_commit(&s.bar[2]);
+        // half 0: no wait here. The tensor pipe completes MMAs in issue order, so the wait on pre(1) (bar[0], issued
+        // after these) also covers dW2(0), gY(0) and dW1(0) before A2h / AP are overwritten.
+        if (h2 == 1) tc::mma_commit(&s.bar[2]);
       }
-      tc::mbar_wait(&s.bar[2], par2);
-      par2 ^= 1u;
-      tc::tc_fence_after();
     }
+    tc::mbar_wait(&s.bar[2], par2);  // everything of this tile is complete: gY is final, the operand buffers are free
+    par2 ^= 1u;
+    tc::tc_fence_after();
 
-    // A2h / AP (= X1 / X2) are free: prefetch the next tile's x1
+    // A2h / AP (= X2) are free: prefetch the next tile's x2
     {
       const int nt = tile + gridDim.x;
       if (nt < n_tiles) {
-        stage_x1(nt);
+        stage_x2(nt);
         cp_async_commit();
       }
     }
@@ -851,6 +824,7 @@ extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream)
     }
     grl::fbconv_node_bwd_tc_kernel<<<d->n_partials_node, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   } else {
+    GRL_REQUIRE(d->x2, GRL_EINVAL, "grl_fbconv_node_bwd_tc: x2 (saved by grl_fbconv_node_fwd_tc) is required");
     static bool attr = false;
     const int smem = (int)sizeof(grl::NodeBwd2Smem);
     if (!attr) {

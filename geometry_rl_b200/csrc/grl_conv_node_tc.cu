@@ -379,6 +379,11 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
         v[i] = ld4(G.u.x.X2 + r * kLDX + 4 * (2 * i + h));
         sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
+      if (d.x2 && n0 + (r >> 4) < d.n_dst) {  // saved for the backward pass (it then skips the fibre recompute)
+        float* xo = d.x2 + (size_t)(n0 + (r >> 4)) * kRow + (r & 15) * kC + 4 * h;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st4(xo + 8 * i, v[i]);
+      }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       const float mean = sum * (1.0f / 64.0f);
       float sq = 0.f;

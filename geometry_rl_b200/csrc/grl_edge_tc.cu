@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
 
 // ---------------------------------------------------------------------------------------------------
 // (E2) spatial convolution forward: kern = basis Wk^T on the tensor core, message product + CSR-ordered sum.
-// Persistent CTAs own CONTIGUOUS dst-node ranges holding equal shares of the edges (binary search in rowptr), so
+// Persistent CTAs own CONTIGUOUS dst-node ranges of equal cost (edges and nodes; binary search in rowptr), so
 // the edge tiles of a CTA are consecutive 8-edge groups of the CSR: tile t+1's basis rows and gathered x_src rows
 // are fetched with cp.async into the other half of a 2-stage ring while tile t is multiplied and reduced, and the
 // edge indices are prefetched two tiles ahead in registers.
@@ -155,12 +155,13 @@ struct EdgeFwdTcSmem {
   uint32_t tmem_base;
 };
 
-// first node n in [0, n_nodes] with rowptr[n] >= target
+// first node n in [0, n_nodes] with cost(n) = 3 * rowptr[n] + 2 * n >= target (an edge moves ~6 KB, a node's x1 row
+// 4 KB: edge-less padded nodes still have their zero row written, so ranges are balanced on both)
 __device__ __forceinline__ int node_lower_bound(const int32_t* __restrict__ rowptr, int n_nodes, long long target) {
   int lo = 0, hi = n_nodes;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if ((long long)__ldg(rowptr + mid) < target) lo = mid + 1; else hi = mid;
+    if (3ll * __ldg(rowptr + mid) + 2ll * mid < target) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -193,10 +194,10 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
   }
   if (warp == 0) tc::tmem_alloc(&s.tmem_base, 64);
   tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
-  // this CTA's node range: equal edge shares
-  const long long E = d.n_edges;
-  const int n_lo = blockIdx.x == 0 ? 0 : node_lower_bound(d.rowptr_dst, d.n_dst, E * blockIdx.x / gridDim.x);
-  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_dst : node_lower_bound(d.rowptr_dst, d.n_dst, E * (blockIdx.x + 1) / gridDim.x);
+  // this CTA's node range: equal cost shares
+  const long long W = 3ll * d.n_edges + 2ll * d.n_dst;
+  const int n_lo = blockIdx.x == 0 ? 0 : node_lower_bound(d.rowptr_dst, d.n_dst, W * blockIdx.x / gridDim.x);
+  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_dst : node_lower_bound(d.rowptr_dst, d.n_dst, W * (blockIdx.x + 1) / gridDim.x);
   const int p0 = d.rowptr_dst[n_lo], p1 = d.rowptr_dst[n_hi];
   const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
   const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);

@@ -276,20 +276,23 @@ class FiberConvFn(torch.autograd.Function):
                           w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
         shape = (es.n_src, es.n_dst, es.n_edges)
         L.call("grl_fbconv_edge_fwd_tc" if basis.dtype == torch.bfloat16 else "grl_fbconv_edge_fwd", C.byref(d), shape=shape)
+        x2 = x1  # placeholder so that save_for_backward has a tensor in the strict path
         if precision == "bf16":
             w2_rm = _f32c(w2_d)
-            d.w2 = L.ptr(w2_rm)
+            # the tensor-core backward reads the pre-LayerNorm tensor instead of recomputing the fibre convolution
+            x2 = torch.empty_like(x1) if any(ctx.needs_input_grad) else None
+            d.w2, d.x2 = L.ptr(w2_rm), L.ptr(x2)
             L.call("grl_fbconv_node_fwd_tc", C.byref(d), shape=shape)
         else:
             L.call("grl_fbconv_node_fwd", C.byref(d), shape=shape)
         ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1,
-                              _f32c(w2_d) if precision == "bf16" else w2_c)
+                              _f32c(w2_d) if precision == "bf16" else w2_c, x2)
         ctx.es, ctx.homo, ctx.precision, ctx.basis_in_dtype = es, homo, precision, basis_in_dtype
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1, w2_rm = ctx.saved_tensors
+        x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1, w2_rm, x2 = ctx.saved_tensors
         es, homo = ctx.es, ctx.homo
         dev = x_src.device
         g_out = _f32c(g_out)
@@ -317,7 +320,7 @@ class FiberConvFn(torch.autograd.Function):
             g_x2 = torch.empty_like(x1)
             amax = torch.empty(1, dtype=torch.int32, device=dev)  # bit pattern of max |grad_out| (fp16 gradient scale)
             L.call("grl_absmax", L.ptr(g_out), g_out.numel(), L.ptr(amax), shape=shape)
-            d.w2, d.grad_x2, d.grad_amax = L.ptr(w2_rm), L.ptr(g_x2), L.ptr(amax)
+            d.w2, d.grad_x2, d.grad_amax, d.x2 = L.ptr(w2_rm), L.ptr(g_x2), L.ptr(amax), L.ptr(x2)
             L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=shape)
         else:
             L.call("grl_fbconv_node_bwd", C.byref(d), shape=shape)

@@ -181,6 +181,8 @@ typedef struct {
   const void* basis_bf16;    /* [E][16][64] bf16 (edge order)                                       */
   void* grad_basis_bf16;     /* [E][16][64] bf16                                                    */
   float* grad_x2;            /* [n_dst][16][64] workspace: gradient w.r.t. the pre-LayerNorm tensor   */
+  float* x2;                 /* optional [n_dst][16][64]: pre-LayerNorm tensor fibre(x1) + bias, written by
+                                grl_fbconv_node_fwd_tc and read by grl_fbconv_node_bwd_tc instead of recomputing it     */
   const uint32_t* grad_amax; /* grl_absmax(grad_out): the tensor-core backward stages gradients as fp16 scaled by a
                                 power of two derived from it (max |g| -> [32, 64)); NULL = scale 1          */
 } GrlConvDesc;
