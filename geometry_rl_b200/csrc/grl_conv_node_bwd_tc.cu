@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1) fbconv_node_bwd_tc_kernel(const G
 //   * b1 rides in the contraction (K = 80: y[:, 64:66] = 1, W1[:, 64:66] = fp16 (hi, lo) split of b1) and the same
 //     ones-columns turn the dW1 MMA (N = 80) into the b1 gradient: no bias adds, no 64-value column butterfly.
 //   * GELU and GELU' are evaluated two elements per instruction in packed fp16 (gelu_h2); h and dG stay packed.
-//   * grad_out is loaded into registers at the top of the tile (used after the fibre phase); the next tile's x1 /
-//     grad_out are pulled into L2 one tile ahead.
+//   * the x2 and grad_out tiles of the NEXT tile are fetched with cp.async as soon as this tile's last MMA has
+//     retired, and pulled into L2 one tile earlier still.
 //   * no fibre recompute: the forward kernel saves the pre-LayerNorm tensor x2 (GrlConvDesc.x2) and this kernel
 //     streams it back with cp.async (the fibre phase was 20 % of the stall samples of the recomputing version);
 //   * half 0 never waits on its gY / dW MMAs: the tensor pipe retires MMAs in issue order, so the next wait covers them.
@@ -398,7 +398,10 @@ struct NodeBwd2Smem {
   __half A1[kTM * kKb];     // y: [10 chunks][128 rows][8]; chunk 8 = (1, 1, 0 ...), chunk 9 = 0 (written once)
   __half GZh[kTM * kC];     // scaled grad_out [8 chunks][128 rows][8]
   union {
-    float X2[kTM * kLDX2];      // pre-LayerNorm x2 tile (saved by the forward kernel), phase B only
+    struct {
+      float X2[kTM * kLDX2];    // pre-LayerNorm x2 tile (saved by the forward kernel), phase B only
+      float GZf[kTM * kLDX2];   // grad_out tile (fp32), phase B only
+    } in;
     struct {
       __half A2h[kTM * 128];    // h           half: [16 chunks][128 rows][8]
       __half AP[kTM * 128];     // scaled gPre half: [16 chunks][128 rows][8]
@@ -466,15 +469,21 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
   const float inv_gscale = 1.0f / gscale;  // exact: gscale is a power of two
   const int n_tiles = (d.n_dst + kTE - 1) / kTE;
   int tile = blockIdx.x;
-  auto stage_x2 = [&](int t) {  // x2 rows of tile t -> X2 (row stride kLDX2), 16-byte cp.async pieces
+  auto stage_x2 = [&](int t) {  // x2 and grad_out rows of tile t -> X2 / GZf (row stride kLDX2), 16-byte cp.async pieces
     const int cnt = min(kTE, d.n_dst - t * kTE);
     const float* src = d.x2 + (size_t)t * kTE * kRow;
+    const float* gsrc = d.grad_out + (size_t)t * kTE * kRow;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int f = tid + kNB2Threads * i;  // float4 index 0..2047 of the [128][64] tile
-      float* dp = s.u.X2 + (f >> 4) * kLDX2 + 4 * (f & 15);
-      if ((f >> 8) < cnt) cp_async16(dp, src + 4 * f);
-      else *reinterpret_cast<float4*>(dp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int so = (f >> 4) * kLDX2 + 4 * (f & 15);
+      if ((f >> 8) < cnt) {
+        cp_async16(s.u.in.X2 + so, src + 4 * f);
+        cp_async16(s.u.in.GZf + so, gsrc + 4 * f);
+      } else {
+        *reinterpret_cast<float4*>(s.u.in.X2 + so) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s.u.in.GZf + so) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   };
   if (tile < n_tiles) {
@@ -497,10 +506,6 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
     const int node = n0 + (row >> 4);
     const bool live = node < d.n_dst;
     const size_t roff = (size_t)(live ? node : 0) * kRow + (row & 15) * kC + 16 * cg;  // this thread's 16 channels
-    // grad_out of this thread: in flight while the x2 tile lands
-    float4 gzv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) gzv[i] = live ? ldg4(d.grad_out + roff + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {  // next tile's x1 / grad_out -> L2
       const int nt = tile + gridDim.x;
       if (nt < n_tiles) {
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 v = ld4(s.u.X2 + row * kLDX2 + 16 * cg + 4 * i);
+        const float4 v = ld4(s.u.in.X2 + row * kLDX2 + 16 * cg + 4 * i);
         xh[4 * i] = v.x; xh[4 * i + 1] = v.y; xh[4 * i + 2] = v.z; xh[4 * i + 3] = v.w;
         sum += (v.x + v.y) + (v.z + v.w);
       }
@@ -546,7 +551,10 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
       // grad_out row piece: column sums (gb2) of the raw values, then scaled -> GZh
       float g16[16], gs[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { g16[4 * i] = gzv[i].x; g16[4 * i + 1] = gzv[i].y; g16[4 * i + 2] = gzv[i].z; g16[4 * i + 3] = gzv[i].w; }
+      for (int i = 0; i < 4; ++i) {
+        const float4 gv = ld4(s.u.in.GZf + row * kLDX2 + 16 * cg + 4 * i);
+        g16[4 * i] = gv.x; g16[4 * i + 1] = gv.y; g16[4 * i + 2] = gv.z; g16[4 * i + 3] = gv.w;
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) gs[i] = g16[i] * gscale;
       *reinterpret_cast<uint4*>(s.GZh + ((size_t)(2 * cg) * kTM + row) * 8) = tc::pack8_h(gs);

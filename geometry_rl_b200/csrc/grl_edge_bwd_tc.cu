@@ -14,6 +14,7 @@
 // hold X^T Y and are ignored).  Reference: autograd of ponita/conv.py:84-87,116-149 and hepi.py:76-82,109-123.
 #include <stdlib.h>
 
+#include "grl_basis_feat.cuh"
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
 
@@ -469,32 +470,6 @@ struct BasisBwdTcSmem {
   uint32_t tmem_base;
 };
 
-// shared with grl_edge_tc.cu (same translation-unit-local copies)
-__device__ __forceinline__ void basis_features_tc2(const GrlBasisDesc& d, int tile, __nv_bfloat16* __restrict__ F) {
-  const int r = threadIdx.x;
-  if (r < kTM) {
-    const int e = tile * kTE + (r >> 4), o = r & 15;
-    float f[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = 0.f;
-    if (e < d.n_edges) {
-      const float* ps = d.pos_src + 3 * (size_t)d.edge_src[e];
-      const float* pd = d.pos_dst + 3 * (size_t)d.edge_dst[e];
-      const float rx = ps[0] - pd[0], ry = ps[1] - pd[1], rz = (d.dim == 3) ? ps[2] - pd[2] : 0.f;
-      const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
-      const float i1 = (rx * ox + ry * oy) + rz * oz;
-      const float tx = rx - i1 * ox, ty = ry - i1 * oy, tz = rz - i1 * oz;
-      const float i2 = sqrtf((tx * tx + ty * ty) + tz * tz);
-      f[0] = i1; f[1] = i2;
-      f[2] = i1 * i1; f[3] = i1 * i2; f[4] = i2 * i1; f[5] = i2 * i2;
-      f[6] = f[2] * i1; f[7] = f[2] * i2; f[8] = f[3] * i1; f[9] = f[3] * i2;
-      f[10] = f[4] * i1; f[11] = f[4] * i2; f[12] = f[5] * i1; f[13] = f[5] * i2;
-    }
-    *reinterpret_cast<uint4*>(F + ((size_t)0 * kTM + r) * 8) = tc::pack8(f);
-    *reinterpret_cast<uint4*>(F + ((size_t)1 * kTM + r) * 8) = tc::pack8(f + 8);
-  }
-}
-
 __global__ void __launch_bounds__(kThreads, 2) edge_basis_bwd_tc_kernel(const GrlBasisDesc d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BasisBwdTcSmem& s = *reinterpret_cast<BasisBwdTcSmem*>(smem_raw);
@@ -526,8 +501,14 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_bwd_tc_kernel(const Gr
   uint32_t parity = 0;
   bool first = true;
   const int n_tiles = (d.n_edges + kTE - 1) / kTE;
+  BasisFeatPipe feat;
+  feat.start(d, blockIdx.x, gridDim.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    basis_features_tc2(d, tile, s.F);
+    feat.emit_and_advance(d, tile, gridDim.x, s.F, 0.0f);
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {  // next tile's grad_basis rows (contiguous) -> L2
+      const int nt = tile + gridDim.x;
+      tc::prefetch_l2(gb + (size_t)nt * kTE * kRow, (uint32_t)min(kTE, d.n_edges - nt * kTE) * kRow * 2u);
+    }
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -559,22 +540,29 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_bwd_tc_kernel(const Gr
       tc::issue_mma(tmem + 64, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
       tc::mma_commit(&s.bar[1]);
     }
+    // this thread's grad_basis piece: requested before the wait so the round trip hides behind the pre2 MMA
+    // (the tile's rows were pulled into L2 one tile ahead)
+    uint4 gq[4];
+    {
+      const int e_idx = tile * kTE + (row >> 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gq[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (e_idx < d.n_edges) {
+        const uint4* p = reinterpret_cast<const uint4*>(gb + (size_t)e_idx * kRow + (row & 15) * kC + 32 * ch);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gq[i] = __ldg(p + i);
+      }
+    }
     tc::mbar_wait(&s.bar[1], parity);
     tc::tc_fence_after();
     {
-      const int e_idx = tile * kTE + (row >> 4);
       float gp2[32];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c0 = 32 * ch + 16 * i;
         float v[16];
         tc::tmem_ld16(lane_addr + 64 + c0, v);
-        uint4 g0 = make_uint4(0u, 0u, 0u, 0u), g1 = g0;
-        if (e_idx < d.n_edges) {
-          const uint4* p = reinterpret_cast<const uint4*>(gb + (size_t)e_idx * kRow + (row & 15) * kC + c0);
-          g0 = __ldg(p);
-          g1 = __ldg(p + 1);
-        }
+        const uint4 g0 = gq[2 * i], g1 = gq[2 * i + 1];
         const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
         const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
 #pragma unroll

@@ -7,6 +7,7 @@
 // HBM as bf16 [E][16][64] (2 KB per edge instead of 4); invariants, GELU, the message product and the
 // deterministic CSR-ordered segmented sum stay fp32.  Small per-CTA footprints (<= 64 KB smem, <= 128 TMEM
 // columns) so 2-3 CTAs share an SM and overlap each other's MMA / epilogue / gather phases.
+#include "grl_basis_feat.cuh"
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
 
@@ -16,54 +17,13 @@ namespace grl {
 // (E1) edge basis forward
 // ---------------------------------------------------------------------------------------------------
 struct BasisTcSmem {
-  __nv_bfloat16 F[kTM * 16];    // [2 chunks][128 rows][8]
-  __nv_bfloat16 H1[kTM * kC];   // [8 chunks][128 rows][8]
-  __nv_bfloat16 W1b[kC * 16];   // [2 chunks][64 rows n][8 f]
-  __nv_bfloat16 W2b[kC * kC];   // [8 chunks][64 rows n][8 k]
-  float b1[kC], b2[kC];
+  __nv_bfloat16 F[kTM * 16];    // [2 chunks][128 rows][8]: 14 invariants, then (1, 1) multiplying the b1 columns of W1b
+  __half H1[kTM * 80];          // [10 chunks][128 rows][8]: GELU(pre1) fp16, chunk 8 = (1, 1, 0 ...), chunk 9 = 0
+  __nv_bfloat16 W1b[kC * 16];   // [2 chunks][64 rows n][8 f]: f = 14, 15 hold the bf16 (hi, lo) split of b1
+  __half W2h[kC * 80];          // [10 chunks][64 rows n][8 k]: chunk 8 = fp16 (hi, lo) split of b2
   uint64_t bar[2];
   uint32_t tmem_base;
 };
-
-// 14 invariant features of (edge, orientation) -> two 16-byte chunks of the F operand image (features 14, 15 = 0)
-__device__ __forceinline__ void basis_features_tc(const GrlBasisDesc& d, int tile, __nv_bfloat16* __restrict__ F) {
-  const int r = threadIdx.x;
-  if (r < kTM) {
-    const int e = tile * kTE + (r >> 4), o = r & 15;
-    float f[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = 0.f;
-    if (e < d.n_edges) {
-      const float* ps = d.pos_src + 3 * (size_t)d.edge_src[e];
-      const float* pd = d.pos_dst + 3 * (size_t)d.edge_dst[e];
-      const float rx = ps[0] - pd[0], ry = ps[1] - pd[1], rz = (d.dim == 3) ? ps[2] - pd[2] : 0.f;
-      const float ox = d.ori[3 * o], oy = d.ori[3 * o + 1], oz = (d.dim == 3) ? d.ori[3 * o + 2] : 0.f;
-      const float i1 = (rx * ox + ry * oy) + rz * oz;
-      const float tx = rx - i1 * ox, ty = ry - i1 * oy, tz = rz - i1 * oz;
-      const float i2 = sqrtf((tx * tx + ty * ty) + tz * tz);
-      f[0] = i1; f[1] = i2;
-      f[2] = i1 * i1; f[3] = i1 * i2; f[4] = i2 * i1; f[5] = i2 * i2;
-      f[6] = f[2] * i1; f[7] = f[2] * i2; f[8] = f[3] * i1; f[9] = f[3] * i2;
-      f[10] = f[4] * i1; f[11] = f[4] * i2; f[12] = f[5] * i1; f[13] = f[5] * i2;
-    }
-    *reinterpret_cast<uint4*>(F + ((size_t)0 * kTM + r) * 8) = tc::pack8(f);
-    *reinterpret_cast<uint4*>(F + ((size_t)1 * kTM + r) * 8) = tc::pack8(f + 8);
-  }
-}
-
-// B operand images from the transposed fp32 weights the descriptor carries (w1t[f][n], w2t[k][n])
-__device__ __forceinline__ void stage_basis_weights(const GrlBasisDesc& d, __nv_bfloat16* W1b, __nv_bfloat16* W2b, float* b1,
-                                                    float* b2) {
-  for (int i = threadIdx.x; i < kC * 16; i += blockDim.x) {
-    const int n = i >> 4, f = i & 15;
-    W1b[tc::op_index(kC, n, f)] = __float2bfloat16(d.w1t[f * kC + n]);
-  }
-  for (int i = threadIdx.x; i < kC * kC; i += blockDim.x) {
-    const int n = i >> 6, k = i & 63;
-    W2b[tc::op_index(kC, n, k)] = __float2bfloat16(d.w2t[k * kC + n]);
-  }
-  if (threadIdx.x < kC) { b1[threadIdx.x] = d.b1[threadIdx.x]; b2[threadIdx.x] = d.b2[threadIdx.x]; }
-}
 
 __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const GrlBasisDesc d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -76,18 +36,47 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&s.tmem_base, 128);
-  stage_basis_weights(d, s.W1b, s.W2b, s.b1, s.b2);
+  // B operand images from the transposed fp32 weights the descriptor carries (w1t[f][n], w2t[k][n]); both biases ride in
+  // the contractions as (hi, lo) pairs against ones columns of the A operands
+  for (int i = tid; i < kC * 16; i += kThreads) {
+    const int n = i >> 4, f = i & 15;
+    float w = d.w1t[f * kC + n];
+    if (f >= 14) {
+      const float b = d.b1[n];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      w = f == 14 ? hi : b - hi;
+    }
+    s.W1b[tc::op_index(kC, n, f)] = __float2bfloat16_rn(w);
+  }
+  for (int i = tid; i < kC * 80; i += kThreads) {
+    const int n = i / 80, k = i % 80;
+    float w = 0.f;
+    if (k < kC) {
+      w = d.w2t[k * kC + n];
+    } else if (k < kC + 2) {
+      const float b = d.b2[n];
+      const float hi = __half2float(__float2half_rn(b));
+      w = k == kC ? hi : b - hi;
+    }
+    s.W2h[tc::op_index(kC, n, k)] = __float2half_rn(w);
+  }
+  if (tid < kTM) {  // ones / zero columns of H1 (persistent)
+    *reinterpret_cast<uint4*>(s.H1 + ((size_t)8 * kTM + tid) * 8) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s.H1 + ((size_t)9 * kTM + tid) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t fa = tc::smem_u32(s.F), ha = tc::smem_u32(s.H1), w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b);
+  const uint32_t fa = tc::smem_u32(s.F), ha = tc::smem_u32(s.H1), w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2h);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.basis_bf16);
   uint32_t parity = 0;
   const int n_tiles = (d.n_edges + kTE - 1) / kTE;
+  BasisFeatPipe feat;
+  feat.start(d, blockIdx.x, gridDim.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    basis_features_tc(d, tile, s.F);
+    feat.emit_and_advance(d, tile, gridDim.x, s.F, 1.0f);
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -103,17 +92,21 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
       const int c0 = 32 * ch + 16 * i;
       float v[16];
       tc::tmem_ld16(lane_addr + c0, v);
+      __half2 h0[4], h1[4];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = gelu_fast(v[e] + s.b1[c0 + e]);
-      *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-      *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+      for (int e = 0; e < 4; ++e) {
+        h0[e] = tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]));
+        h1[e] = tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]));
+      }
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack_h8(h0);
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack_h8(h1);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc::tc_fence_after();
-      tc::issue_mma(tmem + kC, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+      tc::issue_mma(tmem + kC, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), 80 / 16, false);
       tc::mma_commit(&s.bar[1]);
     }
     tc::mbar_wait(&s.bar[1], parity);
@@ -124,12 +117,17 @@ __global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const Gr
       const int c0 = 32 * ch + 16 * i;
       float v[16];
       tc::tmem_ld16(lane_addr + kC + c0, v);
+      uint32_t ob[8];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = gelu_fast(v[e] + s.b2[c0 + e]);
+      for (int e = 0; e < 8; ++e) {
+        const float2 g = __half22float2(tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1])));
+        const __nv_bfloat162 b = __floats2bfloat162_rn(g.x, g.y);
+        ob[e] = *reinterpret_cast<const uint32_t*>(&b);
+      }
       if (e_idx < d.n_edges) {
         __nv_bfloat16* p = out + (size_t)e_idx * kRow + (row & 15) * kC + c0;
-        *reinterpret_cast<uint4*>(p) = tc::pack8(v);
-        *reinterpret_cast<uint4*>(p + 8) = tc::pack8(v + 8);
+        *reinterpret_cast<uint4*>(p) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+        *reinterpret_cast<uint4*>(p + 8) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
       }
     }
     tc::tc_fence_before();
