@@ -27,8 +27,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 DEFAULT_CONFIG = "rigid_pushing_multi_empn_trpl_cfg"  # BASELINE.json configs[1]: 4096 envs x 16 steps, 1 B200
-METRIC = "policy update samples/sec (policy fwd+bwd + TRPL projection + critic + Adam)"
+METRIC = "fwd+bwd+TRPL update samples/sec (policy fwd+bwd, TRPL projection, losses, critic, Adam)"  # BASELINE.json metric
 N_ROTATE = 8  # distinct minibatches cycled through the timed region
+_emit = print
 
 
 def parse():
@@ -42,7 +43,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--dp-graph", action="store_true", help="also replay the data-parallel step (NCCL included) from a CUDA graph")
+    ap.add_argument("--no-dp-graph", action="store_true", help="N > 1: launch the step eagerly instead of replaying it "
+                    "(NCCL all-reduces included) from a CUDA graph")
+    ap.add_argument("--dp-graph", action="store_true", help=argparse.SUPPRESS)  # now the default
     ap.add_argument("--single-precision", action="store_true", help="skip the second (other precision) measurement")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="nn.Linear contractions of the message-passing kernels: fp32 FFMA (parity 1e-5) or bf16 tcgen05 "
@@ -98,6 +101,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(kernel, workload, minibatch):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_traffic.json, written by profiles/summarise.py
+    traffic); None when no capture matches the workload being run."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    if t.get("workload") != workload or t.get("minibatch_per_gpu") != minibatch:
+        return None
+    return t.get("kernels", {}).get(kernel)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -118,14 +134,18 @@ def kernel_bytes(name, shape):
         "grl_edge_basis_bwd": E * (R + 32),
         "grl_fbconv_edge_fwd": E * R + n_src * R + n_dst * R + E * 8,
         "grl_fbconv_node_fwd": 3 * n_dst * R,
+        # x1 read, x_dst read, out write; the x2 row the kernel also saves for the backward pass is a design choice of
+        # this implementation, not compulsory traffic, and is NOT counted (it shows up in `traffic`)
         "grl_fbconv_node_fwd_tc": 3 * n_dst * R,
+        "grl_absmax": n_dst * R,
         # bf16 path: basis / grad_basis rows are 2 KB (R / 2)
         "grl_edge_basis_fwd_tc": E * (R // 2 + 32),
         "grl_edge_basis_bwd_tc": E * (R // 2 + 32),
         "grl_fbconv_edge_fwd_tc": E * R // 2 + n_src * R + n_dst * R + E * 8,
         "grl_fbconv_edge_bwd_tc": 2 * E * R // 2 + 2 * n_src * R + n_dst * R + E * 12,
         "grl_fbconv_node_bwd": 3 * n_dst * R,
-        "grl_fbconv_node_bwd_tc": 5 * n_dst * R,  # x1, grad_out read, g_x2 write + (fibre kernel) g_x2 re-read, g_x1 write
+        "grl_fbconv_node_bwd_tc": 5 * n_dst * R,  # x2, grad_out read, g_x2 write + (fibre kernel) g_x2 re-read, g_x1 write
+                                                   # (the fibre kernel's x1 read, 1 more R per node, is not counted)
         "grl_fbconv_edge_bwd": 2 * E * R + 2 * n_src * R + n_dst * R + E * 12,
     }.get(name)
 
@@ -178,7 +198,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,7 +254,7 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
         return float(t[0])
 
     # ---- device-resident timing ----------------------------------------------------------------------
-    use_graph = not args.no_graph and (dp is None or args.dp_graph)
+    use_graph = not args.no_graph and (dp is None or not args.no_dp_graph)
     launches_per_step = None
     if use_graph:
         c0 = _lib.launch_count
@@ -303,7 +323,7 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
             achieved = ab / dur / 1e9 if dur > 0 else 0.0
             res["roofline"] = {
                 "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": tot[top] / len(per_kernel[top]),
+                "traffic": measured_traffic(top, args.config, B), "peak_source": peak_src, "avg_launch_ms": tot[top] / len(per_kernel[top]),
                 "launches_per_step": len(per_kernel[top]) / n_prof, "algorithmic_bytes_per_launch": ab / len(per_kernel[top]),
                 "share_of_kernel_time": tot[top] / step_kernel_ms,
                 "kernel_ms_per_step": {k: round(v / n_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
@@ -368,13 +388,18 @@ def run_ours(args):
                                        "value": other_res["value"], "unit": "samples/s", "ms_per_step": other_res["ms_per_step"],
                                        "steps": other_res["steps"], "e2e": other_res["e2e"]["value"],
                                        "parity": "1e-5 vs reference fp32" if other == "fp32" else "1e-2 vs reference fp32"}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if dp is not None:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: library chatter (e.g. the reference's "Callibrating...") goes to stderr
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    global _emit
+    _emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -12,8 +12,6 @@
 // The 64 x 64 (and 64 x 16) weight gradients are formed with M = 128 MMAs by reading a 128-column operand image
 // made of two ADJACENT 64-column images [X | G]: lanes 64..127 of the accumulator then hold G^T Y (lanes 0..63
 // hold X^T Y and are ignored).  Reference: autograd of ponita/conv.py:84-87,116-149 and hepi.py:76-82,109-123.
-#include <stdlib.h>
-
 #include "grl_basis_feat.cuh"
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
@@ -26,180 +24,7 @@ __device__ __forceinline__ void cp_async16_any(void* smem_dst, const void* gmem_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// (E3)
-// ---------------------------------------------------------------------------------------------------
-struct EdgeBwdTcSmem {
-  __nv_bfloat16 BZ[kTM * kC];   // basis rows gathered by edge id   [8 chunks][128][8]
-  __nv_bfloat16 GK[kTM * kC];   // g_kern, MUST directly follow BZ ([BZ | GK] is read as one 128-column image)
-  __nv_bfloat16 Wkb[kC * kC];   // [8 chunks][64 rows c][8 j]
-  float GX[kTileFloats];        // g_x1 rows gathered by dst, then g_x1 * kern in place
-  float XS[kTileFloats];        // x_src rows gathered by src
-  int eid[kTE], src[kTE], dst[kTE];
-  uint64_t bar[2];
-  uint32_t tmem_base;
-};
-constexpr int kSrcNodesPerBlockTc = 16;
-
-__global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc_kernel(const GrlConvDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  EdgeBwdTcSmem& s = *reinterpret_cast<EdgeBwdTcSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
-  const int o = tid >> 4, cg = tid & 15;
-  if (tid == 0) {
-    tc::mbar_init(&s.bar[0], 1);
-    tc::mbar_init(&s.bar[1], 1);
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 256);
-  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t bz = tc::smem_u32(s.BZ), gk = tc::smem_u32(s.GK), wk = tc::smem_u32(s.Wkb);
-  const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);
-  __nv_bfloat16* g_basis = reinterpret_cast<__nv_bfloat16*>(d.grad_basis_bf16);
-  uint32_t par0 = 0, par1 = 0;
-  bool first = true;
-
-  const int n_blocks = (d.n_src + kSrcNodesPerBlockTc - 1) / kSrcNodesPerBlockTc;
-  for (int nb = blockIdx.x; nb < n_blocks; nb += gridDim.x) {
-    const int n0 = nb * kSrcNodesPerBlockTc;
-    const int n1 = min(n0 + kSrcNodesPerBlockTc, d.n_src);
-    const int q0 = d.rowptr_src[n0], q1 = d.rowptr_src[n1];
-    int cur = n0;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto flush = [&](int node) {
-      const size_t off = (size_t)node * kRow + o * kC + 4 * cg;
-      if (d.grad_x_src_init) {
-        const float4 b = ldg4(d.grad_x_src_init + off);
-        sum.x += b.x; sum.y += b.y; sum.z += b.z; sum.w += b.w;
-      }
-      st4(d.grad_x_src + off, sum);
-      sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    for (int base = q0; base < q1; base += kTE) {
-      const int cnt = min(kTE, q1 - base);
-      __syncthreads();
-      if (tid < kTE) {
-        const int e = (tid < cnt) ? d.src_eid[base + tid] : 0;
-        s.eid[tid] = e;
-        s.src[tid] = (tid < cnt) ? d.edge_src[e] : 0;
-        s.dst[tid] = (tid < cnt) ? d.edge_dst[e] : 0;
-      }
-      __syncthreads();
-      // basis rows (bf16) by edge id -> operand image
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = tid + kThreads * i;
-        const int r = f >> 3, c8 = f & 7, j = r >> 4;
-        __nv_bfloat16* dpt = s.BZ + ((size_t)c8 * kTM + r) * 8;
-        if (j < cnt) cp_async16_any(dpt, basis + (size_t)s.eid[j] * kRow + (r & 15) * kC + 8 * c8);
-        else *reinterpret_cast<uint4*>(dpt) = make_uint4(0u, 0u, 0u, 0u);
-      }
-      stage_rows_gather(s.GX, d.grad_x1, s.dst, cnt);
-      stage_rows_gather(s.XS, d.x_src, s.src, cnt);
-      cp_async_commit();
-      cp_async_wait_all();
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        tc::issue_mma(tmem, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-        tc::mma_commit(&s.bar[0]);
-      }
-      tc::mbar_wait(&s.bar[0], par0);
-      par0 ^= 1u;
-      tc::tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 32 * ch + 16 * i;
-        float v[16], gkv[16];
-        tc::tmem_ld16(lane_addr + c0, v);
-        float* gx = s.GX + row * kLDT + c0;
-        const float* xs = s.XS + row * kLDT + c0;
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const float4 gm = ld4(gx + e), x = ld4(xs + e);
-          st4(gx + e, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
-          gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
-        }
-        *reinterpret_cast<uint4*>(s.GK + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
-        *reinterpret_cast<uint4*>(s.GK + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        // g_basis = g_kern Wk   (Wk image [c rows][j cols] read MN-major: K = c, N = j)
-        tc::issue_mma(tmem + 64, tc::view_k(gk, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-        // lanes 64..127: gWk[c][j] += sum_rows g_kern[row][c] basis[row][j]   ([BZ | GK] as one 128-column image)
-        tc::issue_mma(tmem + 128, tc::view_mn(bz, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, !first);
-        tc::mma_commit(&s.bar[1]);
-      }
-      first = false;
-      // src-CSR segmented sum of g_x1 * kern while the tensor core works
-#pragma unroll
-      for (int j = 0; j < kTE; ++j) {
-        if (j < cnt) {
-          const int sn = s.src[j];
-          while (cur < sn) { flush(cur); ++cur; }
-          const float4 m = ld4(s.GX + (16 * j + o) * kLDT + 4 * cg);
-          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
-        }
-      }
-      tc::mbar_wait(&s.bar[1], par1);
-      par1 ^= 1u;
-      tc::tc_fence_after();
-      {
-        const int j = row >> 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16];
-          tc::tmem_ld16(lane_addr + 64 + c0, v);
-          if (j < cnt) {
-            __nv_bfloat16* p = g_basis + (size_t)s.eid[j] * kRow + (row & 15) * kC + c0;
-            *reinterpret_cast<uint4*>(p) = tc::pack8(v);
-            *reinterpret_cast<uint4*>(p + 8) = tc::pack8(v + 8);
-          }
-        }
-      }
-      tc::tc_fence_before();
-    }
-    while (cur < n1) { flush(cur); ++cur; }
-  }
-  // gWk partial of this CTA: lanes 64..127 = rows c, columns j
-  __syncthreads();
-  tc::tc_fence_after();
-  float* P = d.edge_grad_partials + (size_t)blockIdx.x * kWFloats;
-#pragma unroll 1
-  for (int i = 0; i < 2; ++i) {
-    const int c0 = 32 * ch + 16 * i;
-    float v[16];
-    if (first) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = 0.f;
-    } else {
-      tc::tmem_ld16(lane_addr + 128 + c0, v);
-    }
-    if (row >= 64) {
-      float* p = P + (size_t)(row - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// (E3) v2: the same arithmetic in the same order (bit-identical results), restructured around latency:
+// (E3) structured around latency:
 //   * persistent CTAs own CONTIGUOUS src-node ranges holding equal shares of the edges (binary search in
 //     rowptr_src), so a CTA walks consecutive 8-entry tiles of the src-sorted list;
 //   * the (eid, src, dst) triples need two dependent global loads: they are fetched two tiles ahead into
@@ -207,7 +32,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc_kernel(const G
 //   * one tile ahead, threads 0..23 pull the rows the next tile will gather (basis 2 KB, g_x1 4 KB, x_src 4 KB per
 //     edge) into L2 with cp.async.bulk.prefetch.L2, so the cp.async gathers pay L2 hits, not DRAM round trips;
 //   * the residual row added at a node's flush (grad_x_src_init) is loaded when the node STARTS accumulating.
-// ncu r01 of the v1 kernel: smsp__issue_active 19 %, stall samples on the index loads (8 %), the gather issue and
+// ncu r01 of the block-interleaved, unpipelined version: smsp__issue_active 19 %, stall samples on the index loads (8 %), the gather issue and
 // wait (36 %) and the flush's dependent global load (14 %).
 // ---------------------------------------------------------------------------------------------------
 struct EdgeBwd2Smem {
@@ -233,7 +58,7 @@ __device__ __forceinline__ int node_lower_bound_src(const int32_t* __restrict__ 
   return lo;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const GrlConvDesc d, const int flags) {
+__global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const GrlConvDesc d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   EdgeBwd2Smem& s = *reinterpret_cast<EdgeBwd2Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -292,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
 
   // rows of tile t -> L2 (threads 0..23: 8 edges x {basis, g_x1, x_src}); slot (t & 3) must be visible
   auto prefetch_tile = [&](int t) {
-    if (!(flags & 1) && tid < 3 * kTE && t < n_tiles) {
+    if (tid < 3 * kTE && t < n_tiles) {
       const int j = tid & 7, which = tid >> 3;
       if (p0 + t * kTE + j < p1) {
         if (which == 0) tc::prefetch_l2(basis + (size_t)s.eid[t & 3][j] * kRow, kRow * 2u);
@@ -675,25 +500,13 @@ int grl_fbconv_edge_bwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
                   (d->n_edges == 0 || (d->src_eid && d->edge_src && d->edge_dst && d->basis_bf16 && d->grad_basis_bf16)),
               GRL_EINVAL, "grl_fbconv_edge_bwd_tc: null pointer");
   GRL_REQUIRE(d->n_partials_edge > 0, GRL_EINVAL, "grl_fbconv_edge_bwd_tc: n_partials_edge must be > 0");
-  static const bool use_v1 = getenv("GRL_EDGE_BWD_V1") != nullptr;
-  if (use_v1) {
-    static bool attr = false;
-    const int smem = (int)sizeof(grl::EdgeBwdTcSmem);
-    if (!attr) {
-      cudaFuncSetAttribute(grl::fbconv_edge_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr = true;
-    }
-    grl::fbconv_edge_bwd_tc_kernel<<<d->n_partials_edge, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
-    return grl::check_launch("grl_fbconv_edge_bwd_tc");
-  }
   static bool attr2 = false;
   const int smem2 = (int)sizeof(grl::EdgeBwd2Smem);
   if (!attr2) {
     cudaFuncSetAttribute(grl::fbconv_edge_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     attr2 = true;
   }
-  static const int flags = getenv("GRL_EB2_FLAGS") ? atoi(getenv("GRL_EB2_FLAGS")) : 0;
-  grl::fbconv_edge_bwd_tc2_kernel<<<d->n_partials_edge, grl::kThreads, smem2, (cudaStream_t)stream>>>(*d, flags);
+  grl::fbconv_edge_bwd_tc2_kernel<<<d->n_partials_edge, grl::kThreads, smem2, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_edge_bwd_tc");
 }
 

@@ -257,11 +257,14 @@ class FiberConvFn(torch.autograd.Function):
         assert tuple(x_src.shape[1:]) == (16, 64) and tuple(w1.shape) == (256, 64) and tuple(w2.shape) == (64, 256)
         wk_d, w1_d, w2_d = wk.detach(), w1.detach(), w2.detach()
         wk_c = _f32c(wk_d)
-        wk_t = wk_d.t().contiguous()
         w1_c = _f32c(w1_d)
-        w1_t = w1_d.view(4, 64, 64).transpose(1, 2).contiguous()
-        w2_t = w2_d.view(64, 4, 64).permute(1, 2, 0).contiguous()
-        w2_c = w2_d.view(64, 4, 64).permute(1, 0, 2).contiguous()
+        tc_edge, tc_node = basis.dtype == torch.bfloat16, precision == "bf16"
+        # transposed / chunked copies are operands of the strict FFMA kernels only (the tensor-core kernels stage the
+        # row-major weights themselves)
+        wk_t = wk_c if tc_edge else wk_d.t().contiguous()
+        w1_t = w1_c if tc_node else w1_d.view(4, 64, 64).transpose(1, 2).contiguous()
+        w2_t = w1_c if tc_node else w2_d.view(64, 4, 64).permute(1, 2, 0).contiguous()
+        w2_c = w1_c if tc_node else w2_d.view(64, 4, 64).permute(1, 0, 2).contiguous()
         bias_c, lng_c, lnb_c = _f32c(bias.detach()), _f32c(ln_g.detach()), _f32c(ln_b.detach())
         b1_c, b2_c = _f32c(b1.detach()), _f32c(b2.detach())
         x1 = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=dev)

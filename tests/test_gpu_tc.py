@@ -188,3 +188,50 @@ def test_policy_body_bf16_path_matches_reference_fixture_within_1e_2(name):
         if G.rel(params[k].grad, gref) >= 1e-2:
             bad.append(G.err_report(k, params[k].grad, gref))
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096 * 1024 + 5])
+def test_absmax_is_exact(n):
+    """grl_absmax returns the bit pattern of max |x| (NaNs ignored): it sets the power-of-two scale of the fp16
+    gradient operands, so it must be exact and order-independent."""
+    from geometry_rl_b200 import _lib as L
+    g = torch.Generator().manual_seed(n)
+    x = (torch.randn(n, generator=g) * 10 ** torch.randint(-6, 3, (n,), generator=g).float()).cuda()
+    if n > 3:
+        x[1] = float("nan")
+    out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("grl_absmax", L.ptr(x), n, L.ptr(out))
+    torch.cuda.synchronize()
+    ref = torch.nan_to_num(x, nan=0.0).abs().max()
+    assert out.view(torch.float32).item() == ref.item()
+
+
+@pytest.mark.parametrize("scale", [1e-7, 1.0, 3e4])
+def test_fiber_conv_backward_is_invariant_to_the_gradient_scale(scale):
+    """The tensor-core backward stages gradients as fp16 after multiplying them by a power of two taken from
+    grl_absmax(grad_out).  Gradients of the loss `scale * L` must therefore equal `scale` times those of L up to fp32
+    rounding, whether the incoming gradients are O(1e-7) (mean losses over large minibatches) or O(1e4)."""
+    from geometry_rl_b200 import ops
+    es, p = _conv_inputs(6, 21, 3, 31)
+    g = torch.Generator().manual_seed(9)
+    w = torch.randn(p["x"].shape, generator=g).cuda()
+    names = ["x", "basis", "fk", "wk", "bias", "ln_g", "ln_b", "w1", "b1", "w2", "b2"]
+    grads = {}
+    ops.set_precision("bf16")
+    try:
+        for sc in (1.0, scale):
+            leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+            out = ops.fiber_conv(leaves["x"], None, leaves["basis"], leaves["fk"], leaves["wk"], leaves["bias"], leaves["ln_g"],
+                                 leaves["ln_b"], leaves["w1"], leaves["b1"], leaves["w2"], leaves["b2"], es)
+            (out * (w * sc)).sum().backward()
+            grads[sc] = {k: leaves[k].grad.clone() for k in names}
+    finally:
+        ops.set_precision("fp32")
+    torch.cuda.synchronize()
+    pow2 = 2.0 ** round(torch.log2(torch.tensor(scale)).item())
+    for k in ["fk", "bias", "ln_g", "ln_b", "w1", "b1", "w2", "b2"]:  # produced by the node kernels
+        a, b = grads[scale][k] / scale, grads[1.0][k]
+        # exact when the scale is a power of two (the fp16 payload is then bit-identical), tiny otherwise
+        tol = 1e-6 if scale == pow2 else 2e-3
+        err = float((a - b).abs().max()) / float(b.abs().max())
+        assert err <= tol, f"{k}: gradient not scale-covariant (rel {err:.2e} at scale {scale})"
