@@ -77,7 +77,12 @@ class TRPLLoss(nn.Module):
             return x.mean()
         return x.sum() / (x.numel() * self.dp.world_size)
 
-    def forward(self, td) -> dict:
+    def critic_term(self, td) -> torch.Tensor:
+        """`loss_critic` entry of forward(): the critic branch shares nothing with the actor branch, so the learner
+        may evaluate (and differentiate) it on a second CUDA stream."""
+        return self._mean(self.loss_critic(td))
+
+    def forward(self, td, with_critic: bool = True) -> dict:
         advantage = td_get(td, "advantage")
         if self.normalize_advantage and advantage.numel() > 1:
             if self.dp is None:
@@ -103,8 +108,8 @@ class TRPLLoss(nn.Module):
             entropy = dist.entropy()
             out["entropy"] = self._mean(entropy).detach()
             out["loss_entropy"] = -self.entropy_coef * self._mean(entropy)
-        if self.critic_coef:
-            out["loss_critic"] = self._mean(self.loss_critic(td))
+        if self.critic_coef and with_critic:
+            out["loss_critic"] = self.critic_term(td)
         out["ESS"] = ess.mean() / batch
         # trpl.py:318-320: metrics compare p with the PROJECTED distribution (log_tr_metrics(..., p, proj_p))
         m = self.projection.compute_metrics(policy, (p[0].detach(), p[1].detach()), p_target, step=self._global_steps,

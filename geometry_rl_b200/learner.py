@@ -1,6 +1,7 @@
 """The learner side of examples/torchrl/train.py:134-146,249-316 without Hydra / collectors / logging:
 model assembly from a PathConfig (what AgentBuilder + make_ppo_models produce,
 examples/torchrl/builders/utils_algo_graph.py:208-276), the advantage phase and one minibatch update."""
+import os
 from typing import Dict, Optional
 
 import torch
@@ -105,9 +106,15 @@ def build_agent(cfg: PathConfig, device, proj_type: str = "kl", seed: int = 0):
 class Learner:
     """train.py:145-146 (two Adam optimisers, eps=1e-5) + one iteration of the minibatch loop (:275-316)."""
 
-    def __init__(self, cfg: PathConfig, actor, critic, loss_module, dp=None, fused_adam: bool = True):
+    def __init__(self, cfg: PathConfig, actor, critic, loss_module, dp=None, fused_adam: bool = True,
+                 overlap_critic: bool = True):
         self.cfg, self.actor, self.critic, self.loss_module, self.dp = cfg, actor, critic, loss_module, dp
         fused = fused_adam and next(actor.parameters()).is_cuda
+        # The critic branch (DeepSets forward, clipped value loss, backward: ~100 small launches) is independent of the
+        # actor branch until the optimiser steps: it runs on a second stream, under the actor's large kernels.
+        # Single process only: under data parallelism its graph-LayerNorm statistics are collectives.
+        self._critic_stream = (torch.cuda.Stream() if overlap_critic and (dp is None or os.environ.get('GRL_DP_OVERLAP')) and loss_module.critic_coef
+                               and next(actor.parameters()).is_cuda else None)
         # capturable: the step counter lives on the device, so the whole update can be replayed from a CUDA graph
         self.actor_optim = torch.optim.Adam(actor.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
         self.critic_optim = torch.optim.Adam(critic.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
@@ -123,6 +130,8 @@ class Learner:
         return loss
 
     def update(self, batch) -> Dict[str, torch.Tensor]:
+        if self._critic_stream is not None:
+            return self._update_two_streams(batch)
         loss = self.compute_losses(batch)
         self.num_network_updates += 1
         loss["actor_loss"].backward()
@@ -138,6 +147,32 @@ class Learner:
         self.critic_optim.zero_grad()
         return loss
 
+
+    def _update_two_streams(self, batch) -> Dict[str, torch.Tensor]:
+        """Same arithmetic as `update`; the critic loss and its backward are enqueued on `_critic_stream` (forked from
+        and joined to the current stream, so the pattern is also valid inside a CUDA-graph capture)."""
+        main, side = torch.cuda.current_stream(), self._critic_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            loss_critic = self.loss_module.critic_term(batch)
+            loss_critic.backward()  # autograd runs these nodes on the stream of their forward: `side`
+        self.loss_module._global_steps = self.num_network_updates
+        loss = self.loss_module(batch, with_critic=False)
+        loss["actor_loss"] = loss["loss_objective"] + loss["loss_entropy"] + loss["loss_trust_region"]
+        loss["loss_critic"] = loss_critic.detach()
+        self.num_network_updates += 1
+        loss["actor_loss"].backward()
+        main.wait_stream(side)
+        if self.dp is not None:
+            self.dp.allreduce_grads(list(self.actor.parameters()) + list(self.critic.parameters()))
+        if self.cfg.clip_grad_norm:
+            torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.cfg.max_grad_norm)
+            torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.cfg.max_grad_norm)
+        self.actor_optim.step()
+        self.critic_optim.step()
+        self.actor_optim.zero_grad()
+        self.critic_optim.zero_grad()
+        return loss
 
     # ---- CUDA-graph replay of the whole update (launch-bound glue: ~500 launches per step) -----------------------
     def capture(self, example_batch, warmup: int = 3):
