@@ -1,7 +1,6 @@
 """The learner side of examples/torchrl/train.py:134-146,249-316 without Hydra / collectors / logging:
 model assembly from a PathConfig (what AgentBuilder + make_ppo_models produce,
 examples/torchrl/builders/utils_algo_graph.py:208-276), the advantage phase and one minibatch update."""
-import os
 from typing import Dict, Optional
 
 import torch
@@ -112,8 +111,9 @@ class Learner:
         fused = fused_adam and next(actor.parameters()).is_cuda
         # The critic branch (DeepSets forward, clipped value loss, backward: ~100 small launches) is independent of the
         # actor branch until the optimiser steps: it runs on a second stream, under the actor's large kernels.
-        # Single process only: under data parallelism its graph-LayerNorm statistics are collectives.
-        self._critic_stream = (torch.cuda.Stream() if overlap_critic and (dp is None or os.environ.get('GRL_DP_OVERLAP')) and loss_module.critic_coef
+        # Single process only: under data parallelism its graph-LayerNorm statistics are collectives, which cannot start
+        # while a persistent kernel holds every SM (measured at 2 GPUs: no gain).
+        self._critic_stream = (torch.cuda.Stream() if overlap_critic and dp is None and loss_module.critic_coef
                                and next(actor.parameters()).is_cuda else None)
         # capturable: the step counter lives on the device, so the whole update can be replayed from a CUDA graph
         self.actor_optim = torch.optim.Adam(actor.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
@@ -163,8 +163,6 @@ class Learner:
         self.num_network_updates += 1
         loss["actor_loss"].backward()
         main.wait_stream(side)
-        if self.dp is not None:
-            self.dp.allreduce_grads(list(self.actor.parameters()) + list(self.critic.parameters()))
         if self.cfg.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.cfg.max_grad_norm)
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.cfg.max_grad_norm)
