@@ -1,6 +1,9 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small tracked text files under profiles/.
   python profiles/summarise.py launches gpurun_out/launches_r01.csv profiles/r01_launches.md
-  python profiles/summarise.py full     gpurun_out/prof_r01_conv.ncu-rep profiles/r01_conv_full.md"""
+  python profiles/summarise.py full     gpurun_out/prof_r01_conv.ncu-rep profiles/r01_conv_full.md
+  python profiles/summarise.py traffic  gpurun_out/prof_r01_conv.ncu-rep profiles/r01_traffic.json WORKLOAD MINIBATCH
+     (DRAM bytes per launch of every C-ABI entry point: what bench.py reports as roofline.traffic)"""
+import json
 import collections
 import csv
 import io
@@ -59,5 +62,48 @@ def full(src, dst):
     print(open(dst).read()[:6000])
 
 
+# C-ABI entry point -> the kernels one call launches
+ABI_KERNELS = {
+    "grl_fbconv_node_bwd_tc": ["fbconv_node_bwd_tc2_kernel", "fbconv_fiber_bwd_kernel"],
+    "grl_fbconv_node_fwd_tc": ["fbconv_node_fwd_tc2_kernel"],
+    "grl_fbconv_edge_fwd_tc": ["fbconv_edge_fwd_tc_kernel"],
+    "grl_fbconv_edge_bwd_tc": ["fbconv_edge_bwd_tc2_kernel"],
+    "grl_edge_basis_fwd_tc": ["edge_basis_fwd_tc_kernel"],
+    "grl_edge_basis_bwd_tc": ["edge_basis_bwd_tc_kernel"],
+    "grl_embed_fwd": ["embed_fwd_kernel"],
+    "grl_embed_bwd": ["embed_bwd_kernel"],
+    "grl_absmax": ["absmax_kernel"],
+}
+
+
+def traffic(src, dst, workload, minibatch):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_kernel = collections.defaultdict(list)
+    for r in data:
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
+        per_kernel[r[idx["Kernel Name"]]].append(b)
+    res = {}
+    for abi, kernels in ABI_KERNELS.items():
+        tot, ok = 0.0, True
+        for kn in kernels:
+            v = [x for name, xs in per_kernel.items() if kn in name for x in xs]
+            if not v:
+                ok = False
+                break
+            tot += sum(v) / len(v)
+        if ok:
+            res[abi] = tot
+    json.dump({"source": src, "workload": workload, "minibatch_per_gpu": int(minibatch),
+               "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the C-ABI entry point (mean over the captured launches)",
+               "kernels": res}, open(dst, "w"), indent=1)
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
