@@ -375,8 +375,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": args.config, "model": cfg.model, "mlp_precision": args.precision,
                        "parity": "1e-5 vs reference fp32" if args.precision == "fp32" else
-                                 "1e-2 vs reference fp32 (north_star bf16 MLP path: bf16 tcgen05 operands, fp32 accumulation; "
-                                 "latents, LayerNorm, segmented sums, projection, losses fp32)",
+                                 "1e-2 vs reference fp32 (north_star bf16 MLP path: 16-bit tcgen05 operands - fp16 in the node kernels with "
+                                 "power-of-two scaled gradients, bf16 in the edge kernels - fp32 accumulation; latents, LayerNorm, "
+                                 "segmented sums, projection, losses fp32)",
                        "cuda_graph": main_res["cuda_graph"], "minibatch_per_gpu": B, "global_minibatch": B * world,
                        "parallelism": f"dp{world}", "l2": f"rotating {N_ROTATE} minibatches; per-step working set "
                        f"(latents {B * 49 * 4096 / 1e6:.0f} MB each) exceeds the 126 MB L2"},
