@@ -29,7 +29,7 @@ __device__ __forceinline__ void cp_async16_any(void* smem_dst, const void* gmem_
 //     rowptr_src), so a CTA walks consecutive 8-entry tiles of the src-sorted list;
 //   * the (eid, src, dst) triples need two dependent global loads: they are fetched two tiles ahead into
 //     registers of threads 0..7 and published through a 4-deep shared-memory ring;
-//   * one tile ahead, threads 0..23 pull the rows the next tile will gather (basis 2 KB, g_x1 4 KB, x_src 4 KB per
+//   * one tile ahead, threads 0..31 pull the rows the next tile will gather (basis 2 KB, g_x1 4 KB, x_src 4 KB per
 //     edge) into L2 with cp.async.bulk.prefetch.L2, so the cp.async gathers pay L2 hits, not DRAM round trips;
 //   * the residual row added at a node's flush (grad_x_src_init) is loaded when the node STARTS accumulating.
 // ncu r01 of the block-interleaved, unpipelined version: smsp__issue_active 19 %, stall samples on the index loads (8 %), the gather issue and
@@ -117,12 +117,13 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
 
   // rows of tile t -> L2 (threads 0..23: 8 edges x {basis, g_x1, x_src}); slot (t & 3) must be visible
   auto prefetch_tile = [&](int t) {
-    if (tid < 3 * kTE && t < n_tiles) {
+    if (tid < 4 * kTE && t < n_tiles) {
       const int j = tid & 7, which = tid >> 3;
       if (p0 + t * kTE + j < p1) {
         if (which == 0) tc::prefetch_l2(basis + (size_t)s.eid[t & 3][j] * kRow, kRow * 2u);
         else if (which == 1) tc::prefetch_l2(d.grad_x1 + (size_t)s.dst[t & 3][j] * kRow, kRow * 4u);
-        else tc::prefetch_l2(d.x_src + (size_t)s.src[t & 3][j] * kRow, kRow * 4u);
+        else if (which == 2) tc::prefetch_l2(d.x_src + (size_t)s.src[t & 3][j] * kRow, kRow * 4u);
+        else if (d.accumulate_grad_basis) tc::prefetch_l2(g_basis + (size_t)s.eid[t & 3][j] * kRow, kRow * 2u);
       }
     }
   };
@@ -224,6 +225,13 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
       tc::mma_commit(&s.bar[1]);
     }
     first = false;
+    // another layer's share of the basis gradient (accumulate mode): requested before the segmented sum, used after the MMA wait
+    uint4 og[4];
+    if (d.accumulate_grad_basis && (row >> 4) < cnt) {
+      const uint4* p = reinterpret_cast<const uint4*>(g_basis + (size_t)s.eid[slot][row >> 4] * kRow + (row & 15) * kC + 32 * ch);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) og[i] = p[i];
+    }
     // src-CSR segmented sum of g_x1 * kern while the tensor core works
 #pragma unroll
     for (int j = 0; j < kTE; ++j) {
@@ -246,6 +254,17 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
         tc::tmem_ld16(lane_addr + 64 + c0, v);
         if (j < cnt) {
           __nv_bfloat16* p = g_basis + (size_t)s.eid[slot][j] * kRow + (row & 15) * kC + c0;
+          if (d.accumulate_grad_basis) {  // add in fp32, round once
+            const uint4 o0 = og[2 * i], o1 = og[2 * i + 1];
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&o0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&o1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = __bfloat1622float2(h0[e]), b = __bfloat1622float2(h1[e]);
+              v[2 * e] += a.x; v[2 * e + 1] += a.y;
+              v[8 + 2 * e] += b.x; v[8 + 2 * e + 1] += b.y;
+            }
+          }
           *reinterpret_cast<uint4*>(p) = tc::pack8(v);
           *reinterpret_cast<uint4*>(p + 8) = tc::pack8(v + 8);
         }

@@ -207,6 +207,13 @@ class EdgeBasisFn(torch.autograd.Function):
                    shape=(es.n_src, es.n_dst, es.n_edges))
         ctx.save_for_backward(pos_src, pos_dst, w1t, b1c, w2t, b2c, _f32c(w2.detach()), ori3)
         ctx.es, ctx.dim = es, dim
+        # One basis feeds every layer of the model.  Instead of letting autograd add the layers' [E,16,64] gradients
+        # with a separate kernel, the first FiberConvFn.backward to run returns its gradient buffer and the later ones
+        # accumulate into that same buffer inside the edge kernel (and return None).  This function's backward runs
+        # after all of them (topological order), so it sees the complete sum whichever subset of consumers ran.
+        ctx.gacc = {"buf": None}
+        if bf16:
+            basis._grl_gacc = ctx.gacc
         return basis
 
     @staticmethod
@@ -214,6 +221,7 @@ class EdgeBasisFn(torch.autograd.Function):
         pos_src, pos_dst, w1t, b1c, w2t, b2c, w2, ori3 = ctx.saved_tensors
         es, dim = ctx.es, ctx.dim
         dev = pos_src.device
+        ctx.gacc["buf"] = None  # a later backward through the same graph starts a fresh accumulation
         if es.n_edges == 0:
             z = torch.zeros
             return (None, None, z(64, 14, device=dev), z(64, device=dev), z(64, 64, device=dev), z(64, device=dev),
@@ -291,6 +299,7 @@ class FiberConvFn(torch.autograd.Function):
         ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1,
                               _f32c(w2_d) if precision == "bf16" else w2_c, x2)
         ctx.es, ctx.homo, ctx.precision, ctx.basis_in_dtype = es, homo, precision, basis_in_dtype
+        ctx.gacc = getattr(basis, "_grl_gacc", None) if tc_edge else None
         return out
 
     @staticmethod
@@ -302,7 +311,11 @@ class FiberConvFn(torch.autograd.Function):
         g_x1 = torch.empty_like(x1)
         g_xsrc = torch.empty_like(x_src)
         basis_bf16 = basis.dtype == torch.bfloat16
-        g_basis = torch.empty_like(basis)
+        gacc = ctx.gacc
+        acc_basis = gacc is not None and gacc["buf"] is not None
+        g_basis = gacc["buf"] if acc_basis else torch.empty_like(basis)
+        if gacc is not None and not acc_basis:
+            gacc["buf"] = g_basis
         n_pn = _n_partials((es.n_dst + 7) // 8)
         n_pe = _n_partials((es.n_src + 15) // 16, 2 if basis_bf16 else 1)
         node_part = torch.empty(n_pn, L.NODE_GRAD_FLOATS, dtype=torch.float32, device=dev)
@@ -316,7 +329,7 @@ class FiberConvFn(torch.autograd.Function):
                           grad_out=L.ptr(g_out), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),
                           grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=None if basis_bf16 else L.ptr(g_basis),
                           grad_basis_bf16=L.ptr(g_basis) if basis_bf16 else None,
-                          accumulate_grad_basis=0, node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
+                          accumulate_grad_basis=int(acc_basis), node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
         shape = (es.n_src, es.n_dst, es.n_edges)
         if ctx.precision == "bf16":
@@ -340,7 +353,9 @@ class FiberConvFn(torch.autograd.Function):
         gfk = g[o:o + 16 * 16 * 64].view(16, 16, 64)
         gwk = _reduce(edge_part).view(64, 64)
         g_xdst = None if homo else g_out
-        if g_basis.dtype != ctx.basis_in_dtype:
+        if acc_basis:
+            g_basis = None  # already inside the buffer the first consumer handed to autograd
+        elif g_basis.dtype != ctx.basis_in_dtype:
             g_basis = g_basis.to(ctx.basis_in_dtype)
         return g_xsrc, g_xdst, g_basis, gfk, gwk, gbias, glng, glnb, gw1, gb1, gw2, gb2, None
 
