@@ -210,7 +210,7 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
     import torch.distributed as dist
     from geometry_rl_b200 import _lib, learner, ops
     from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs
-    from geometry_rl_b200.smoke import to_device
+    from geometry_rl_b200.tensors import to_device
 
     # strict mode: fp32 everywhere.  bf16 mode: the library GEMMs of the DeepSets critic / heads may use TF32, as the
     # reference itself does on GPU (examples/torchrl/train.py:29-30)

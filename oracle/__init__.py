@@ -5,7 +5,7 @@ CPU (torch fp32 / fp64) restatement of the reference's policy-training hot path
 TRPL loss).  Every function cites the reference file:line it follows (paths relative to the
 reference checkout, `/root/reference` in the build container).
 
-Who may import this package: `tests/`, `__graft_entry__.smoke()` (as the checker) and
+Who may import this package: `tests/`, `__graft_entry__.smoke()` (through `smoke_check.py`, as the checker) and
 `bench.py`'s `cpu_baseline` / `--impl reference` legs.  Nothing under `geometry_rl_b200/` imports
 it; the product path raises if its CUDA library is missing instead of falling back to this code.
 

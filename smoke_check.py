@@ -1,15 +1,13 @@
-"""smoke(): one small HEPi update step + GAE on cuda:0, checked against the CPU oracle (the oracle is the
-checker here, never the thing run: every product tensor below comes out of libgrl_b200 / torch CUDA)."""
+"""Checker behind __graft_entry__.smoke(): one small HEPi update step + GAE on cuda:0, compared with the CPU oracle.
+The oracle is the checker here, never the thing run: every product tensor below comes out of libgrl_b200 / torch CUDA.
+Lives at the repo root (not inside geometry_rl_b200/) because it imports oracle/, which the product package must not."""
 import torch
 
 
-def to_device(batch, device):
-    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
-
-
 def run_smoke(cfg_name: str = "rigid_insertion_multi_hepi_trpl_cfg", B: int = 32, verbose: bool = True):
-    from . import learner
-    from .synthetic import CONFIGS, synthetic_obs, synthetic_rollout
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.synthetic import CONFIGS, synthetic_obs, synthetic_rollout
+    from geometry_rl_b200.tensors import to_device
     from oracle.step import OracleAgent, make_minibatch
 
     dev = torch.device("cuda:0")

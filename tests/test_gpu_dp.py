@@ -27,7 +27,7 @@ def _free_port():
 
 def _setup(dev):
     from geometry_rl_b200 import learner
-    from geometry_rl_b200.smoke import to_device
+    from geometry_rl_b200.tensors import to_device
     from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs
     cfg = CONFIGS[CFG]
     actor, critic, _, loss_module, _ = learner.build_agent(cfg, dev, seed=0)
@@ -51,7 +51,7 @@ def _worker(rank, world, port, out_path):
     try:
         from geometry_rl_b200 import learner
         from geometry_rl_b200.parallel import DataParallel
-        from geometry_rl_b200.smoke import to_device
+        from geometry_rl_b200.tensors import to_device
         dev = torch.device("cuda", rank if torch.cuda.device_count() >= world else 0)
         torch.cuda.set_device(dev)
         cfg, actor, critic, loss_module, mb = _setup(dev)
@@ -75,7 +75,7 @@ def _worker(rank, world, port, out_path):
 
 def test_two_rank_step_equals_single_process(tmp_path):
     from geometry_rl_b200 import learner
-    from geometry_rl_b200.smoke import to_device
+    from geometry_rl_b200.tensors import to_device
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     out_path = str(tmp_path / "rank0.pt")

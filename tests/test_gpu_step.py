@@ -20,7 +20,7 @@ SIZES = {"rigid_insertion_multi_hepi_trpl_cfg": 48, "rigid_pushing_multi_empn_tr
 
 def _setup(cfg_name, proj_type="kl", seed=0):
     from geometry_rl_b200 import learner
-    from geometry_rl_b200.smoke import to_device
+    from geometry_rl_b200.tensors import to_device
     from oracle.step import OracleAgent, make_minibatch
     cfg = CONFIGS[cfg_name]
     B = SIZES[cfg_name]
@@ -43,7 +43,7 @@ def test_update_step_matches_oracle(cfg_name, proj_type):
     if proj_type == "w2" and cfg_name not in ("rigid_insertion_multi_hepi_trpl_cfg", "cloth_hanging_multi_hepi_trpl_cfg"):
         pytest.skip("W2 covered on two configs")
     from geometry_rl_b200 import learner
-    from geometry_rl_b200.smoke import to_device
+    from geometry_rl_b200.tensors import to_device
     cfg, actor, critic, loss_module, _, oracle, mb, _ = _setup(cfg_name, proj_type)
     ref, ga, gc = oracle.step_grads(mb)
     lrn = learner.Learner(cfg, actor, critic, loss_module)
@@ -127,7 +127,7 @@ def test_learner_update_changes_parameters_and_is_deterministic():
     """Two learners from the same seed fed the same minibatch end with bit-identical parameters
     (deterministic segmented sums and fixed-order partial reductions: no atomics anywhere)."""
     from geometry_rl_b200 import learner
-    from geometry_rl_b200.smoke import to_device
+    from geometry_rl_b200.tensors import to_device
     res = []
     for _ in range(2):
         cfg, actor, critic, loss_module, _, _, mb, _ = _setup("rigid_insertion_multi_hepi_trpl_cfg", seed=3)

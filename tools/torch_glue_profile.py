@@ -8,7 +8,7 @@ import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 from geometry_rl_b200 import learner, ops  # noqa: E402
-from geometry_rl_b200.smoke import to_device  # noqa: E402
+from geometry_rl_b200.tensors import to_device  # noqa: E402
 from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs  # noqa: E402
 
 cfg = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "rigid_pushing_multi_empn_trpl_cfg"]
