@@ -45,7 +45,8 @@ static_assert(kPGFK + kO * kO * kC == GRL_NODE_GRAD_FLOATS, "partial layout");
 //     retired, and pulled into L2 one tile earlier still.
 //   * no fibre recompute: the forward kernel saves the pre-LayerNorm tensor x2 (GrlConvDesc.x2) and this kernel
 //     streams it back with cp.async (the fibre phase was 20 % of the stall samples of the recomputing version);
-//   * half 0 never waits on its gY / dW MMAs: the tensor pipe retires MMAs in issue order, so the next wait covers them.
+//   * half 0 never waits on its gY / dW MMAs: they are issued behind pre(1) and retire under the next epilogue (the
+//     tensor pipe completes MMAs in issue order, so a later wait covers them).
 // TMEM columns: D 0..127 | gY 128..191 | dW1 192..351 (2 x 80) | dW2^T 352..479 (2 x 64).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kNB2Threads = 512;
@@ -234,6 +235,15 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
         tc::issue_mma(tmem + kCol2D, tc::view_k(a1, kTM), tc::view_k(w1 + 128 * h2 * 16, kH),
                       tc::idesc_f16_ex(128, 128, 0, 0, 0, 0), kKb / 16, false);
         tc::mma_commit(&s.bar[0]);
+        if (h2 == 1) {
+          // half 0's gY / dW1 are issued BEHIND pre(1): the GELU epilogue below only waits for pre(1), and these two
+          // (576 tensor-pipe cycles) run underneath it.  They read AP(0) / A1, which nobody writes before the wait on
+          // gH(1) (bar[1]) that, by in-order completion, also covers them.
+          tc::issue_mma(tmem + kCol2GY, tc::view_k(ap, kTM), tc::view_mn(w1, kH), tc::idesc_f16_ex(128, 64, 0, 1, 0, 0),
+                        128 / 16, false);
+          tc::issue_mma(tmem + kCol2DW1, tc::view_mn(ap, kTM), tc::view_mn(a1, kTM), tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0),
+                        kTM / 16, !first_tile);
+        }
       }
       tc::mbar_wait(&s.bar[0], par0);
       par0 ^= 1u;
@@ -285,20 +295,19 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
         *reinterpret_cast<uint4*>(s.u.h.AP + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8_h(v);
         *reinterpret_cast<uint4*>(s.u.h.AP + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8_h(v + 8);
       }
+      if (h2 == 0) continue;  // half 0's gY / dW1 are issued at the top of the next iteration, behind pre(1)
       tc::fence_async_smem();
       tc::tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc::tc_fence_after();
         // gY' += gPre' W1[half]   (W1h read MN-major: N = c, K = k')
-        tc::issue_mma(tmem + kCol2GY, tc::view_k(ap, kTM), tc::view_mn(w1 + 128 * h2 * 16, kH),
-                      tc::idesc_f16_ex(128, 64, 0, 1, 0, 0), 128 / 16, h2 > 0);
+        tc::issue_mma(tmem + kCol2GY, tc::view_k(ap, kTM), tc::view_mn(w1 + 128 * 16, kH),
+                      tc::idesc_f16_ex(128, 64, 0, 1, 0, 0), 128 / 16, true);
         // [dW1' | gb1'][k'][c] += gPre'^T [y | 1 1 0..]
-        tc::issue_mma(tmem + kCol2DW1 + kKb * h2, tc::view_mn(ap, kTM), tc::view_mn(a1, kTM),
+        tc::issue_mma(tmem + kCol2DW1 + kKb, tc::view_mn(ap, kTM), tc::view_mn(a1, kTM),
                       tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0), kTM / 16, !first_tile);
-        // half 0: no wait here. The tensor pipe completes MMAs in issue order, so the wait on pre(1) (bar[0], issued
-        // after these) also covers dW2(0), gY(0) and dW1(0) before A2h / AP are overwritten.
-        if (h2 == 1) tc::mma_commit(&s.bar[2]);
+        tc::mma_commit(&s.bar[2]);
       }
     }
     tc::mbar_wait(&s.bar[2], par2);  // everything of this tile is complete: gY is final, the operand buffers are free
