@@ -7,6 +7,7 @@ addition, the sorted-CSR `EdgeSet`s the CUDA kernels consume.  Topology lives on
 by the K1 kernels (ops.knn_graph / dense_edges / build_edge_set); it is constructed once per batch
 size and re-used, exactly like the reference's cached placeholder (rigid_tasks_data.py:254-255).
 """
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -24,6 +25,21 @@ class NodeStore:
         self.pos: Optional[torch.Tensor] = None
         self.norm_pos: Optional[torch.Tensor] = None
         self.properties: Optional[torch.Tensor] = None
+
+
+@dataclass
+class PrunedHomo:
+    """Homogeneous topology restricted to the rows that can influence the readout (built once per topology).
+
+    `es` is the homogeneous edge set over the LIVE nodes only: a node is dropped when it has no edge at all and is
+    not an output node (the zero-padded object points of rigid_tasks_data.py:272-300, isolated target nodes) — its
+    latent row never reaches an output, so neither the forward values read by anybody nor any gradient change.
+    The edge order (dst-sorted, ties in COO order) is that of the full set: the renumbering is monotone.
+    `sub` is the bipartite set "live nodes -> output nodes" of the LAST layer, whose result is only read at the
+    output nodes (ponita_gcn.py:132-146 slices `output_mask` out of the last latent)."""
+    live_ids: torch.Tensor  # [n_live] int64: full (padded) node index of every live node, ascending
+    es: ops.EdgeSet  # n_src = n_dst = n_live, all E edges, compact node ids
+    sub: ops.SubEdgeSet
 
 
 class GraphBatch:
@@ -110,3 +126,30 @@ class GraphBatch:
                 before = before + cnt
             self._homo_cache["homo"] = ops.build_edge_set(coo[:, :E], homo_ptr, B, n_tot, n_tot)
         return self._homo_cache["homo"]
+
+    def homogeneous_pruned(self) -> PrunedHomo:
+        """See PrunedHomo.  Derived from `homogeneous()` with a handful of torch index ops, once per topology."""
+        if "pruned" not in self._homo_cache:
+            es = self.homogeneous()
+            B, dev = self.num_graphs, self.device
+            n_tot = sum(self.nodes_per_graph.values())
+            is_out = torch.zeros(n_tot, dtype=torch.bool, device=dev)
+            is_out[self.output_mask] = True
+            is_out = is_out.repeat(B)
+            deg_in = es.rowptr_dst[1:] - es.rowptr_dst[:-1]
+            deg_out = es.rowptr_src[1:] - es.rowptr_src[:-1]
+            live = (deg_in > 0) | (deg_out > 0) | is_out
+            live_ids = live.nonzero().squeeze(1)
+            n_live = int(live_ids.numel())
+            new_id = torch.cumsum(live.to(torch.int64), 0) - 1
+            edge_src = new_id[es.edge_src.long()].to(torch.int32).contiguous()
+            edge_dst = new_id[es.edge_dst.long()].to(torch.int32).contiguous()
+            # dropped nodes own no edges, so their CSR rows are empty and can simply be removed
+            rowptr_dst = torch.cat([es.rowptr_dst[:-1][live_ids], es.rowptr_dst[-1:]]).contiguous()
+            rowptr_src = torch.cat([es.rowptr_src[:-1][live_ids], es.rowptr_src[-1:]]).contiguous()
+            compact = ops.EdgeSet(n_live, n_live, es.n_edges, es.coo, es.edge_ptr, rowptr_dst, edge_src, edge_dst,
+                                  es.eid_coo, rowptr_src, es.src_eid)
+            out_ids = new_id[is_out.nonzero().squeeze(1)]
+            sub = ops.build_sub_edge_set(compact, out_ids)
+            self._homo_cache["pruned"] = PrunedHomo(live_ids, compact, sub)
+        return self._homo_cache["pruned"]

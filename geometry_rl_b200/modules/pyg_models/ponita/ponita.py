@@ -115,15 +115,18 @@ class SeparableFiberBundleConvNext(nn.Module):
         self.register_buffer("layer_scale", None)
         self.norm = nn.LayerNorm(channels)
 
-    def forward(self, x, kernel_basis, fiber_kernel_basis, edge_set: ops.EdgeSet):
+    def forward(self, x, kernel_basis, fiber_kernel_basis, edge_set: ops.EdgeSet, sub: Optional[ops.SubEdgeSet] = None):
+        """`sub`: evaluate the layer at the rows `sub.out_ids` only (returns [len(out_ids), 16, 64])."""
         c = self.conv
         fk = F.linear(fiber_kernel_basis, c.fiber_kernel.weight)  # [p, o, c] (ponita.py:166 "boc,poc->bpc")
         fk_op = fk.transpose(0, 1).contiguous()  # kernel layout [o][p][c]
         pending = None
         if self.training and not c.is_callibrated():
+            assert sub is None, "the one-time calibration needs the statistics of ALL rows (ponita.py:178-192)"
             pending = self._callibration_factors(x, kernel_basis, fk_op, edge_set)
         out = ops.fiber_conv(x, None, kernel_basis, fk_op, c.kernel.weight, c.bias, self.norm.weight, self.norm.bias,
-                             self.linear_1.weight, self.linear_1.bias, self.linear_2.weight, self.linear_2.bias, edge_set)
+                             self.linear_1.weight, self.linear_1.bias, self.linear_2.weight, self.linear_2.bias, edge_set,
+                             sub)
         if pending is not None:
             # ponita.py:178-192: the kernels are re-scaled after this forward consumed the un-calibrated ones
             c.kernel.weight.data = c.kernel.weight.data * pending[0]
@@ -174,14 +177,19 @@ class Ponita(nn.Module):
         inv3 = (g[None, :, :] * g[:, None, :]).sum(-1, keepdim=True)  # [16,16,1]
         return self.fiber_basis_fn(inv3)
 
-    def forward(self, scalars, vectors, pos, edge_set: ops.EdgeSet, batch=None):
-        """scalars [N,S], vectors [N,3V] (un-lifted), pos [N,3] -> latent [N,16,64]."""
+    def calibration_pending(self) -> bool:
+        return self.training and any(not l.conv.is_callibrated() for l in self.interaction_layers)
+
+    def forward(self, scalars, vectors, pos, edge_set: ops.EdgeSet, batch=None, last_sub: Optional[ops.SubEdgeSet] = None):
+        """scalars [N,S], vectors [N,3V] (un-lifted), pos [N,3] -> latent [N,16,64]; with `last_sub` the last layer is
+        evaluated at `last_sub.out_ids` only and the result is [len(out_ids),16,64]."""
         ori3 = pad_ori3(self.ori_grid)
         bf = self.basis_fn
         kernel_basis = ops.EdgeBasisFn.apply(pos, pos, bf[1].weight, bf[1].bias, bf[3].weight, bf[3].bias, ori3, self.dim,
                                              edge_set)
         fiber_kernel_basis = self.fiber_basis()
         x = ops.EmbedFn.apply(scalars, vectors, self.x_embedder.weight, ori3, self.dim)
-        for layer in self.interaction_layers:
-            x = layer(x, kernel_basis, fiber_kernel_basis, edge_set)
+        n_layers = len(self.interaction_layers)
+        for i, layer in enumerate(self.interaction_layers):
+            x = layer(x, kernel_basis, fiber_kernel_basis, edge_set, last_sub if i == n_layers - 1 else None)
         return x

@@ -22,6 +22,11 @@ class PonitaGCN(torch.nn.Module):
                              last_feature_conditioning=False, task_level="node", attention=attention,
                              only_upper_hemisphere=only_upper_hemisphere)
         self.linear = Linear(hidden_dim, output_dim + output_dim_vec)
+        # Evaluate only the latent rows that can reach the readout: nodes without any edge that are not output nodes
+        # (zero-padded object points) are dropped from every layer, and the last layer is computed at the output nodes
+        # alone.  The reference computes those rows and then discards them (ponita_gcn.py:132-146 masks the last
+        # latent); outputs and every parameter gradient are unchanged.  False = dense evaluation of all B*n rows.
+        self.prune_dead_rows = True
 
     @property
     def device(self):
@@ -41,10 +46,19 @@ class PonitaGCN(torch.nn.Module):
             pos = torch.cat([graph[t].pos.reshape(B, -1, 3) for t in graph.node_types], dim=1)
             n_per_graph = sc.shape[1]
             sc, vc, pos = sc.reshape(B * n_per_graph, -1), vc.reshape(B * n_per_graph, -1), pos.reshape(-1, 3)
-            edge_set = graph.homogeneous()
-        hidden = self.ponita(sc, vc, pos, edge_set)  # [B*n, 16, 64]
-        # ponita_gcn.py:132-146 reads out every node and then masks; reading out the masked nodes is the same
-        m = graph.output_mask
-        latent = hidden.reshape(B, n_per_graph, 16, -1)[:, m].reshape(-1, 16, hidden.shape[-1])
+            # the one-time calibration (ponita.py:178-192) takes statistics over ALL rows: that call runs dense
+            pruned = graph.homogeneous_pruned() if (self.prune_dead_rows and not self.ponita.calibration_pending()) else None
+            if pruned is not None:
+                sc, vc, pos = sc[pruned.live_ids], vc[pruned.live_ids], pos[pruned.live_ids]
+            else:
+                edge_set = graph.homogeneous()
+        if pruned is not None:
+            # [B*A, 16, 64]: rows of the output nodes, graph-major like the masked slice below
+            latent = self.ponita(sc, vc, pos, pruned.es, last_sub=pruned.sub)
+        else:
+            hidden = self.ponita(sc, vc, pos, edge_set)  # [B*n, 16, 64]
+            # ponita_gcn.py:132-146 reads out every node and then masks; reading out the masked nodes is the same
+            m = graph.output_mask
+            latent = hidden.reshape(B, n_per_graph, 16, -1)[:, m].reshape(-1, 16, hidden.shape[-1])
         return equivariant_readout(latent, self.linear, self.ponita.ori_grid, self.output_dim, self.output_dim_vec,
                                    self.dim)

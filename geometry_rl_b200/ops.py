@@ -62,6 +62,49 @@ class EdgeSet:
     src_eid: torch.Tensor  # [E] int32: src-sorted entry -> edge-order position
 
 
+@dataclass
+class SubEdgeSet:
+    """The edges of a homogeneous `EdgeSet` that END in a given set of nodes (`out_ids`), as a bipartite set
+    "all nodes -> those nodes" for a layer whose result is only read there (the last EMPN layer).
+
+    Forward arrays are contiguous in sub-edge order (= the parent's dst-sorted order restricted to the subset, so the
+    segmented sums add the same edges in the same order); the backward walks the subset in src-sorted order and
+    addresses the PARENT's per-edge arrays (basis, basis gradient, edge_src) through `src_eid_parent`."""
+    n_src: int
+    n_dst: int  # = len(out_ids)
+    n_edges: int
+    out_ids: torch.Tensor  # [n_dst] int64, ascending: row of the parent's node tensor behind every dst row
+    eids: torch.Tensor  # [E_sub] int64, ascending: position of every sub-edge in the parent's edge order
+    rowptr_dst: torch.Tensor  # [n_dst+1] int32
+    edge_src: torch.Tensor  # [E_sub] int32 (parent node ids)
+    edge_dst: torch.Tensor  # [E_sub] int32 (0..n_dst-1)
+    rowptr_src: torch.Tensor  # [n_src+1] int32
+    src_eid_parent: torch.Tensor  # [E_sub] int32: src-sorted entry -> position in the PARENT's edge order
+    edge_dst_parent: torch.Tensor  # [E_parent] int32: dst rank (0..n_dst-1) of every parent edge (0 outside the subset)
+
+
+def build_sub_edge_set(es: "EdgeSet", out_ids: torch.Tensor) -> SubEdgeSet:
+    assert es.n_src == es.n_dst, "sub edge sets are derived from homogeneous graphs"
+    dev = es.edge_src.device
+    n_out = int(out_ids.numel())
+    rank = torch.full((es.n_dst,), -1, dtype=torch.int64, device=dev)
+    rank[out_ids] = torch.arange(n_out, device=dev)
+    dst_rank = rank[es.edge_dst.long()]
+    eids = (dst_rank >= 0).nonzero().squeeze(1)
+    edge_src = es.edge_src[eids].contiguous()
+    edge_dst = dst_rank[eids].to(torch.int32).contiguous()
+
+    def rowptr(keys, n):
+        rp = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(torch.bincount(keys.long(), minlength=n), 0)
+        return rp.to(torch.int32).contiguous()
+
+    order = torch.sort(edge_src.long(), stable=True).indices  # ties keep edge order, like grl_csr_build
+    return SubEdgeSet(es.n_src, n_out, int(eids.numel()), out_ids.contiguous(), eids.contiguous(),
+                      rowptr(edge_dst, n_out), edge_src, edge_dst, rowptr(edge_src, es.n_src),
+                      eids[order].to(torch.int32).contiguous(), dst_rank.clamp_min(0).to(torch.int32).contiguous())
+
+
 def knn_edge_ptr(num_valid: Optional[torch.Tensor], B: int, P: int, k: int, device) -> torch.Tensor:
     edge_ptr = torch.empty(B + 1, dtype=torch.int64, device=device)
     L.call("grl_knn_edge_ptr", L.ptr(num_valid), B, P, k, L.ptr(edge_ptr))
@@ -249,19 +292,30 @@ class EdgeBasisFn(torch.autograd.Function):
 class FiberConvFn(torch.autograd.Function):
     """out = x_dst + MLP(LN(fibre(scatter(kernel(basis) * x_src[src])) + bias)).
 
-    `x_dst is None` means a homogeneous graph (source and destination nodes are the same tensor)."""
+    `x_dst is None` means a homogeneous graph (source and destination nodes are the same tensor).  With `sub`
+    (homogeneous graphs only) the layer is evaluated at the rows `sub.out_ids` alone: `out` is [len(out_ids), 16, 64],
+    only the edges ending there are visited, `basis` stays the parent's full [E, 16, 64] tensor."""
 
     @staticmethod
-    def forward(ctx, x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet):
+    def forward(ctx, x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet,
+                sub: Optional[SubEdgeSet] = None):
         homo = x_dst is None
         x_src = _f32c(x_src)
-        xd = x_src if homo else _f32c(x_dst)
+        if sub is not None:
+            assert homo and sub.n_src == es.n_src
+            xd = x_src.index_select(0, sub.out_ids)
+        else:
+            xd = x_src if homo else _f32c(x_dst)
         precision = _PRECISION if "node" in _TC_PARTS else "fp32"
         basis_in_dtype = basis.dtype
         basis = basis.contiguous() if (precision == "bf16" and basis.dtype == torch.bfloat16) else _f32c(basis)
         fk = _f32c(fk)
         dev = x_src.device
-        assert x_src.shape[0] == es.n_src and xd.shape[0] == es.n_dst, "latent rows do not match the edge set"
+        basis_full = basis
+        if sub is not None:  # forward reads the basis contiguously in edge order: compact copy of the subset's rows
+            basis = basis.index_select(0, sub.eids)
+        top = sub if sub is not None else es  # topology of the forward kernels
+        assert x_src.shape[0] == top.n_src and xd.shape[0] == top.n_dst, "latent rows do not match the edge set"
         assert tuple(x_src.shape[1:]) == (16, 64) and tuple(w1.shape) == (256, 64) and tuple(w2.shape) == (64, 256)
         wk_d, w1_d, w2_d = wk.detach(), w1.detach(), w2.detach()
         wk_c = _f32c(wk_d)
@@ -275,17 +329,17 @@ class FiberConvFn(torch.autograd.Function):
         w2_c = w1_c if tc_node else w2_d.view(64, 4, 64).permute(1, 0, 2).contiguous()
         bias_c, lng_c, lnb_c = _f32c(bias.detach()), _f32c(ln_g.detach()), _f32c(ln_b.detach())
         b1_c, b2_c = _f32c(b1.detach()), _f32c(b2.detach())
-        x1 = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=dev)
-        out = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=dev)
-        d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
-                          edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), rowptr_src=L.ptr(es.rowptr_src),
-                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), x_dst=L.ptr(xd),
+        x1 = torch.empty(top.n_dst, 16, 64, dtype=torch.float32, device=dev)
+        out = torch.empty(top.n_dst, 16, 64, dtype=torch.float32, device=dev)
+        d = L.GrlConvDesc(n_src=top.n_src, n_dst=top.n_dst, n_edges=top.n_edges, rowptr_dst=L.ptr(top.rowptr_dst),
+                          edge_src=L.ptr(top.edge_src), edge_dst=L.ptr(top.edge_dst), rowptr_src=L.ptr(top.rowptr_src),
+                          src_eid=None if sub is not None else L.ptr(es.src_eid), x_src=L.ptr(x_src), x_dst=L.ptr(xd),
                           basis=L.ptr(basis) if basis.dtype == torch.float32 else None,
                           basis_bf16=L.ptr(basis) if basis.dtype == torch.bfloat16 else None,
                           fiber_kernel=L.ptr(fk), wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
                           ln_b=L.ptr(lnb_c), w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_t=L.ptr(w2_t),
                           w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
-        shape = (es.n_src, es.n_dst, es.n_edges)
+        shape = (top.n_src, top.n_dst, top.n_edges)
         L.call("grl_fbconv_edge_fwd_tc" if basis.dtype == torch.bfloat16 else "grl_fbconv_edge_fwd", C.byref(d), shape=shape)
         x2 = x1  # placeholder so that save_for_backward has a tensor in the strict path
         if precision == "bf16":
@@ -296,16 +350,17 @@ class FiberConvFn(torch.autograd.Function):
             L.call("grl_fbconv_node_fwd_tc", C.byref(d), shape=shape)
         else:
             L.call("grl_fbconv_node_fwd", C.byref(d), shape=shape)
-        ctx.save_for_backward(x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1,
-                              _f32c(w2_d) if precision == "bf16" else w2_c, x2)
-        ctx.es, ctx.homo, ctx.precision, ctx.basis_in_dtype = es, homo, precision, basis_in_dtype
-        ctx.gacc = getattr(basis, "_grl_gacc", None) if tc_edge else None
+        ctx.save_for_backward(x_src, basis_full if sub is not None else basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t,
+                              w1_c, b1_c, w2_c, x1, _f32c(w2_d) if precision == "bf16" else w2_c, x2)
+        ctx.es, ctx.sub, ctx.homo, ctx.precision, ctx.basis_in_dtype = es, sub, homo, precision, basis_in_dtype
+        ctx.gacc = getattr(basis_full, "_grl_gacc", None) if tc_edge else None
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         x_src, basis, fk, wk_t, wk_c, bias_c, lng_c, lnb_c, w1_t, w1_c, b1_c, w2_c, x1, w2_rm, x2 = ctx.saved_tensors
-        es, homo = ctx.es, ctx.homo
+        es, sub, homo = ctx.es, ctx.sub, ctx.homo
+        top = sub if sub is not None else es
         dev = x_src.device
         g_out = _f32c(g_out)
         g_x1 = torch.empty_like(x1)
@@ -313,25 +368,31 @@ class FiberConvFn(torch.autograd.Function):
         basis_bf16 = basis.dtype == torch.bfloat16
         gacc = ctx.gacc
         acc_basis = gacc is not None and gacc["buf"] is not None
-        g_basis = gacc["buf"] if acc_basis else torch.empty_like(basis)
+        # a sub layer writes the rows of its own edges only: the rest of a fresh buffer must read as zero
+        g_basis = gacc["buf"] if acc_basis else (torch.zeros_like(basis) if sub is not None else torch.empty_like(basis))
         if gacc is not None and not acc_basis:
             gacc["buf"] = g_basis
-        n_pn = _n_partials((es.n_dst + 7) // 8)
-        n_pe = _n_partials((es.n_src + 15) // 16, 2 if basis_bf16 else 1)
+        n_pn = _n_partials((top.n_dst + 7) // 8)
+        n_pe = _n_partials((top.n_src + 15) // 16, 2 if basis_bf16 else 1)
         node_part = torch.empty(n_pn, L.NODE_GRAD_FLOATS, dtype=torch.float32, device=dev)
         edge_part = torch.empty(n_pe, L.EDGE_GRAD_FLOATS, dtype=torch.float32, device=dev)
-        d = L.GrlConvDesc(n_src=es.n_src, n_dst=es.n_dst, n_edges=es.n_edges, rowptr_dst=L.ptr(es.rowptr_dst),
-                          edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(es.edge_dst), rowptr_src=L.ptr(es.rowptr_src),
-                          src_eid=L.ptr(es.src_eid), x_src=L.ptr(x_src), basis=None if basis_bf16 else L.ptr(basis),
+        # the edge backward reaches per-edge data through src_eid: for a sub layer that is the parent's edge order, so
+        # basis / grad_basis / edge_src are the parent's arrays and edge_dst the parent-order dst ranks
+        d = L.GrlConvDesc(n_src=top.n_src, n_dst=top.n_dst, n_edges=top.n_edges, rowptr_dst=L.ptr(top.rowptr_dst),
+                          edge_src=L.ptr(es.edge_src), edge_dst=L.ptr(sub.edge_dst_parent if sub is not None else es.edge_dst),
+                          rowptr_src=L.ptr(top.rowptr_src),
+                          src_eid=L.ptr(sub.src_eid_parent if sub is not None else es.src_eid), x_src=L.ptr(x_src),
+                          basis=None if basis_bf16 else L.ptr(basis),
                           basis_bf16=L.ptr(basis) if basis_bf16 else None, fiber_kernel=L.ptr(fk),
                           wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c), ln_b=L.ptr(lnb_c),
                           w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_c=L.ptr(w2_c), x1=L.ptr(x1),
                           grad_out=L.ptr(g_out), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),
-                          grad_x_src_init=L.ptr(g_out) if homo else None, grad_basis=None if basis_bf16 else L.ptr(g_basis),
+                          grad_x_src_init=L.ptr(g_out) if (homo and sub is None) else None,
+                          grad_basis=None if basis_bf16 else L.ptr(g_basis),
                           grad_basis_bf16=L.ptr(g_basis) if basis_bf16 else None,
                           accumulate_grad_basis=int(acc_basis), node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
-        shape = (es.n_src, es.n_dst, es.n_edges)
+        shape = (top.n_src, top.n_dst, top.n_edges)
         if ctx.precision == "bf16":
             g_x2 = torch.empty_like(x1)
             amax = torch.empty(1, dtype=torch.int32, device=dev)  # bit pattern of max |grad_out| (fp16 gradient scale)
@@ -353,15 +414,18 @@ class FiberConvFn(torch.autograd.Function):
         gfk = g[o:o + 16 * 16 * 64].view(16, 16, 64)
         gwk = _reduce(edge_part).view(64, 64)
         g_xdst = None if homo else g_out
+        if sub is not None:  # residual path of the output rows (out_ids are unique: plain read-modify-write)
+            g_xsrc.index_copy_(0, sub.out_ids, g_xsrc.index_select(0, sub.out_ids) + g_out)
         if acc_basis:
             g_basis = None  # already inside the buffer the first consumer handed to autograd
         elif g_basis.dtype != ctx.basis_in_dtype:
             g_basis = g_basis.to(ctx.basis_in_dtype)
-        return g_xsrc, g_xdst, g_basis, gfk, gwk, gbias, glng, glnb, gw1, gb1, gw2, gb2, None
+        return g_xsrc, g_xdst, g_basis, gfk, gwk, gbias, glng, glnb, gw1, gb1, gw2, gb2, None, None
 
 
-def fiber_conv(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet):
-    return FiberConvFn.apply(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es)
+def fiber_conv(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet,
+               sub: Optional[SubEdgeSet] = None):
+    return FiberConvFn.apply(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es, sub)
 
 
 def aggregate_messages(x_src, basis, wk, es: EdgeSet) -> torch.Tensor:

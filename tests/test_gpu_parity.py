@@ -164,6 +164,53 @@ def test_policy_body_matches_oracle(cfg_name, B):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("bf16", 4e-3)])
+def test_empn_pruned_rows_equal_dense_evaluation(precision, tol):
+    """PonitaGCN.prune_dead_rows (drop edge-less padded nodes, last layer at the output nodes only) changes neither
+    the outputs nor any parameter gradient: compared with the dense evaluation of all B*n rows by the same kernels.
+    fp32: only the grouping of the weight-gradient partial sums differs.  bf16: the fp16 gradient scale of the last
+    layer is taken from fewer (but all non-zero) rows and basis-gradient rows are rounded in a different order."""
+    from geometry_rl_b200 import ops
+    cfg = CONFIGS["rigid_pushing_multi_empn_trpl_cfg"]
+    gen = torch.Generator().manual_seed(21)
+    B = 72
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
+    torch.manual_seed(5)
+    net = G.make_policy_body(cfg)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("bias") and float(p.abs().max()) == 0:
+                p.normal_(0, 0.05)
+    net.eval()
+    data = G.make_data(cfg, policy=True)
+    graph, u = data.build_data(*G.obs_args(cfg, obs, policy=True), train=False)
+    pr = graph.homogeneous_pruned()
+    n_valid = obs["infos"][:, 0].long()  # object_num_points
+    assert pr.es.n_src == int(n_valid.sum()) + B < graph.num_nodes  # valid points + one gripper per graph
+    assert pr.sub.n_dst == B and pr.sub.n_edges == int(n_valid.sum())  # TASK edges: every valid point -> the gripper
+    res = {}
+    ops.set_precision(precision)
+    try:
+        for prune in (False, True):
+            net.prune_dead_rows = prune
+            net.zero_grad(set_to_none=True)
+            out, hidden = net.one_step(graph, u)
+            if not prune:
+                w_out = torch.randn(out.shape, generator=gen).cuda()
+                w_hid = torch.randn(hidden.shape, generator=gen).cuda()
+            ((out * w_out).sum() + (hidden * w_hid).sum()).backward()
+            res[prune] = (out.detach().clone(), hidden.detach().clone(),
+                          {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None})
+    finally:
+        ops.set_precision("fp32")
+    (o0, h0, g0), (o1, h1, g1) = res[False], res[True]
+    assert G.rel(o1, o0) < tol, G.err_report("out", o1, o0)
+    assert G.rel(h1, h0) < tol, G.err_report("hidden", h1, h0)
+    assert set(g0) == set(g1)
+    bad = [G.err_report(k, g1[k], g0[k]) for k in g0 if G.rel(g1[k], g0[k]) >= tol]
+    assert not bad, "\n".join(bad)
+
+
 def test_calibration_matches_reference_semantics():
     """First training-mode forward re-scales kernel / fiber_kernel by std ratios (conv.py:151-157) AFTER
     using the un-calibrated weights; second forward then reproduces the fixture recorded post-calibration."""

@@ -5,7 +5,14 @@ import io
 import subprocess
 import sys
 
-src = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# optional: --skip N selects the N-th captured launch of a multi-kernel report
+SEL = []
+if "--skip" in sys.argv:
+    i = sys.argv.index("--skip")
+    SEL = ["--launch-skip", sys.argv[i + 1], "--launch-count", "1"]
+    del sys.argv[i:i + 2]
+
+src = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", *SEL], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]

@@ -5,9 +5,16 @@ import io
 import subprocess
 import sys
 
+# optional: --skip N selects the N-th captured launch of a multi-kernel report
+SEL = []
+if "--skip" in sys.argv:
+    i = sys.argv.index("--skip")
+    SEL = ["--launch-skip", sys.argv[i + 1], "--launch-count", "1"]
+    del sys.argv[i:i + 2]
+
 rep = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", *SEL], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 KEYS = ["gpu__time_duration.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -24,7 +31,7 @@ for vals in rows[2:]:
     st = {h.split("issue_stalled_")[1].split("_per_issue")[0]: float(vals[i]) for i, h in enumerate(hdr)
           if "average_warps_issue_stalled" in h and "per_issue_active" in h and vals[i]}
     print("  stalls/issue:", ", ".join(f"{k} {v:.2f}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:7]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *SEL], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
