@@ -42,13 +42,31 @@ class GrlConvDesc(C.Structure):
                 ("grad_out", _fp), ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp),
                 ("grad_basis", _fp), ("accumulate_grad_basis", _i32), ("node_grad_partials", _fp),
                 ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp),
-                ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp), ("x2", _fp), ("grad_amax", _fp)]
+                ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp), ("x2", _fp), ("grad_amax", _fp),
+                ("basis_row", _fp), ("grad_basis_acc_mask", _fp)]
 
 
 class GrlProjDesc(C.Structure):
     _fields_ = [("batch", _i32), ("k", _i32), ("proj_type", _i32), ("eps_mean", C.c_float), ("eps_cov", C.c_float),
                 ("mean", _fp), ("v", _fp), ("old_mean", _fp), ("old_v", _fp), ("proj_mean", _fp), ("proj_v", _fp),
-                ("eta", _fp), ("grad_proj_mean", _fp), ("grad_proj_v", _fp), ("grad_mean", _fp), ("grad_v", _fp)]
+                ("eta", _fp), ("grad_proj_mean", _fp), ("grad_proj_v", _fp), ("grad_mean", _fp), ("grad_v", _fp),
+                ("grad_mean_add", _fp), ("grad_v_add", _fp)]
+
+
+class GrlLossDesc(C.Structure):
+    _fields_ = [("batch", _i32), ("k", _i32), ("proj_type", _i32), ("normalize_advantage", _i32),
+                ("entropy_coef", C.c_float), ("trust_region_coeff", C.c_float),
+                ("mean", _fp), ("v", _fp), ("proj_mean", _fp), ("proj_v", _fp), ("action", _fp), ("prev_log_prob", _fp),
+                ("advantage", _fp), ("terms", _fp), ("stats", _fp), ("scalars", _fp), ("grad_losses", _fp),
+                ("grad_proj_mean", _fp), ("grad_proj_v", _fp), ("grad_mean_direct", _fp), ("grad_v_direct", _fp)]
+
+
+LOSS_TERMS = 8
+LOSS_SCALARS = 16
+# index of every scalar grl_trpl_loss_fwd writes (GRL_LS_* in include/grl_b200.h)
+LOSS_SCALAR_INDEX = {"loss_objective": 0, "loss_trust_region": 1, "loss_entropy": 2, "dist_entropy": 3, "ESS": 4, "kl": 5,
+                     "constraint": 6, "mean_constraint": 7, "mean_constraint_max": 8, "cov_constraint": 9,
+                     "cov_constraint_max": 10, "entropy": 11, "entropy_diff": 12}
 
 
 # name -> (restype, argtypes); every symbol include/grl_b200.h declares
@@ -75,6 +93,8 @@ SIGNATURES = {
     "grl_fbconv_edge_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_edge_basis_bwd_tc": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
     "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_trpl_loss_fwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),
+    "grl_trpl_loss_bwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),
     "grl_absmax": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),

@@ -12,6 +12,11 @@ import torch
 from torch import nn
 
 from .operators import td_get
+
+
+def td_is_cuda(module) -> bool:
+    p = next(module.parameters(), None)
+    return p is not None and p.is_cuda
 from .utils import _clip_value_loss, distance_loss
 
 
@@ -39,6 +44,9 @@ class TRPLLoss(nn.Module):
         self._global_steps = 0
         # data-parallel hooks (None = single process): see geometry_rl_b200/parallel.py
         self.dp = None
+        # single process: projection + every actor-side loss term and metric in five kernel launches
+        # (ops.trpl_loss) instead of ~170 elementwise / reduction launches; False = the torch formulation below
+        self.fused = True
 
     @property
     def _clip_bounds(self):
@@ -82,7 +90,40 @@ class TRPLLoss(nn.Module):
         may evaluate (and differentiate) it on a second CUDA stream."""
         return self._mean(self.loss_critic(td))
 
+    def _can_fuse(self, policy) -> bool:
+        pr = self.projection
+        return (self.fused and self.dp is None and getattr(pr, "KERNEL_TYPE", None) in ("kl", "w2")
+                and not pr.has_entropy_control and (pr.KERNEL_TYPE != "w2" or pr.scale_prec)
+                and getattr(policy, "contextual_std", True) and td_is_cuda(policy))
+
+    def _forward_fused(self, td, with_critic: bool) -> dict:
+        from .... import _lib, ops
+        policy = self.actor_network.get_submodule("0").module
+        previous_dist = self.actor_network.build_dist_from_params(td)
+        current_dist = self.actor_network.get_dist(td)
+        pr = self.projection
+        if pr.initial_entropy is None:  # base_projection_layer.py:202-203
+            pr.initial_entropy = policy.entropy((previous_dist.mean, previous_dist.var_diag)).mean().detach()
+        advantage = td_get(td, "advantage")
+        l_obj, l_tr, l_ent, sc = ops.trpl_loss(
+            current_dist.mean, current_dist.var_diag, previous_dist.mean, previous_dist.var_diag, td_get(td, "action"),
+            td_get(td, "sample_log_prob"), advantage, pr.mean_bound, pr.cov_bound, pr.KERNEL_TYPE,
+            self.entropy_coef if self.entropy_bonus else 0.0, pr.trust_region_coeff,
+            self.normalize_advantage and advantage.numel() > 1)
+        ix = _lib.LOSS_SCALAR_INDEX
+        out = {"loss_objective": l_obj, "loss_trust_region": l_tr}
+        if self.entropy_bonus:
+            out["loss_entropy"] = l_ent
+        if self.critic_coef and with_critic:
+            out["loss_critic"] = self.critic_term(td)
+        for key in ("ESS", "kl", "constraint", "mean_constraint", "mean_constraint_max", "cov_constraint",
+                    "cov_constraint_max", "entropy", "entropy_diff"):
+            out[key] = sc[ix[key]]
+        return out
+
     def forward(self, td, with_critic: bool = True) -> dict:
+        if self._can_fuse(self.actor_network.get_submodule("0").module):
+            return self._forward_fused(td, with_critic)
         advantage = td_get(td, "advantage")
         if self.normalize_advantage and advantage.numel() > 1:
             if self.dp is None:

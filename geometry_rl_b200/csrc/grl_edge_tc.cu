@@ -25,7 +25,7 @@ struct BasisTcSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 2) edge_basis_fwd_tc_kernel(const GrlBasisDesc d) {
+__global__ void __launch_bounds__(kThreads, 3) edge_basis_fwd_tc_kernel(const GrlBasisDesc d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BasisTcSmem& s = *reinterpret_cast<BasisTcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -149,6 +149,7 @@ struct EdgeFwdTcSmem {
   float XS[2][kTileFloats];       // gathered x_src rows, then messages in place
   __nv_bfloat16 Wkb[kC * kC];     // [8 chunks][64 rows c][8 j]
   int src[4][kTE], dst[4][kTE];   // 4-deep index ring: slot (t & 3) holds the edges of tile t
+  int brow[4][kTE];               // row of each edge in the basis tensor (= edge position unless d.basis_row is given)
   uint64_t bar;
   uint32_t tmem_base;
 };
@@ -164,16 +165,18 @@ __device__ __forceinline__ int node_lower_bound(const int32_t* __restrict__ rowp
   return lo;
 }
 
-// basis rows of `cnt` consecutive edges (bf16, row-major in HBM) -> operand image, 16-byte cp.async pieces
-__device__ __forceinline__ void stage_basis_image(__nv_bfloat16* __restrict__ img, const __nv_bfloat16* __restrict__ src, int cnt) {
+// basis rows of `cnt` edges (bf16 [16][64] per edge in HBM, edge j at row brow[j]) -> operand image, 16-byte cp.async pieces
+__device__ __forceinline__ void stage_basis_image(__nv_bfloat16* __restrict__ img, const __nv_bfloat16* __restrict__ basis,
+                                                  const int* __restrict__ brow, int cnt) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int f = threadIdx.x + kThreads * i;  // 16-byte piece 0..1023
-    const int r = f >> 3, c8 = f & 7;
+    const int r = f >> 3, c8 = f & 7, j = r >> 4;
     __nv_bfloat16* dpt = img + ((size_t)c8 * kTM + r) * 8;
-    if ((r >> 4) < cnt) {
+    if (j < cnt) {
       const unsigned sa = tc::smem_u32(dpt);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + (size_t)r * kC + 8 * c8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa),
+                   "l"(basis + (size_t)brow[j] * kRow + (r & 15) * kC + 8 * c8) : "memory");
     } else {
       *reinterpret_cast<uint4*>(dpt) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -201,23 +204,27 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
   const __nv_bfloat16* basis = reinterpret_cast<const __nv_bfloat16*>(d.basis_bf16);
 
   // edge indices of tile t live in registers of threads 0..7 until they are published to s.src / s.dst
-  auto load_idx = [&](int t, int& es, int& ed) {
-    es = 0; ed = 0;
+  auto load_idx = [&](int t, int& es, int& ed, int& eb) {
+    es = 0; ed = 0; eb = 0;
     const int e = p0 + t * kTE + tid;
-    if (tid < kTE && t < n_tiles && e < p1) { es = __ldg(d.edge_src + e); ed = __ldg(d.edge_dst + e); }
+    if (tid < kTE && t < n_tiles && e < p1) {
+      es = __ldg(d.edge_src + e);
+      ed = __ldg(d.edge_dst + e);
+      eb = d.basis_row ? __ldg(d.basis_row + e) : e;  // sub layers read the parent's basis rows in place
+    }
   };
   auto stage = [&](int t, int buf) {  // requires index slot (t & 3) to be visible
     const int cnt = min(kTE, p1 - (p0 + t * kTE));
-    stage_basis_image(s.BZ[buf], basis + (size_t)(p0 + t * kTE) * kRow, cnt);
+    stage_basis_image(s.BZ[buf], basis, s.brow[t & 3], cnt);
     stage_rows_gather(s.XS[buf], d.x_src, s.src[t & 3], cnt);
   };
-  int es_a, ed_a, es_b, ed_b;  // a: tile t+2 (published in iteration t), b: tile t+3
-  load_idx(0, es_a, ed_a);
-  if (tid < kTE) { s.src[0][tid] = es_a; s.dst[0][tid] = ed_a; }
-  load_idx(1, es_a, ed_a);
-  if (tid < kTE) { s.src[1][tid] = es_a; s.dst[1][tid] = ed_a; }
-  load_idx(2, es_a, ed_a);
-  load_idx(3, es_b, ed_b);
+  int es_a, ed_a, eb_a, es_b, ed_b, eb_b;  // a: tile t+2 (published in iteration t), b: tile t+3
+  load_idx(0, es_a, ed_a, eb_a);
+  if (tid < kTE) { s.src[0][tid] = es_a; s.dst[0][tid] = ed_a; s.brow[0][tid] = eb_a; }
+  load_idx(1, es_a, ed_a, eb_a);
+  if (tid < kTE) { s.src[1][tid] = es_a; s.dst[1][tid] = ed_a; s.brow[1][tid] = eb_a; }
+  load_idx(2, es_a, ed_a, eb_a);
+  load_idx(3, es_b, ed_b, eb_b);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -234,9 +241,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
     const int buf = t & 1;
     const int cnt = min(kTE, p1 - (p0 + t * kTE));
     // publish the indices of tile t+2: slot (t+2)&3 was last read by tile t-2, two barriers ago
-    if (tid < kTE) { s.src[(t + 2) & 3][tid] = es_a; s.dst[(t + 2) & 3][tid] = ed_a; }
-    es_a = es_b; ed_a = ed_b;
-    load_idx(t + 4, es_b, ed_b);
+    if (tid < kTE) { s.src[(t + 2) & 3][tid] = es_a; s.dst[(t + 2) & 3][tid] = ed_a; s.brow[(t + 2) & 3][tid] = eb_a; }
+    es_a = es_b; ed_a = ed_b; eb_a = eb_b;
+    load_idx(t + 4, es_b, ed_b, eb_b);
     __syncthreads();  // everyone is done reducing tile t-1: its data buffers (buf ^ 1) may be overwritten
     if (t + 1 < n_tiles) stage(t + 1, buf ^ 1);
     cp_async_commit();
@@ -310,7 +317,7 @@ int grl_edge_basis_fwd_tc(const GrlBasisDesc* d, grl_stream_t stream) {
     attr = true;
   }
   const int n_tiles = (d->n_edges + grl::kTE - 1) / grl::kTE;
-  int grid = 2 * grl::sm_count();
+  int grid = 3 * grl::sm_count();  // 37 KB smem, 128 TMEM columns, <= 85 registers: three CTAs share an SM
   if (grid > n_tiles) grid = n_tiles;
   grl::edge_basis_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_edge_basis_fwd_tc");

@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(128) trpl_bwd_kernel(const GrlProjDesc d) {
   if (b >= d.batch) return;
   const int k = d.k;
   double m[kMaxK], v[kMaxK], mo[kMaxK], vo[kMaxK], gm[kMaxK], gv[kMaxK];
+  double am[kMaxK], av[kMaxK];  // gradients that reach (mean, v) directly (grad_mean_add / grad_v_add)
+#pragma unroll
+  for (int i = 0; i < kMaxK; ++i) {
+    am[i] = (i < k && d.grad_mean_add) ? (double)d.grad_mean_add[(size_t)b * k + i] : 0.0;
+    av[i] = (i < k && d.grad_v_add) ? (double)d.grad_v_add[(size_t)b * k + i] : 0.0;
+  }
 #pragma unroll
   for (int i = 0; i < kMaxK; ++i) {
     if (i < k) {
@@ -155,11 +161,11 @@ __global__ void __launch_bounds__(128) trpl_bwd_kernel(const GrlProjDesc d) {
     for (int i = 0; i < kMaxK; ++i)
       if (i < k)
         d.grad_mean[(size_t)b * k + i] =
-            (float)(gm[i] / (1.0 + w) + dot * dw_dM * scale * 2.0 * (m[i] - mo[i]) / (vo[i] * vo[i]));
+            (float)(gm[i] / (1.0 + w) + dot * dw_dM * scale * 2.0 * (m[i] - mo[i]) / (vo[i] * vo[i]) + am[i]);
   } else {
 #pragma unroll
     for (int i = 0; i < kMaxK; ++i)
-      if (i < k) d.grad_mean[(size_t)b * k + i] = (float)gm[i];
+      if (i < k) d.grad_mean[(size_t)b * k + i] = (float)(gm[i] + am[i]);
   }
   // ---- covariance
   const double eta = d.eta[2 * (size_t)b];
@@ -187,13 +193,13 @@ __global__ void __launch_bounds__(128) trpl_bwd_kernel(const GrlProjDesc d) {
       for (int i = 0; i < kMaxK; ++i)
         if (i < k) {
           const double gc = gct[i] * dct_dc[i] - num * (dkl_dct[i] * dct_dc[i]) / den;
-          d.grad_v[(size_t)b * k + i] = (float)(gc * 2.0 * v[i]);
+          d.grad_v[(size_t)b * k + i] = (float)(gc * 2.0 * v[i] + av[i]);
         }
     } else {
       // identity: pv = sqrt(v^2) = v
 #pragma unroll
       for (int i = 0; i < kMaxK; ++i)
-        if (i < k) d.grad_v[(size_t)b * k + i] = (float)gv[i];
+        if (i < k) d.grad_v[(size_t)b * k + i] = (float)(gv[i] + av[i]);
     }
   } else {
     if (eta > 0.0) {
@@ -207,11 +213,173 @@ __global__ void __launch_bounds__(128) trpl_bwd_kernel(const GrlProjDesc d) {
       for (int i = 0; i < kMaxK; ++i)
         if (i < k)
           d.grad_v[(size_t)b * k + i] =
-              (float)(gv[i] / (1.0 + eta) + dot * deta_dS * 2.0 * (v[i] / vo[i] - 1.0) / vo[i]);
+              (float)(gv[i] / (1.0 + eta) + dot * deta_dS * 2.0 * (v[i] / vo[i] - 1.0) / vo[i] + av[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < kMaxK; ++i)
-        if (i < k) d.grad_v[(size_t)b * k + i] = (float)gv[i];
+        if (i < k) d.grad_v[(size_t)b * k + i] = (float)(gv[i] + av[i]);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Loss terms around the projection (objectives/trpl.py:231-321, base_projection_layer.py:292-384).
+// terms[b] = { log_w, tr_mean, tr_cov, kl_mean + kl_cov, H_dist(proj), H_policy(p), H_policy(proj), advantage }
+// ---------------------------------------------------------------------------------------------------
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+
+__global__ void __launch_bounds__(128) trpl_loss_terms_kernel(const GrlLossDesc d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.batch) return;
+  const int k = d.k;
+  double maha_a = 0.0, logdet_pv = 0.0, log_pv = 0.0, log_v = 0.0, maha_m = 0.0, trace = 0.0, w2_cov = 0.0;
+#pragma unroll
+  for (int i = 0; i < kMaxK; ++i) {
+    if (i < k) {
+      const size_t j = (size_t)b * k + i;
+      const double m = d.mean[j], v = d.v[j], pm = d.proj_mean[j], pv = d.proj_v[j], a = d.action[j];
+      maha_a += (a - pm) * (a - pm) / pv;          // MultivariateNormal(proj_mean, covariance = diag(proj_v)).log_prob
+      logdet_pv += log(pv);
+      log_pv += log(pv);
+      log_v += log(v);
+      const double t = (m - pm) / pv;              // "std" convention: distances divide by the matrix itself
+      maha_m += t * t;
+      trace += (v / pv) * (v / pv);
+      w2_cov += 1.0 + v * v / (pv * pv) - 2.0 * v / pv;
+    }
+  }
+  const double log_prob = -0.5 * (maha_a + k * kLog2Pi + logdet_pv);
+  const double kl_mean = 0.5 * maha_m;                                         // projection_utils.py:34-67
+  const double kl_cov = 0.5 * (trace - k + 2.0 * log_pv - 2.0 * log_v);
+  const double tr_mean = d.proj_type == 0 ? kl_mean : maha_m;                  // projection_utils.py:107-149
+  const double tr_cov = d.proj_type == 0 ? kl_cov : w2_cov;
+  double* T = d.terms + (size_t)b * GRL_LOSS_TERMS;
+  T[0] = log_prob - (double)d.prev_log_prob[b];
+  T[1] = tr_mean;
+  T[2] = tr_cov;
+  T[3] = kl_mean + kl_cov;
+  T[4] = 0.5 * (k * (1.0 + kLog2Pi) + logdet_pv);                              // dist.entropy()
+  T[5] = 0.5 * (k * (1.0 + kLog2Pi) + 2.0 * log_v);                            // policy.entropy(p): log_determinant = 2 sum log
+  T[6] = 0.5 * (k * (1.0 + kLog2Pi) + 2.0 * log_pv);                           // policy.entropy(proj)
+  T[7] = (double)d.advantage[b];
+}
+
+constexpr int kLossThreads = 1024;
+
+// fixed-order block reductions (deterministic): warp shuffles, then one warp over the 32 partials
+__device__ __forceinline__ double block_sum(double x, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  x = sh[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+__device__ __forceinline__ double block_max(double x, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  x = sh[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+
+__global__ void __launch_bounds__(kLossThreads) trpl_loss_reduce_kernel(const GrlLossDesc d) {
+  __shared__ double sh[32];
+  const int B = d.batch, tid = threadIdx.x;
+  const double* T = d.terms;
+  // advantage standardisation (trpl.py:286-289): mean, unbiased std clamped at 1e-6
+  double loc = 0.0, inv_scale = 1.0;
+  if (d.normalize_advantage && B > 1) {
+    double s = 0.0;
+    for (int b = tid; b < B; b += kLossThreads) s += T[(size_t)b * GRL_LOSS_TERMS + 7];
+    loc = block_sum(s, sh) / B;
+    double q = 0.0;
+    for (int b = tid; b < B; b += kLossThreads) { const double t = T[(size_t)b * GRL_LOSS_TERMS + 7] - loc; q += t * t; }
+    const double sd = sqrt(block_sum(q, sh) / (B - 1));
+    inv_scale = 1.0 / fmax(sd, 1e-6);
+  }
+  double mx = -1e300;
+  for (int b = tid; b < B; b += kLossThreads) mx = fmax(mx, T[(size_t)b * GRL_LOSS_TERMS]);
+  mx = block_max(mx, sh);
+  double s_obj = 0.0, s_e1 = 0.0, s_e2 = 0.0, s_trm = 0.0, s_trc = 0.0, s_kl = 0.0, s_hd = 0.0, s_hp = 0.0, s_hq = 0.0;
+  double m_trm = -1e300, m_trc = -1e300;
+  for (int b = tid; b < B; b += kLossThreads) {
+    const double* t = T + (size_t)b * GRL_LOSS_TERMS;
+    const double lw = t[0];
+    s_obj += exp(lw) * ((t[7] - loc) * inv_scale);
+    const double e = exp(lw - mx);
+    s_e1 += e;
+    s_e2 += e * e;
+    s_trm += t[1]; s_trc += t[2]; s_kl += t[3]; s_hd += t[4]; s_hp += t[5]; s_hq += t[6];
+    m_trm = fmax(m_trm, t[1]);
+    m_trc = fmax(m_trc, t[2]);
+  }
+  s_obj = block_sum(s_obj, sh); s_e1 = block_sum(s_e1, sh); s_e2 = block_sum(s_e2, sh);
+  s_trm = block_sum(s_trm, sh); s_trc = block_sum(s_trc, sh); s_kl = block_sum(s_kl, sh);
+  s_hd = block_sum(s_hd, sh); s_hp = block_sum(s_hp, sh); s_hq = block_sum(s_hq, sh);
+  m_trm = block_max(m_trm, sh); m_trc = block_max(m_trc, sh);
+  if (tid == 0) {
+    const double n = (double)B;
+    float* S = d.scalars;
+    S[GRL_LS_LOSS_OBJECTIVE] = (float)(-s_obj / n);
+    S[GRL_LS_LOSS_TRUST_REGION] = (float)((s_trm + s_trc) / n * (double)d.trust_region_coeff);
+    S[GRL_LS_LOSS_ENTROPY] = (float)(-(double)d.entropy_coef * s_hd / n);
+    S[GRL_LS_DIST_ENTROPY] = (float)(s_hd / n);
+    // exp(2 lse(lw) - lse(2 lw)) / B with both log-sum-exps shifted by max(lw)
+    S[GRL_LS_ESS] = (float)(s_e1 * s_e1 / s_e2 / n);
+    S[GRL_LS_KL] = (float)(s_kl / n);
+    S[GRL_LS_CONSTRAINT] = (float)((s_trm + s_trc) / n);
+    S[GRL_LS_MEAN_CONSTRAINT] = (float)(s_trm / n);
+    S[GRL_LS_MEAN_CONSTRAINT_MAX] = (float)m_trm;
+    S[GRL_LS_COV_CONSTRAINT] = (float)(s_trc / n);
+    S[GRL_LS_COV_CONSTRAINT_MAX] = (float)m_trc;
+    S[GRL_LS_ENTROPY] = (float)(s_hp / n);
+    S[GRL_LS_ENTROPY_DIFF] = (float)((s_hq - s_hp) / n);
+    for (int i = GRL_LS_ENTROPY_DIFF + 1; i < GRL_LOSS_SCALARS; ++i) S[i] = 0.f;
+    d.stats[0] = loc;
+    d.stats[1] = inv_scale;
+  }
+}
+
+__global__ void __launch_bounds__(128) trpl_loss_bwd_kernel(const GrlLossDesc d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.batch) return;
+  const int k = d.k;
+  const double n = (double)d.batch;
+  const double g_obj = d.grad_losses[0], g_tr = d.grad_losses[1], g_ent = d.grad_losses[2];
+  const double* T = d.terms + (size_t)b * GRL_LOSS_TERMS;
+  const double adv = (T[7] - d.stats[0]) * d.stats[1];
+  const double g_lw = -g_obj / n * exp(T[0]) * adv;           // d loss_objective / d log_prob
+  const double c_ent = -g_ent * (double)d.entropy_coef / n;   // d loss_entropy / d H_dist
+  const double c_tr = g_tr * (double)d.trust_region_coeff / n;
+#pragma unroll
+  for (int i = 0; i < kMaxK; ++i) {
+    if (i < k) {
+      const size_t j = (size_t)b * k + i;
+      const double m = d.mean[j], v = d.v[j], pm = d.proj_mean[j], pv = d.proj_v[j], a = d.action[j];
+      const double r = a - pm;
+      // log_prob = -0.5 (sum r^2 / pv + k log 2pi + sum log pv);  H_dist = 0.5 (k (1 + log 2pi) + sum log pv)
+      d.grad_proj_mean[j] = (float)(g_lw * r / pv);
+      d.grad_proj_v[j] = (float)(g_lw * 0.5 * (r * r / (pv * pv) - 1.0 / pv) + c_ent * 0.5 / pv);
+      // trust-region value of p against the DETACHED projection
+      double gm, gv;
+      if (d.proj_type == 0) {
+        gm = (m - pm) / (pv * pv);
+        gv = v / (pv * pv) - 1.0 / v;
+      } else {
+        gm = 2.0 * (m - pm) / (pv * pv);
+        gv = 2.0 * v / (pv * pv) - 2.0 / pv;
+      }
+      d.grad_mean_direct[j] = (float)(c_tr * gm);
+      d.grad_v_direct[j] = (float)(c_tr * gv);
     }
   }
 }
@@ -244,6 +412,34 @@ int grl_trpl_bwd(const GrlProjDesc* d, grl_stream_t stream) {
   if (rc != GRL_OK) return rc;
   grl::trpl_bwd_kernel<<<(d->batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_trpl_bwd");
+}
+
+static int check_loss(const GrlLossDesc* d, const char* who, bool bwd) {
+  GRL_REQUIRE(d, GRL_EINVAL, "%s: null descriptor", who);
+  GRL_REQUIRE(d->batch > 0 && d->k > 0, GRL_EINVAL, "%s: batch=%d k=%d", who, d->batch, d->k);
+  GRL_REQUIRE(d->k <= GRL_MAX_ACTION_DIM, GRL_EUNSUPPORTED, "%s: k=%d > %d", who, d->k, GRL_MAX_ACTION_DIM);
+  GRL_REQUIRE(d->proj_type == 0 || d->proj_type == 1, GRL_EUNSUPPORTED, "%s: proj_type=%d", who, d->proj_type);
+  GRL_REQUIRE(d->mean && d->v && d->proj_mean && d->proj_v && d->action && d->terms && d->stats, GRL_EINVAL,
+              "%s: null pointer", who);
+  if (bwd) GRL_REQUIRE(d->grad_losses && d->grad_proj_mean && d->grad_proj_v && d->grad_mean_direct && d->grad_v_direct,
+                       GRL_EINVAL, "%s: null grad pointer", who);
+  else GRL_REQUIRE(d->prev_log_prob && d->advantage && d->scalars, GRL_EINVAL, "%s: null input / output pointer", who);
+  return GRL_OK;
+}
+
+int grl_trpl_loss_fwd(const GrlLossDesc* d, grl_stream_t stream) {
+  const int rc = check_loss(d, "grl_trpl_loss_fwd", false);
+  if (rc != GRL_OK) return rc;
+  grl::trpl_loss_terms_kernel<<<(d->batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d);
+  grl::trpl_loss_reduce_kernel<<<1, grl::kLossThreads, 0, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_trpl_loss_fwd");
+}
+
+int grl_trpl_loss_bwd(const GrlLossDesc* d, grl_stream_t stream) {
+  const int rc = check_loss(d, "grl_trpl_loss_bwd", true);
+  if (rc != GRL_OK) return rc;
+  grl::trpl_loss_bwd_kernel<<<(d->batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_trpl_loss_bwd");
 }
 
 }  // extern "C"

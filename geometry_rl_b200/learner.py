@@ -152,13 +152,18 @@ class Learner:
         """Same arithmetic as `update`; the critic loss and its backward are enqueued on `_critic_stream` (forked from
         and joined to the current stream, so the pattern is also valid inside a CUDA-graph capture)."""
         main, side = torch.cuda.current_stream(), self._critic_stream
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            loss_critic = self.loss_module.critic_term(batch)
-            loss_critic.backward()  # autograd runs these nodes on the stream of their forward: `side`
+        # The critic branch forks from the START of the step but is enqueued AFTER the actor's forward: in a graph replay
+        # the device picks nodes up in creation order, and with the ~120 small critic nodes first the actor's first
+        # kernel started 0.47 ms late (tools/step_timeline.py); now they run under the actor's large kernels.
+        fork = torch.cuda.Event()
+        fork.record(main)
         self.loss_module._global_steps = self.num_network_updates
         loss = self.loss_module(batch, with_critic=False)
         loss["actor_loss"] = loss["loss_objective"] + loss["loss_entropy"] + loss["loss_trust_region"]
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            loss_critic = self.loss_module.critic_term(batch)
+            loss_critic.backward()  # autograd runs these nodes on the stream of their forward: `side`
         loss["loss_critic"] = loss_critic.detach()
         self.num_network_updates += 1
         loss["actor_loss"].backward()

@@ -75,12 +75,13 @@ class SubEdgeSet:
     n_edges: int
     out_ids: torch.Tensor  # [n_dst] int64, ascending: row of the parent's node tensor behind every dst row
     eids: torch.Tensor  # [E_sub] int64, ascending: position of every sub-edge in the parent's edge order
+    eids32: torch.Tensor  # the same as int32 (GrlConvDesc.basis_row of the tensor-core forward)
     rowptr_dst: torch.Tensor  # [n_dst+1] int32
     edge_src: torch.Tensor  # [E_sub] int32 (parent node ids)
     edge_dst: torch.Tensor  # [E_sub] int32 (0..n_dst-1)
     rowptr_src: torch.Tensor  # [n_src+1] int32
     src_eid_parent: torch.Tensor  # [E_sub] int32: src-sorted entry -> position in the PARENT's edge order
-    edge_dst_parent: torch.Tensor  # [E_parent] int32: dst rank (0..n_dst-1) of every parent edge (0 outside the subset)
+    edge_dst_parent: torch.Tensor  # [E_parent] int32: dst rank (0..n_dst-1) of every parent edge, -1 outside the subset
 
 
 def build_sub_edge_set(es: "EdgeSet", out_ids: torch.Tensor) -> SubEdgeSet:
@@ -101,8 +102,9 @@ def build_sub_edge_set(es: "EdgeSet", out_ids: torch.Tensor) -> SubEdgeSet:
 
     order = torch.sort(edge_src.long(), stable=True).indices  # ties keep edge order, like grl_csr_build
     return SubEdgeSet(es.n_src, n_out, int(eids.numel()), out_ids.contiguous(), eids.contiguous(),
-                      rowptr(edge_dst, n_out), edge_src, edge_dst, rowptr(edge_src, es.n_src),
-                      eids[order].to(torch.int32).contiguous(), dst_rank.clamp_min(0).to(torch.int32).contiguous())
+                      eids.to(torch.int32).contiguous(), rowptr(edge_dst, n_out), edge_src, edge_dst,
+                      rowptr(edge_src, es.n_src), eids[order].to(torch.int32).contiguous(),
+                      dst_rank.to(torch.int32).contiguous())
 
 
 def knn_edge_ptr(num_valid: Optional[torch.Tensor], B: int, P: int, k: int, device) -> torch.Tensor:
@@ -254,7 +256,7 @@ class EdgeBasisFn(torch.autograd.Function):
         # with a separate kernel, the first FiberConvFn.backward to run returns its gradient buffer and the later ones
         # accumulate into that same buffer inside the edge kernel (and return None).  This function's backward runs
         # after all of them (topological order), so it sees the complete sum whichever subset of consumers ran.
-        ctx.gacc = {"buf": None}
+        ctx.gacc = {"buf": None, "mask": None}
         if bf16:
             basis._grl_gacc = ctx.gacc
         return basis
@@ -264,7 +266,11 @@ class EdgeBasisFn(torch.autograd.Function):
         pos_src, pos_dst, w1t, b1c, w2t, b2c, w2, ori3 = ctx.saved_tensors
         es, dim = ctx.es, ctx.dim
         dev = pos_src.device
-        ctx.gacc["buf"] = None  # a later backward through the same graph starts a fresh accumulation
+        pending_mask = ctx.gacc.get("mask")
+        ctx.gacc["buf"], ctx.gacc["mask"] = None, None  # a later backward through the same graph starts a fresh accumulation
+        if pending_mask is not None and g_basis is not None and es.n_edges > 0:
+            # the only consumer was a sub layer: rows of the other edges were never written
+            g_basis = g_basis.masked_fill((pending_mask < 0).view(-1, 1, 1), 0)
         if es.n_edges == 0:
             z = torch.zeros
             return (None, None, z(64, 14, device=dev), z(64, device=dev), z(64, 64, device=dev), z(64, device=dev),
@@ -312,7 +318,10 @@ class FiberConvFn(torch.autograd.Function):
         fk = _f32c(fk)
         dev = x_src.device
         basis_full = basis
-        if sub is not None:  # forward reads the basis contiguously in edge order: compact copy of the subset's rows
+        # the tensor-core edge kernel reads the parent's basis rows in place (GrlConvDesc.basis_row); the strict fp32
+        # kernel reads the basis contiguously in edge order and gets a compact copy of the subset's rows
+        basis_row = sub.eids32 if (sub is not None and basis.dtype == torch.bfloat16) else None
+        if sub is not None and basis_row is None:
             basis = basis.index_select(0, sub.eids)
         top = sub if sub is not None else es  # topology of the forward kernels
         assert x_src.shape[0] == top.n_src and xd.shape[0] == top.n_dst, "latent rows do not match the edge set"
@@ -338,7 +347,8 @@ class FiberConvFn(torch.autograd.Function):
                           basis_bf16=L.ptr(basis) if basis.dtype == torch.bfloat16 else None,
                           fiber_kernel=L.ptr(fk), wk_t=L.ptr(wk_t), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
                           ln_b=L.ptr(lnb_c), w1_t=L.ptr(w1_t), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2_t=L.ptr(w2_t),
-                          w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0)
+                          w2_c=L.ptr(w2_c), b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0,
+                          basis_row=L.ptr(basis_row))
         shape = (top.n_src, top.n_dst, top.n_edges)
         L.call("grl_fbconv_edge_fwd_tc" if basis.dtype == torch.bfloat16 else "grl_fbconv_edge_fwd", C.byref(d), shape=shape)
         x2 = x1  # placeholder so that save_for_backward has a tensor in the strict path
@@ -368,10 +378,23 @@ class FiberConvFn(torch.autograd.Function):
         basis_bf16 = basis.dtype == torch.bfloat16
         gacc = ctx.gacc
         acc_basis = gacc is not None and gacc["buf"] is not None
-        # a sub layer writes the rows of its own edges only: the rest of a fresh buffer must read as zero
-        g_basis = gacc["buf"] if acc_basis else (torch.zeros_like(basis) if sub is not None else torch.empty_like(basis))
-        if gacc is not None and not acc_basis:
-            gacc["buf"] = g_basis
+        acc_mode, acc_mask = int(acc_basis), None
+        if acc_basis:
+            g_basis = gacc["buf"]
+            if gacc.get("mask") is not None:  # only the rows a sub layer wrote are valid so far: add there, overwrite the rest
+                assert sub is None, "two sub layers on one basis are not supported"
+                acc_mode, acc_mask = 2, gacc["mask"]
+                gacc["mask"] = None  # after this launch every row is valid
+        elif sub is not None and gacc is not None:
+            # first consumer is a sub layer: it writes the rows of its own edges into an uninitialised buffer and leaves
+            # a mask behind; the next (full) layer overwrites the other rows, EdgeBasisFn.backward zeroes them otherwise
+            g_basis = torch.empty_like(basis)
+            gacc["buf"], gacc["mask"] = g_basis, sub.edge_dst_parent
+        else:
+            # strict path (autograd sums the layers' gradients): rows outside a sub layer's edges must read as zero
+            g_basis = torch.zeros_like(basis) if sub is not None else torch.empty_like(basis)
+            if gacc is not None:
+                gacc["buf"] = g_basis
         n_pn = _n_partials((top.n_dst + 7) // 8)
         n_pe = _n_partials((top.n_src + 15) // 16, 2 if basis_bf16 else 1)
         node_part = torch.empty(n_pn, L.NODE_GRAD_FLOATS, dtype=torch.float32, device=dev)
@@ -390,7 +413,8 @@ class FiberConvFn(torch.autograd.Function):
                           grad_x_src_init=L.ptr(g_out) if (homo and sub is None) else None,
                           grad_basis=None if basis_bf16 else L.ptr(g_basis),
                           grad_basis_bf16=L.ptr(g_basis) if basis_bf16 else None,
-                          accumulate_grad_basis=int(acc_basis), node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
+                          accumulate_grad_basis=acc_mode, grad_basis_acc_mask=L.ptr(acc_mask),
+                          node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
                           edge_grad_partials=L.ptr(edge_part), n_partials_edge=n_pe)
         shape = (top.n_src, top.n_dst, top.n_edges)
         if ctx.precision == "bf16":
@@ -494,3 +518,75 @@ def trpl_project(mean, v, old_mean, old_v, eps_mean, eps_cov, proj_type="kl"):
     """Projected (mean, v) of a diagonal Gaussian; v is the diagonal of the reference's "std" matrix."""
     code = {"kl": 0, "w2": 1}[proj_type]
     return TrplProjectFn.apply(mean, v, old_mean, old_v, eps_mean, eps_cov, code)
+
+
+# ------------------------------------------------------------------------------------------------
+# L1 / P3: projection + every loss term around it in five launches
+# ------------------------------------------------------------------------------------------------
+class TrplLossFn(torch.autograd.Function):
+    """(mean, v) of the current policy -> (loss_objective, loss_trust_region, loss_entropy, scalars[16]).
+
+    grl_trpl_fwd projects, grl_trpl_loss_fwd evaluates log-weights, the standardised-advantage surrogate, the
+    trust-region value against the detached projection, entropies, ESS and the trust-region metrics; the backward
+    is grl_trpl_loss_bwd (gradients w.r.t. the projected parameters and the direct trust-region gradients) followed
+    by grl_trpl_bwd (implicit differentiation of the projection).  `scalars` is not differentiable."""
+
+    @staticmethod
+    def forward(ctx, mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, proj_type,
+                entropy_coef, trust_region_coeff, normalize_advantage):
+        mean, v, old_mean, old_v = _f32c(mean), _f32c(v), _f32c(old_mean), _f32c(old_v)
+        action, prev_log_prob, advantage = _f32c(action), _f32c(prev_log_prob).reshape(-1), _f32c(advantage).reshape(-1)
+        B, k = mean.shape
+        assert action.shape == (B, k) and prev_log_prob.numel() == B and advantage.numel() == B
+        dev = mean.device
+        pm, pv = torch.empty_like(mean), torch.empty_like(v)
+        eta = torch.empty(B, 2, dtype=torch.float64, device=dev)
+        d = L.GrlProjDesc(batch=B, k=k, proj_type=proj_type, eps_mean=float(eps_mean), eps_cov=float(eps_cov),
+                          mean=L.ptr(mean), v=L.ptr(v), old_mean=L.ptr(old_mean), old_v=L.ptr(old_v), proj_mean=L.ptr(pm),
+                          proj_v=L.ptr(pv), eta=L.ptr_any(eta))
+        L.call("grl_trpl_fwd", C.byref(d))
+        terms = torch.empty(B, L.LOSS_TERMS, dtype=torch.float64, device=dev)
+        stats = torch.empty(2, dtype=torch.float64, device=dev)
+        scalars = torch.empty(L.LOSS_SCALARS, dtype=torch.float32, device=dev)
+        ld = L.GrlLossDesc(batch=B, k=k, proj_type=proj_type, normalize_advantage=int(bool(normalize_advantage)),
+                           entropy_coef=float(entropy_coef), trust_region_coeff=float(trust_region_coeff),
+                           mean=L.ptr(mean), v=L.ptr(v), proj_mean=L.ptr(pm), proj_v=L.ptr(pv), action=L.ptr(action),
+                           prev_log_prob=L.ptr(prev_log_prob), advantage=L.ptr(advantage), terms=L.ptr_any(terms),
+                           stats=L.ptr_any(stats), scalars=L.ptr(scalars))
+        L.call("grl_trpl_loss_fwd", C.byref(ld))
+        ctx.save_for_backward(mean, v, old_mean, old_v, action, pm, pv, eta, terms, stats)
+        ctx.meta = (float(eps_mean), float(eps_cov), proj_type, float(entropy_coef), float(trust_region_coeff))
+        ctx.mark_non_differentiable(scalars)
+        return scalars[0].clone(), scalars[1].clone(), scalars[2].clone(), scalars
+
+    @staticmethod
+    def backward(ctx, g_obj, g_tr, g_ent, _g_scalars):
+        mean, v, old_mean, old_v, action, pm, pv, eta, terms, stats = ctx.saved_tensors
+        eps_mean, eps_cov, proj_type, entropy_coef, trust_region_coeff = ctx.meta
+        B, k = mean.shape
+        dev = mean.device
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g3 = torch.stack([zero if g is None else g.reshape(()).float() for g in (g_obj, g_tr, g_ent)])
+        g_pm, g_pv = torch.empty_like(mean), torch.empty_like(v)
+        g_md, g_vd = torch.empty_like(mean), torch.empty_like(v)
+        ld = L.GrlLossDesc(batch=B, k=k, proj_type=proj_type, normalize_advantage=0, entropy_coef=entropy_coef,
+                           trust_region_coeff=trust_region_coeff, mean=L.ptr(mean), v=L.ptr(v), proj_mean=L.ptr(pm),
+                           proj_v=L.ptr(pv), action=L.ptr(action), terms=L.ptr_any(terms), stats=L.ptr_any(stats),
+                           grad_losses=L.ptr(g3), grad_proj_mean=L.ptr(g_pm), grad_proj_v=L.ptr(g_pv),
+                           grad_mean_direct=L.ptr(g_md), grad_v_direct=L.ptr(g_vd))
+        L.call("grl_trpl_loss_bwd", C.byref(ld))
+        gm, gv = torch.empty_like(mean), torch.empty_like(v)
+        d = L.GrlProjDesc(batch=B, k=k, proj_type=proj_type, eps_mean=eps_mean, eps_cov=eps_cov, mean=L.ptr(mean),
+                          v=L.ptr(v), old_mean=L.ptr(old_mean), old_v=L.ptr(old_v), eta=L.ptr_any(eta),
+                          grad_proj_mean=L.ptr(g_pm), grad_proj_v=L.ptr(g_pv), grad_mean=L.ptr(gm), grad_v=L.ptr(gv),
+                          grad_mean_add=L.ptr(g_md), grad_v_add=L.ptr(g_vd))
+        L.call("grl_trpl_bwd", C.byref(d))
+        return (gm, gv) + (None,) * 11
+
+
+def trpl_loss(mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, proj_type, entropy_coef,
+              trust_region_coeff, normalize_advantage=True):
+    """-> (loss_objective, loss_trust_region, loss_entropy, scalars) with scalars indexed by _lib.LOSS_SCALAR_INDEX."""
+    code = {"kl": 0, "w2": 1}[proj_type]
+    return TrplLossFn.apply(mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, code,
+                            entropy_coef, trust_region_coeff, normalize_advantage)

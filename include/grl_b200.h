@@ -171,7 +171,7 @@ typedef struct {
   float* grad_x_src;         /* [n_src][16][64]                                                 */
   const float* grad_x_src_init; /* optional [n_src][16][64] added in (may alias nothing)        */
   float* grad_basis;         /* [E][16][64]                                                     */
-  int32_t accumulate_grad_basis;
+  int32_t accumulate_grad_basis; /* 0 overwrite, 1 add (fp32 sum, rounded once), 2 per edge (grad_basis_acc_mask; *_tc only) */
   float* node_grad_partials; /* [n_partials_node][GRL_NODE_GRAD_FLOATS]                         */
   int32_t n_partials_node;
   float* edge_grad_partials; /* [n_partials_edge][64*64] (kernel.weight)                        */
@@ -185,6 +185,11 @@ typedef struct {
                                 grl_fbconv_node_fwd_tc and read by grl_fbconv_node_bwd_tc instead of recomputing it     */
   const uint32_t* grad_amax; /* grl_absmax(grad_out): the tensor-core backward stages gradients as fp16 scaled by a
                                 power of two derived from it (max |g| -> [32, 64)); NULL = scale 1          */
+  /* sub layers (a layer evaluated at a subset of dst nodes that shares the PARENT graph's per-edge tensors):         */
+  const int32_t* basis_row;  /* optional [E], grl_fbconv_edge_fwd_tc: row of edge e in basis_bf16 (NULL = e)          */
+  const int32_t* grad_basis_acc_mask; /* accumulate_grad_basis == 2, grl_fbconv_edge_bwd_tc: [E_parent], indexed like
+                                basis_bf16; edge e ADDS to its grad_basis_bf16 row iff mask[e] >= 0 (a sub layer wrote
+                                that row earlier in this backward pass) and overwrites it otherwise                    */
 } GrlConvDesc;
 /* node partial layout: gW1[256][64] | gb1[256] | gW2[64][256] | gb2[64] | g_ln_g[64] | g_ln_b[64]
  *                      | g_bias[64] | g_fk[16][16][64] */
@@ -240,9 +245,59 @@ typedef struct {
   const float* grad_proj_v;    /* [B][k]                                                        */
   float* grad_mean;            /* [B][k]                                                        */
   float* grad_v;               /* [B][k]                                                        */
+  const float* grad_mean_add;  /* optional [B][k]: added to grad_mean (gradient reaching `mean` directly)   */
+  const float* grad_v_add;     /* optional [B][k]: added to grad_v                                          */
 } GrlProjDesc;
 int grl_trpl_fwd(const GrlProjDesc* d, grl_stream_t stream);
 int grl_trpl_bwd(const GrlProjDesc* d, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L1/P3  TRPL loss terms around the projection: replaces the ~170 elementwise / reduction launches of
+ * objectives/trpl.py:231-321 (advantage standardisation :286-289, log-weight :246-251, surrogate :303,
+ * entropy bonus :310-312, ESS :294-300, log_tr_metrics :255-273) and of
+ * projections/base_projection_layer.py:292-327 (get_trust_region_loss), :332-384 (compute_metrics) with
+ * utils/projection_utils.py:34-67,107-149 (gaussian_kl / gaussian_wasserstein_commutative) and the policy's
+ * entropy (gnn_gaussian_policy_diag.py:117-137), for diagonal Gaussians under "std := covariance diagonal".
+ * Per-sample terms are evaluated in fp64 and summed in a fixed order by one CTA (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+#define GRL_LOSS_TERMS 8    /* doubles per sample in GrlLossDesc.terms */
+#define GRL_LOSS_SCALARS 16 /* floats in GrlLossDesc.scalars */
+enum {
+  GRL_LS_LOSS_OBJECTIVE = 0, /* -mean(exp(log_w) * A_hat)                                   trpl.py:303      */
+  GRL_LS_LOSS_TRUST_REGION,  /* coeff * mean(mean_part + cov_part)(p || proj.detach())      base:292-327     */
+  GRL_LS_LOSS_ENTROPY,       /* -entropy_coef * mean(H[N(proj)])                            trpl.py:310-312  */
+  GRL_LS_DIST_ENTROPY,       /* mean(H[N(proj_mean, diag(proj_v))])                                          */
+  GRL_LS_ESS,                /* exp(2 lse(log_w) - lse(2 log_w)) / B                        trpl.py:294-300  */
+  GRL_LS_KL,                 /* mean gaussian_kl(p, proj) (mean + cov part)                 base:355-369     */
+  GRL_LS_CONSTRAINT,         /* mean trust_region_value(p, proj) (mean + cov part)                           */
+  GRL_LS_MEAN_CONSTRAINT, GRL_LS_MEAN_CONSTRAINT_MAX, GRL_LS_COV_CONSTRAINT, GRL_LS_COV_CONSTRAINT_MAX,
+  GRL_LS_ENTROPY,            /* mean policy.entropy(p)                                                        */
+  GRL_LS_ENTROPY_DIFF        /* mean(policy.entropy(proj) - policy.entropy(p))                                */
+};
+typedef struct {
+  int32_t batch, k;
+  int32_t proj_type;          /* trust_region_value: 0 = gaussian_kl, 1 = commuting W2 with scale_prec       */
+  int32_t normalize_advantage;
+  float entropy_coef, trust_region_coeff;
+  const float* mean;          /* [B][k] current policy p                                                     */
+  const float* v;             /* [B][k]                                                                      */
+  const float* proj_mean;     /* [B][k] grl_trpl_fwd outputs                                                 */
+  const float* proj_v;        /* [B][k]                                                                      */
+  const float* action;        /* [B][k]                                                                      */
+  const float* prev_log_prob; /* [B]                                                                         */
+  const float* advantage;     /* [B] un-normalised                                                           */
+  double* terms;              /* [B][GRL_LOSS_TERMS] workspace: written by fwd, read by bwd                  */
+  double* stats;              /* [2] advantage (loc, 1/scale): written by fwd, read by bwd                   */
+  float* scalars;             /* [GRL_LOSS_SCALARS] outputs, GRL_LS_* order                                  */
+  /* backward */
+  const float* grad_losses;   /* [3] upstream gradients of (loss_objective, loss_trust_region, loss_entropy) */
+  float* grad_proj_mean;      /* [B][k] -> GrlProjDesc.grad_proj_mean                                        */
+  float* grad_proj_v;         /* [B][k] -> GrlProjDesc.grad_proj_v                                           */
+  float* grad_mean_direct;    /* [B][k] -> GrlProjDesc.grad_mean_add (trust-region loss reaches p directly)  */
+  float* grad_v_direct;       /* [B][k] -> GrlProjDesc.grad_v_add                                            */
+} GrlLossDesc;
+int grl_trpl_loss_fwd(const GrlLossDesc* d, grl_stream_t stream);
+int grl_trpl_loss_bwd(const GrlLossDesc* d, grl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core building-block self-test: D[128][N] = bf16(A[128][K]) * bf16(B[N][K])^T, fp32 accumulate in

@@ -76,6 +76,96 @@ def test_update_step_matches_oracle(cfg_name, proj_type):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("proj_type", ["kl", "w2"])
+@pytest.mark.parametrize("B,k", [(1, 3), (37, 6), (4096, 12), (1500, 3)])
+def test_fused_trpl_loss_matches_torch_formulation(proj_type, B, k):
+    """ops.trpl_loss (grl_trpl_fwd + grl_trpl_loss_fwd / _bwd + grl_trpl_bwd) against the same quantities written
+    with torch ops in fp64 on top of ops.trpl_project (objectives/trpl.py:231-321, base_projection_layer.py:292-384):
+    13 scalars at 1e-6, gradients w.r.t. (mean, v) of an arbitrary combination of the three losses at 2e-6."""
+    import math
+    from geometry_rl_b200 import _lib, ops
+    gen = torch.Generator().manual_seed(B * 100 + k)
+    q_mean = torch.randn(B, k, generator=gen) * 0.3
+    q_v = (0.5 + torch.rand(B, k, generator=gen)) ** 2
+    s = torch.rand(B, 1, generator=gen)
+    mean = (q_mean + torch.randn(B, k, generator=gen) * 0.5 * s).cuda().requires_grad_(True)
+    v = (q_v * torch.exp(torch.randn(B, k, generator=gen) * 0.2 * s)).cuda().requires_grad_(True)
+    q_mean, q_v = q_mean.cuda(), q_v.cuda()
+    action = (q_mean + torch.randn(B, k, generator=gen).cuda() * q_v.sqrt())
+    prev_lp = (-0.5 * (((action - q_mean) ** 2 / q_v).sum(-1) + k * math.log(2 * math.pi) + q_v.log().sum(-1)))
+    adv = torch.randn(B, 1, generator=gen).cuda() * 3 + 1
+    em, ec, c_h, c_tr = 0.05, 0.0025, 0.01, 4.0
+    w = torch.tensor([0.7, 1.3, -0.4]).cuda()  # upstream gradients of the three losses
+
+    l_obj, l_tr, l_ent, sc = ops.trpl_loss(mean, v, q_mean, q_v, action, prev_lp, adv, em, ec, proj_type, c_h, c_tr, True)
+    (w[0] * l_obj + w[1] * l_tr + w[2] * l_ent).backward()
+    g_mean, g_v = mean.grad.clone(), v.grad.clone()
+    mean.grad = v.grad = None
+
+    pm, pv = ops.trpl_project(mean, v, q_mean, q_v, em, ec, proj_type)
+    D = torch.float64
+    m64, v64, pm64, pv64 = mean.to(D), v.to(D), pm.to(D), pv.to(D)
+    a_n = adv.to(D).reshape(-1)
+    if B > 1:
+        a_n = (a_n - a_n.mean()) / a_n.std().clamp_min(1e-6)
+    logp = -0.5 * (((action.to(D) - pm64) ** 2 / pv64).sum(-1) + k * math.log(2 * math.pi) + pv64.log().sum(-1))
+    lw = logp - prev_lp.to(D)
+    ent_dist = 0.5 * (k * (1 + math.log(2 * math.pi)) + pv64.log().sum(-1))
+    pmd, pvd = pm64.detach(), pv64.detach()
+
+    def kl(m_, s_, mo_, so_):
+        return 0.5 * ((m_ - mo_) / so_).pow(2).sum(-1), 0.5 * ((s_ / so_).square().sum(-1) - k + 2 * so_.log().sum(-1)
+                                                                - 2 * s_.log().sum(-1))
+
+    def w2(m_, s_, mo_, so_):
+        return ((m_ - mo_) / so_).pow(2).sum(-1), (1.0 + s_ * s_ / (so_ * so_) - 2.0 * s_ / so_).sum(-1)
+
+    trm, trc = (kl if proj_type == "kl" else w2)(m64, v64, pmd, pvd)
+    klm, klc = kl(m64, v64, pmd, pvd)
+    ref = {"loss_objective": -(lw.exp() * a_n).mean(), "loss_trust_region": (trm + trc).mean() * c_tr,
+           "loss_entropy": -c_h * ent_dist.mean(), "dist_entropy": ent_dist.mean(),
+           "ESS": (2 * lw.logsumexp(0) - (2 * lw).logsumexp(0)).exp() / B, "kl": (klm + klc).mean(),
+           "constraint": (trm + trc).mean(), "mean_constraint": trm.mean(), "mean_constraint_max": trm.max(),
+           "cov_constraint": trc.mean(), "cov_constraint_max": trc.max(),
+           "entropy": (0.5 * (k * math.log(2 * math.e * math.pi) + 2 * v64.log().sum(-1))).mean(),
+           "entropy_diff": (pv64.log().sum(-1) - v64.log().sum(-1)).mean()}
+    (w[0] * ref["loss_objective"] + w[1] * ref["loss_trust_region"] + w[2] * ref["loss_entropy"]).backward()
+    bad = []
+    for key, ix in _lib.LOSS_SCALAR_INDEX.items():
+        a, b = float(sc[ix]), float(ref[key])
+        if abs(a - b) > 1e-6 * abs(b) + 1e-7:
+            bad.append(f"{key}: {a} vs {b}")
+    for key, t in (("loss_objective", l_obj), ("loss_trust_region", l_tr), ("loss_entropy", l_ent)):
+        assert float(t) == float(sc[_lib.LOSS_SCALAR_INDEX[key]])
+    if G.rel(g_mean, mean.grad) >= 2e-6:
+        bad.append(G.err_report("grad mean", g_mean, mean.grad))
+    if G.rel(g_v, v.grad) >= 2e-6:
+        bad.append(G.err_report("grad v", g_v, v.grad))
+    assert not bad, "\n".join(bad)
+
+
+def test_fused_and_unfused_loss_modules_agree():
+    """TRPLLoss.fused switches between ops.trpl_loss and the torch formulation: same 12 outputs, same actor gradients."""
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.tensors import to_device
+    cfg, actor, critic, loss_module, _, oracle, mb, _ = _setup("rigid_pushing_multi_empn_trpl_cfg")
+    lrn = learner.Learner(cfg, actor, critic, loss_module)
+    res = {}
+    for fused in (True, False):
+        loss_module.fused = fused
+        actor.zero_grad(set_to_none=True)
+        out = lrn.compute_losses(to_device(mb, G.dev()))
+        out["actor_loss"].backward()
+        res[fused] = ({k: float(t) for k, t in out.items()},
+                      {k: p.grad.detach().clone() for k, p in actor.named_parameters() if p.grad is not None})
+    (o1, g1), (o0, g0) = res[True], res[False]
+    assert set(o1) == set(o0)
+    bad = [f"{k}: {o1[k]} vs {o0[k]}" for k in o0 if abs(o1[k] - o0[k]) > 1e-5 * abs(o0[k]) + 2e-7]
+    assert set(g1) == set(g0)
+    bad += [G.err_report(k, g1[k], g0[k]) for k in g0 if G.rel(g1[k], g0[k]) >= 2e-5]
+    assert not bad, "\n".join(bad)
+
+
 def test_gaussian_head_matches_reference_fixture():
     from geometry_rl_b200.algorithms.trust_region_projections.models.policy.gnn_gaussian_policy_diag import (
         GNNGaussianPolicyDiag)
