@@ -58,11 +58,14 @@ class GrlLossDesc(C.Structure):
                 ("entropy_coef", C.c_float), ("trust_region_coeff", C.c_float),
                 ("mean", _fp), ("v", _fp), ("proj_mean", _fp), ("proj_v", _fp), ("action", _fp), ("prev_log_prob", _fp),
                 ("advantage", _fp), ("terms", _fp), ("stats", _fp), ("scalars", _fp), ("grad_losses", _fp),
-                ("grad_proj_mean", _fp), ("grad_proj_v", _fp), ("grad_mean_direct", _fp), ("grad_v_direct", _fp)]
+                ("grad_proj_mean", _fp), ("grad_proj_v", _fp), ("grad_mean_direct", _fp), ("grad_v_direct", _fp),
+                ("sums", _fp), ("stage", _i32)]
 
 
 LOSS_TERMS = 8
 LOSS_SCALARS = 16
+LOSS_STATS = 8
+LOSS_SUMS = 16
 # index of every scalar grl_trpl_loss_fwd writes (GRL_LS_* in include/grl_b200.h)
 LOSS_SCALAR_INDEX = {"loss_objective": 0, "loss_trust_region": 1, "loss_entropy": 2, "dist_entropy": 3, "ESS": 4, "kl": 5,
                      "constraint": 6, "mean_constraint": 7, "mean_constraint_max": 8, "cov_constraint": 9,

@@ -44,8 +44,8 @@ class TRPLLoss(nn.Module):
         self._global_steps = 0
         # data-parallel hooks (None = single process): see geometry_rl_b200/parallel.py
         self.dp = None
-        # single process: projection + every actor-side loss term and metric in five kernel launches
-        # (ops.trpl_loss) instead of ~170 elementwise / reduction launches; False = the torch formulation below
+        # projection + every actor-side loss term and metric in a handful of kernel launches (ops.trpl_loss) instead
+        # of ~170 elementwise / reduction launches; False = the torch formulation below
         self.fused = True
 
     @property
@@ -92,7 +92,7 @@ class TRPLLoss(nn.Module):
 
     def _can_fuse(self, policy) -> bool:
         pr = self.projection
-        return (self.fused and self.dp is None and getattr(pr, "KERNEL_TYPE", None) in ("kl", "w2")
+        return (self.fused and getattr(pr, "KERNEL_TYPE", None) in ("kl", "w2")
                 and not pr.has_entropy_control and (pr.KERNEL_TYPE != "w2" or pr.scale_prec)
                 and getattr(policy, "contextual_std", True) and td_is_cuda(policy))
 
@@ -109,7 +109,8 @@ class TRPLLoss(nn.Module):
             current_dist.mean, current_dist.var_diag, previous_dist.mean, previous_dist.var_diag, td_get(td, "action"),
             td_get(td, "sample_log_prob"), advantage, pr.mean_bound, pr.cov_bound, pr.KERNEL_TYPE,
             self.entropy_coef if self.entropy_bonus else 0.0, pr.trust_region_coeff,
-            self.normalize_advantage and advantage.numel() > 1)
+            self.normalize_advantage and advantage.numel() * (1 if self.dp is None else self.dp.world_size) > 1,
+            None if self.dp is None else self.dp.all_reduce_named)
         ix = _lib.LOSS_SCALAR_INDEX
         out = {"loss_objective": l_obj, "loss_trust_region": l_tr}
         if self.entropy_bonus:

@@ -291,24 +291,43 @@ __device__ __forceinline__ double block_max(double x, double* sh) {
   return x;
 }
 
-__global__ void __launch_bounds__(kLossThreads) trpl_loss_reduce_kernel(const GrlLossDesc d) {
+// stats  = { sum A, sum A^2, n, max log_w, loc, 1 / scale }          (entries 0-3: stage 1; 4-5: stage 2)
+// sums   = { [0] sum exp(lw) A_hat, [1] sum (tr_mean + tr_cov), [2] sum H_dist      -> this rank's share of the losses
+//            [3] sum e, [4] sum e^2 (e = exp(lw - max)), [5] sum tr_mean, [6] sum tr_cov, [7] sum kl, [8] sum H_p,
+//            [9] sum (H_proj - H_p)                                                   -> summed over ranks
+//            [10] max tr_mean, [11] max tr_cov }                                      -> max over ranks
+// Between the stages a data-parallel caller all-reduces stats[0:3] (sum), stats[3] (max), sums[3:10] (sum) and
+// sums[10:12] (max); a single process runs the three stages back to back.
+__global__ void __launch_bounds__(kLossThreads) trpl_loss_stats_kernel(const GrlLossDesc d) {
   __shared__ double sh[32];
   const int B = d.batch, tid = threadIdx.x;
   const double* T = d.terms;
-  // advantage standardisation (trpl.py:286-289): mean, unbiased std clamped at 1e-6
-  double loc = 0.0, inv_scale = 1.0;
-  if (d.normalize_advantage && B > 1) {
-    double s = 0.0;
-    for (int b = tid; b < B; b += kLossThreads) s += T[(size_t)b * GRL_LOSS_TERMS + 7];
-    loc = block_sum(s, sh) / B;
-    double q = 0.0;
-    for (int b = tid; b < B; b += kLossThreads) { const double t = T[(size_t)b * GRL_LOSS_TERMS + 7] - loc; q += t * t; }
-    const double sd = sqrt(block_sum(q, sh) / (B - 1));
-    inv_scale = 1.0 / fmax(sd, 1e-6);
+  double s = 0.0, q = 0.0, mx = -1e300;
+  for (int b = tid; b < B; b += kLossThreads) {
+    const double a = T[(size_t)b * GRL_LOSS_TERMS + 7];
+    s += a;
+    q += a * a;
+    mx = fmax(mx, T[(size_t)b * GRL_LOSS_TERMS]);
   }
-  double mx = -1e300;
-  for (int b = tid; b < B; b += kLossThreads) mx = fmax(mx, T[(size_t)b * GRL_LOSS_TERMS]);
+  s = block_sum(s, sh);
+  q = block_sum(q, sh);
   mx = block_max(mx, sh);
+  if (tid == 0) { d.stats[0] = s; d.stats[1] = q; d.stats[2] = (double)B; d.stats[3] = mx; }
+}
+
+__global__ void __launch_bounds__(kLossThreads) trpl_loss_sums_kernel(const GrlLossDesc d) {
+  __shared__ double sh[32];
+  const int B = d.batch, tid = threadIdx.x;
+  const double* T = d.terms;
+  // advantage standardisation (trpl.py:286-289): mean, unbiased std clamped at 1e-6, over the GLOBAL minibatch
+  const double n = d.stats[2];
+  double loc = 0.0, inv_scale = 1.0;
+  if (d.normalize_advantage && n > 1.0) {
+    loc = d.stats[0] / n;
+    const double var = fmax((d.stats[1] - n * loc * loc) / (n - 1.0), 0.0);
+    inv_scale = 1.0 / fmax(sqrt(var), 1e-6);
+  }
+  const double mx = d.stats[3];
   double s_obj = 0.0, s_e1 = 0.0, s_e2 = 0.0, s_trm = 0.0, s_trc = 0.0, s_kl = 0.0, s_hd = 0.0, s_hp = 0.0, s_hq = 0.0;
   double m_trm = -1e300, m_trc = -1e300;
   for (int b = tid; b < B; b += kLossThreads) {
@@ -327,36 +346,46 @@ __global__ void __launch_bounds__(kLossThreads) trpl_loss_reduce_kernel(const Gr
   s_hd = block_sum(s_hd, sh); s_hp = block_sum(s_hp, sh); s_hq = block_sum(s_hq, sh);
   m_trm = block_max(m_trm, sh); m_trc = block_max(m_trc, sh);
   if (tid == 0) {
-    const double n = (double)B;
-    float* S = d.scalars;
-    S[GRL_LS_LOSS_OBJECTIVE] = (float)(-s_obj / n);
-    S[GRL_LS_LOSS_TRUST_REGION] = (float)((s_trm + s_trc) / n * (double)d.trust_region_coeff);
-    S[GRL_LS_LOSS_ENTROPY] = (float)(-(double)d.entropy_coef * s_hd / n);
-    S[GRL_LS_DIST_ENTROPY] = (float)(s_hd / n);
-    // exp(2 lse(lw) - lse(2 lw)) / B with both log-sum-exps shifted by max(lw)
-    S[GRL_LS_ESS] = (float)(s_e1 * s_e1 / s_e2 / n);
-    S[GRL_LS_KL] = (float)(s_kl / n);
-    S[GRL_LS_CONSTRAINT] = (float)((s_trm + s_trc) / n);
-    S[GRL_LS_MEAN_CONSTRAINT] = (float)(s_trm / n);
-    S[GRL_LS_MEAN_CONSTRAINT_MAX] = (float)m_trm;
-    S[GRL_LS_COV_CONSTRAINT] = (float)(s_trc / n);
-    S[GRL_LS_COV_CONSTRAINT_MAX] = (float)m_trc;
-    S[GRL_LS_ENTROPY] = (float)(s_hp / n);
-    S[GRL_LS_ENTROPY_DIFF] = (float)((s_hq - s_hp) / n);
-    for (int i = GRL_LS_ENTROPY_DIFF + 1; i < GRL_LOSS_SCALARS; ++i) S[i] = 0.f;
-    d.stats[0] = loc;
-    d.stats[1] = inv_scale;
+    double* S = d.sums;
+    S[0] = s_obj; S[1] = s_trm + s_trc; S[2] = s_hd;
+    S[3] = s_e1; S[4] = s_e2; S[5] = s_trm; S[6] = s_trc; S[7] = s_kl; S[8] = s_hp; S[9] = s_hq - s_hp;
+    S[10] = m_trm; S[11] = m_trc;
+    d.stats[4] = loc;
+    d.stats[5] = inv_scale;
   }
+}
+
+__global__ void trpl_loss_finalize_kernel(const GrlLossDesc d) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n = d.stats[2];  // global sample count
+  const double* G = d.sums;
+  float* S = d.scalars;
+  // losses: this rank's share (local sum / global count); summed gradients are then the global-mean gradients
+  S[GRL_LS_LOSS_OBJECTIVE] = (float)(-G[0] / n);
+  S[GRL_LS_LOSS_TRUST_REGION] = (float)(G[1] / n * (double)d.trust_region_coeff);
+  S[GRL_LS_LOSS_ENTROPY] = (float)(-(double)d.entropy_coef * G[2] / n);
+  S[GRL_LS_DIST_ENTROPY] = (float)(G[2] / n);
+  // exp(2 lse(lw) - lse(2 lw)) / B with both log-sum-exps shifted by max(lw)
+  S[GRL_LS_ESS] = (float)(G[3] * G[3] / G[4] / n);
+  S[GRL_LS_KL] = (float)(G[7] / n);
+  S[GRL_LS_CONSTRAINT] = (float)((G[5] + G[6]) / n);
+  S[GRL_LS_MEAN_CONSTRAINT] = (float)(G[5] / n);
+  S[GRL_LS_MEAN_CONSTRAINT_MAX] = (float)G[10];
+  S[GRL_LS_COV_CONSTRAINT] = (float)(G[6] / n);
+  S[GRL_LS_COV_CONSTRAINT_MAX] = (float)G[11];
+  S[GRL_LS_ENTROPY] = (float)(G[8] / n);
+  S[GRL_LS_ENTROPY_DIFF] = (float)(G[9] / n);
+  for (int i = GRL_LS_ENTROPY_DIFF + 1; i < GRL_LOSS_SCALARS; ++i) S[i] = 0.f;
 }
 
 __global__ void __launch_bounds__(128) trpl_loss_bwd_kernel(const GrlLossDesc d) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= d.batch) return;
   const int k = d.k;
-  const double n = (double)d.batch;
+  const double n = d.stats[2];  // global sample count
   const double g_obj = d.grad_losses[0], g_tr = d.grad_losses[1], g_ent = d.grad_losses[2];
   const double* T = d.terms + (size_t)b * GRL_LOSS_TERMS;
-  const double adv = (T[7] - d.stats[0]) * d.stats[1];
+  const double adv = (T[7] - d.stats[4]) * d.stats[5];
   const double g_lw = -g_obj / n * exp(T[0]) * adv;           // d loss_objective / d log_prob
   const double c_ent = -g_ent * (double)d.entropy_coef / n;   // d loss_entropy / d H_dist
   const double c_tr = g_tr * (double)d.trust_region_coeff / n;
@@ -423,15 +452,21 @@ static int check_loss(const GrlLossDesc* d, const char* who, bool bwd) {
               "%s: null pointer", who);
   if (bwd) GRL_REQUIRE(d->grad_losses && d->grad_proj_mean && d->grad_proj_v && d->grad_mean_direct && d->grad_v_direct,
                        GRL_EINVAL, "%s: null grad pointer", who);
-  else GRL_REQUIRE(d->prev_log_prob && d->advantage && d->scalars, GRL_EINVAL, "%s: null input / output pointer", who);
+  else GRL_REQUIRE(d->prev_log_prob && d->advantage && d->scalars && d->sums, GRL_EINVAL, "%s: null input / output pointer", who);
   return GRL_OK;
 }
 
 int grl_trpl_loss_fwd(const GrlLossDesc* d, grl_stream_t stream) {
   const int rc = check_loss(d, "grl_trpl_loss_fwd", false);
   if (rc != GRL_OK) return rc;
-  grl::trpl_loss_terms_kernel<<<(d->batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*d);
-  grl::trpl_loss_reduce_kernel<<<1, grl::kLossThreads, 0, (cudaStream_t)stream>>>(*d);
+  GRL_REQUIRE(d->stage >= 0 && d->stage <= 3, GRL_EINVAL, "grl_trpl_loss_fwd: stage=%d", d->stage);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->stage == 0 || d->stage == 1) {
+    grl::trpl_loss_terms_kernel<<<(d->batch + 127) / 128, 128, 0, st>>>(*d);
+    grl::trpl_loss_stats_kernel<<<1, grl::kLossThreads, 0, st>>>(*d);
+  }
+  if (d->stage == 0 || d->stage == 2) grl::trpl_loss_sums_kernel<<<1, grl::kLossThreads, 0, st>>>(*d);
+  if (d->stage == 0 || d->stage == 3) grl::trpl_loss_finalize_kernel<<<1, 32, 0, st>>>(*d);
   return grl::check_launch("grl_trpl_loss_fwd");
 }
 

@@ -533,7 +533,7 @@ class TrplLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, proj_type,
-                entropy_coef, trust_region_coeff, normalize_advantage):
+                entropy_coef, trust_region_coeff, normalize_advantage, all_reduce=None):
         mean, v, old_mean, old_v = _f32c(mean), _f32c(v), _f32c(old_mean), _f32c(old_v)
         action, prev_log_prob, advantage = _f32c(action), _f32c(prev_log_prob).reshape(-1), _f32c(advantage).reshape(-1)
         B, k = mean.shape
@@ -546,14 +546,27 @@ class TrplLossFn(torch.autograd.Function):
                           proj_v=L.ptr(pv), eta=L.ptr_any(eta))
         L.call("grl_trpl_fwd", C.byref(d))
         terms = torch.empty(B, L.LOSS_TERMS, dtype=torch.float64, device=dev)
-        stats = torch.empty(2, dtype=torch.float64, device=dev)
+        stats = torch.empty(L.LOSS_STATS, dtype=torch.float64, device=dev)
+        sums = torch.empty(L.LOSS_SUMS, dtype=torch.float64, device=dev)
         scalars = torch.empty(L.LOSS_SCALARS, dtype=torch.float32, device=dev)
         ld = L.GrlLossDesc(batch=B, k=k, proj_type=proj_type, normalize_advantage=int(bool(normalize_advantage)),
                            entropy_coef=float(entropy_coef), trust_region_coeff=float(trust_region_coeff),
                            mean=L.ptr(mean), v=L.ptr(v), proj_mean=L.ptr(pm), proj_v=L.ptr(pv), action=L.ptr(action),
                            prev_log_prob=L.ptr(prev_log_prob), advantage=L.ptr(advantage), terms=L.ptr_any(terms),
-                           stats=L.ptr_any(stats), scalars=L.ptr(scalars))
-        L.call("grl_trpl_loss_fwd", C.byref(ld))
+                           stats=L.ptr_any(stats), scalars=L.ptr(scalars), sums=L.ptr_any(sums), stage=0)
+        if all_reduce is None:
+            L.call("grl_trpl_loss_fwd", C.byref(ld))
+        else:  # data parallel: `all_reduce(tensor, "sum" | "max")` makes the cross-sample reductions global
+            ld.stage = 1
+            L.call("grl_trpl_loss_fwd", C.byref(ld))
+            all_reduce(stats[0:3], "sum")
+            all_reduce(stats[3:4], "max")
+            ld.stage = 2
+            L.call("grl_trpl_loss_fwd", C.byref(ld))
+            all_reduce(sums[3:10], "sum")
+            all_reduce(sums[10:12], "max")
+            ld.stage = 3
+            L.call("grl_trpl_loss_fwd", C.byref(ld))
         ctx.save_for_backward(mean, v, old_mean, old_v, action, pm, pv, eta, terms, stats)
         ctx.meta = (float(eps_mean), float(eps_cov), proj_type, float(entropy_coef), float(trust_region_coeff))
         ctx.mark_non_differentiable(scalars)
@@ -581,12 +594,14 @@ class TrplLossFn(torch.autograd.Function):
                           grad_proj_mean=L.ptr(g_pm), grad_proj_v=L.ptr(g_pv), grad_mean=L.ptr(gm), grad_v=L.ptr(gv),
                           grad_mean_add=L.ptr(g_md), grad_v_add=L.ptr(g_vd))
         L.call("grl_trpl_bwd", C.byref(d))
-        return (gm, gv) + (None,) * 11
+        return (gm, gv) + (None,) * 12
 
 
 def trpl_loss(mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, proj_type, entropy_coef,
-              trust_region_coeff, normalize_advantage=True):
-    """-> (loss_objective, loss_trust_region, loss_entropy, scalars) with scalars indexed by _lib.LOSS_SCALAR_INDEX."""
+              trust_region_coeff, normalize_advantage=True, all_reduce=None):
+    """-> (loss_objective, loss_trust_region, loss_entropy, scalars) with scalars indexed by _lib.LOSS_SCALAR_INDEX.
+    `all_reduce(tensor, "sum" | "max")` (data parallel, equal shards): advantage statistics, ESS and metrics become
+    global, the three losses are this rank's share (local sum / global count)."""
     code = {"kl": 0, "w2": 1}[proj_type]
     return TrplLossFn.apply(mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, code,
-                            entropy_coef, trust_region_coeff, normalize_advantage)
+                            entropy_coef, trust_region_coeff, normalize_advantage, all_reduce)

@@ -54,6 +54,10 @@ class DataParallel:
         self.collectives += 1
         return t
 
+    def all_reduce_named(self, t: torch.Tensor, op: str) -> torch.Tensor:
+        """In-place all-reduce of a (view of a) small statistics tensor; `op` = "sum" | "max" (ops.trpl_loss hook)."""
+        return self.all_reduce(t, dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)
+
     # ---- forward-side statistics ---------------------------------------------------------------------
     def mean_std_unbiased(self, x: torch.Tensor):
         x = x.detach().float()

@@ -259,9 +259,16 @@ int grl_trpl_bwd(const GrlProjDesc* d, grl_stream_t stream);
  * utils/projection_utils.py:34-67,107-149 (gaussian_kl / gaussian_wasserstein_commutative) and the policy's
  * entropy (gnn_gaussian_policy_diag.py:117-137), for diagonal Gaussians under "std := covariance diagonal".
  * Per-sample terms are evaluated in fp64 and summed in a fixed order by one CTA (deterministic).
+ * Data parallel: the cross-sample reductions must be global.  grl_trpl_loss_fwd runs in three stages
+ * (GrlLossDesc.stage: 0 = all, single process) between which the caller all-reduces a few doubles:
+ *   stage 1  per-sample terms; stats[0:3] = (sum A, sum A^2, n), stats[3] = max log_w     -> SUM stats[0:3], MAX stats[3]
+ *   stage 2  sums[0:3] this rank's loss sums, sums[3:10] metric sums, sums[10:12] maxima   -> SUM sums[3:10], MAX sums[10:12]
+ *   stage 3  scalars (losses = local sum / global count, metrics global)
  * ------------------------------------------------------------------------------------------ */
 #define GRL_LOSS_TERMS 8    /* doubles per sample in GrlLossDesc.terms */
 #define GRL_LOSS_SCALARS 16 /* floats in GrlLossDesc.scalars */
+#define GRL_LOSS_STATS 8    /* doubles in GrlLossDesc.stats */
+#define GRL_LOSS_SUMS 16    /* doubles in GrlLossDesc.sums */
 enum {
   GRL_LS_LOSS_OBJECTIVE = 0, /* -mean(exp(log_w) * A_hat)                                   trpl.py:303      */
   GRL_LS_LOSS_TRUST_REGION,  /* coeff * mean(mean_part + cov_part)(p || proj.detach())      base:292-327     */
@@ -287,7 +294,7 @@ typedef struct {
   const float* prev_log_prob; /* [B]                                                                         */
   const float* advantage;     /* [B] un-normalised                                                           */
   double* terms;              /* [B][GRL_LOSS_TERMS] workspace: written by fwd, read by bwd                  */
-  double* stats;              /* [2] advantage (loc, 1/scale): written by fwd, read by bwd                   */
+  double* stats;              /* [GRL_LOSS_STATS] (sum A, sum A^2, n, max log_w, loc, 1/scale): fwd writes, bwd reads */
   float* scalars;             /* [GRL_LOSS_SCALARS] outputs, GRL_LS_* order                                  */
   /* backward */
   const float* grad_losses;   /* [3] upstream gradients of (loss_objective, loss_trust_region, loss_entropy) */
@@ -295,6 +302,9 @@ typedef struct {
   float* grad_proj_v;         /* [B][k] -> GrlProjDesc.grad_proj_v                                           */
   float* grad_mean_direct;    /* [B][k] -> GrlProjDesc.grad_mean_add (trust-region loss reaches p directly)  */
   float* grad_v_direct;       /* [B][k] -> GrlProjDesc.grad_v_add                                            */
+  /* staged forward (data parallel) */
+  double* sums;               /* [GRL_LOSS_SUMS] workspace between stages 2 and 3                            */
+  int32_t stage;              /* 0 = stages 1-3 in one call, else 1 | 2 | 3                                  */
 } GrlLossDesc;
 int grl_trpl_loss_fwd(const GrlLossDesc* d, grl_stream_t stream);
 int grl_trpl_loss_bwd(const GrlLossDesc* d, grl_stream_t stream);
