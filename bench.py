@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-dp-graph", action="store_true", help="N > 1: launch the step eagerly instead of replaying it "
                     "(NCCL all-reduces included) from a CUDA graph")
     ap.add_argument("--dp-graph", action="store_true", help=argparse.SUPPRESS)  # now the default
+    ap.add_argument("--no-dp-overlap", action="store_true", help="N > 1: keep the critic branch on the actor's stream "
+                    "(default: second stream with its own NCCL communicator)")
     ap.add_argument("--single-precision", action="store_true", help="skip the second (other precision) measurement")
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="nn.Linear contractions of the message-passing kernels: fp32 FFMA (parity 1e-5) or bf16 tcgen05 "
@@ -350,7 +352,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         from geometry_rl_b200.parallel import DataParallel
-        dp = DataParallel()
+        dp = DataParallel(side_group=not args.no_dp_overlap)
     cfg = CONFIGS[args.config]
 
     main_res = measure(args, args.precision, dev, dp, rank, world, local, args.steps)

@@ -111,10 +111,10 @@ class Learner:
         fused = fused_adam and next(actor.parameters()).is_cuda
         # The critic branch (DeepSets forward, clipped value loss, backward: ~100 small launches) is independent of the
         # actor branch until the optimiser steps: it runs on a second stream, under the actor's large kernels.
-        # Single process only: under data parallelism its graph-LayerNorm statistics are collectives, which cannot start
-        # while a persistent kernel holds every SM (measured at 2 GPUs: no gain).
-        self._critic_stream = (torch.cuda.Stream() if overlap_critic and dp is None and loss_module.critic_coef
-                               and next(actor.parameters()).is_cuda else None)
+        # Data parallel: its graph-LayerNorm statistics are collectives, so it needs its own communicator
+        # (DataParallel(side_group=True)); without one the step stays on a single stream.
+        self._critic_stream = (torch.cuda.Stream() if overlap_critic and (dp is None or dp.side is not None)
+                               and loss_module.critic_coef and next(actor.parameters()).is_cuda else None)
         # capturable: the step counter lives on the device, so the whole update can be replayed from a CUDA graph
         self.actor_optim = torch.optim.Adam(actor.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
         self.critic_optim = torch.optim.Adam(critic.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
@@ -168,6 +168,8 @@ class Learner:
         self.num_network_updates += 1
         loss["actor_loss"].backward()
         main.wait_stream(side)
+        if self.dp is not None:
+            self.dp.allreduce_grads(list(self.actor.parameters()) + list(self.critic.parameters()))
         if self.cfg.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.cfg.max_grad_norm)
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.cfg.max_grad_norm)

@@ -41,13 +41,18 @@ class _GraphNormStats(torch.autograd.Function):
 
 
 class DataParallel:
-    def __init__(self, group=None):
+    def __init__(self, group=None, side_group: bool = False):
+        """`side_group=True` creates a SECOND communicator (`self.side`) for the critic branch: the learner then
+        runs that branch on its own CUDA stream under the actor's kernels, and its graph-LayerNorm statistics
+        all-reduce on `side` while the actor-side reductions and the gradient bucket use the main communicator
+        (collectives of one communicator must stay ordered; two streams need two communicators)."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.collectives = 0
+        self.side = DataParallel(group=dist.new_group(), side_group=False) if side_group else None
 
     def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         dist.all_reduce(t, op=op, group=self.group)
@@ -120,7 +125,8 @@ class DataParallel:
         """Install the global-statistics hooks on a TRPLLoss and on every GraphLayerNorm of its critic."""
         from .modules.pyg_models.pyg_compat import GraphLayerNorm
         loss_module.dp = self
+        critic_dp = self.side if self.side is not None else self
         for m in loss_module.critic_network.modules():
             if isinstance(m, GraphLayerNorm):
-                m.stats_reduce = self.graph_norm_stats
+                m.stats_reduce = critic_dp.graph_norm_stats
         return loss_module

@@ -65,12 +65,35 @@ def _worker(rank, world, port, out_path):
         dp.allreduce_grads(list(actor.parameters()) + list(critic.parameters()))
         logged = dp.global_losses(out)
         torch.cuda.synchronize()
+        result = {"losses": {k: logged[k].detach().cpu() for k in KEYS}, "grads": _grads(actor, critic),
+                  "collectives": dp.collectives}
+        # the learner's own update(): critic branch on a second stream with its own communicator
+        cfg, actor2, critic2, loss_module2, _ = _setup(dev)
+        dp2 = DataParallel(side_group=True)
+        lrn2 = learner.Learner(cfg, actor2, critic2, loss_module2, dp=dp2)
+        assert lrn2._critic_stream is not None
+        result["update_grads"] = _update_grads(lrn2, actor2, critic2, to_device(shard, dev))
+        torch.cuda.synchronize()
         if rank == 0:
-            torch.save({"losses": {k: logged[k].detach().cpu() for k in KEYS}, "grads": _grads(actor, critic),
-                        "collectives": dp.collectives}, out_path)
+            torch.save(result, out_path)
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _update_grads(lrn, actor, critic, batch):
+    """Run Learner.update once and return the gradients the optimisers were stepped with."""
+    seen = {}
+    real_step = lrn.actor_optim.step
+
+    def spy(*a, **k):
+        seen["g"] = _grads(actor, critic)
+        return real_step(*a, **k)
+
+    lrn.actor_optim.step = spy
+    lrn.update(batch)
+    lrn.actor_optim.step = real_step
+    return seen["g"]
 
 
 def test_two_rank_step_equals_single_process(tmp_path):
@@ -104,5 +127,15 @@ def test_two_rank_step_equals_single_process(tmp_path):
         err = float((g_dp - g1).abs().max()) / float(g1.abs().max())
         if err > 5e-5:
             bad.append(f"grad[{i}] rel err {err:.2e}")
+    # Learner.update under data parallelism (two streams, two communicators) steps with the single-process gradients
+    cfg, actor3, critic3, loss_module3, _ = _setup(dev)
+    lrn3 = learner.Learner(cfg, actor3, critic3, loss_module3)
+    g_single = _update_grads(lrn3, actor3, critic3, to_device(mb, dev))
+    for i, (g_dp, g1) in enumerate(zip(res["update_grads"], g_single)):
+        if g1 is None or float(g1.abs().max()) == 0.0:
+            continue
+        err = float((g_dp - g1).abs().max()) / float(g1.abs().max())
+        if err > 5e-5:
+            bad.append(f"update grad[{i}] rel err {err:.2e}")
     assert not bad, "\n".join(bad)
     assert res["collectives"] >= 5
