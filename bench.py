@@ -124,6 +124,31 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_shape(cfg, actor, batch, dev, precision):
+    """Rows the message-passing kernels actually process for one minibatch (after EMPN row pruning)."""
+    from geometry_rl_b200.tensors import to_device
+    policy = actor.get_submodule("0").module
+    try:
+        with torch.no_grad():
+            graph, _ = policy.hyper_data.build_data(*[to_device(batch, dev)[k] for k in actor.in_keys], train=False)
+        if cfg.model == "empn" and getattr(policy.gnn, "prune_dead_rows", False):
+            pr = graph.homogeneous_pruned()
+            n, e = pr.es.n_src, pr.es.n_edges
+            rows = (f"EMPN rows that reach the readout only: {n} live of {graph.num_nodes} padded nodes, {e} edges; last layer at "
+                    f"{pr.sub.n_dst} output nodes over {pr.sub.n_edges} edges (outputs and gradients identical to the dense "
+                    f"evaluation, tests/test_gpu_parity.py::test_empn_pruned_rows_equal_dense_evaluation)")
+        elif cfg.model == "empn":
+            es = graph.homogeneous()
+            n, e, rows = es.n_src, es.n_edges, "dense (all padded nodes, every layer)"
+        else:
+            n = graph.num_nodes
+            e = sum(es.n_edges for es in graph.edge_sets.values())
+            rows = "dense"
+        return {"latent_mb": n * 4096 / 1e6, "basis_mb": e * (2048 if precision == "bf16" else 4096) / 1e6, "rows": rows}
+    except Exception as exc:  # reporting only
+        return {"latent_mb": float("nan"), "basis_mb": float("nan"), "rows": f"unavailable ({exc})"}
+
+
 # algorithmic HBM bytes of ONE launch of each kernel (DESIGN.md "Kernels"): R = 4096 B latent row
 R = 16 * 64 * 4
 
@@ -285,6 +310,7 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
     ms = max_over_ranks(e0.elapsed_time(e1))
     res = {"precision": precision, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
            "clocks": clocks, "gpu_launches": launches, "cuda_graph": use_graph, "B": B, "model": cfg.model}
+    res.update(workload_shape(cfg, actor, host_batches[0], dev, precision))
 
     # ---- end to end: pinned host minibatch -> H2D -> step -> loss scalar D2H, every step ----------------
     barrier()
@@ -382,7 +408,9 @@ def run_ours(args):
                                  "segmented sums, projection, losses fp32)",
                        "cuda_graph": main_res["cuda_graph"], "minibatch_per_gpu": B, "global_minibatch": B * world,
                        "parallelism": f"dp{world}", "l2": f"rotating {N_ROTATE} minibatches; per-step working set "
-                       f"(latents {B * 49 * 4096 / 1e6:.0f} MB each) exceeds the 126 MB L2"},
+                       f"(latent tensors of {main_res['latent_mb']:.0f} MB each, edge basis {main_res['basis_mb']:.0f} MB) "
+                       f"exceeds the 126 MB L2",
+                       "rows": main_res["rows"]},
             "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
             "roofline": main_res["roofline"], "cpu_baseline": cpu,
         }

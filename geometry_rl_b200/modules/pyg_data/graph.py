@@ -42,6 +42,16 @@ class PrunedHomo:
     sub: ops.SubEdgeSet
 
 
+@dataclass
+class PrunedHetero:
+    """Heterogeneous topology without the nodes that cannot influence the readout: a node is kept when it has an edge
+    of any type (as source or destination) or belongs to the output node type.  Per node type the renumbering is
+    monotone, so every edge set keeps its edge order; node types left without nodes (isolated target nodes) vanish."""
+    live_ids: Dict[str, torch.Tensor]  # node type -> [n_live] int64 indices into the padded per-type node order
+    edge_sets: Dict[EdgeType, ops.EdgeSet]  # compact node ids; edge types whose endpoints vanished are omitted
+    num_nodes: int  # total live nodes
+
+
 class GraphBatch:
     def __init__(self, num_graphs: int, nodes_per_graph: Dict[str, int], device):
         self.num_graphs = num_graphs
@@ -153,3 +163,37 @@ class GraphBatch:
             sub = ops.build_sub_edge_set(compact, out_ids)
             self._homo_cache["pruned"] = PrunedHomo(live_ids, compact, sub)
         return self._homo_cache["pruned"]
+
+    # -- heterogeneous view without dead rows (HEPi) ---------------------------------------------------
+    def hetero_pruned(self) -> PrunedHetero:
+        if "hetero_pruned" not in self._homo_cache:
+            dev = self.device
+            touched = {t: torch.zeros(self._stores[t].num_nodes, dtype=torch.bool, device=dev) for t in self.node_types}
+            for (src, _, dst), es in self.edge_sets.items():
+                if es.n_edges > 0:
+                    touched[src] |= (es.rowptr_src[1:] - es.rowptr_src[:-1]) > 0
+                    touched[dst] |= (es.rowptr_dst[1:] - es.rowptr_dst[:-1]) > 0
+            if self.output_mask_key is not None:
+                touched[self.output_mask_key][:] = True
+            else:  # no readout restriction: every node is an output
+                for t in touched:
+                    touched[t][:] = True
+            live_ids, new_id = {}, {}
+            for t, m in touched.items():
+                ids = m.nonzero().squeeze(1)
+                if ids.numel() > 0:
+                    live_ids[t] = ids
+                    new_id[t] = torch.cumsum(m.to(torch.int64), 0) - 1
+            edge_sets = {}
+            for et, es in self.edge_sets.items():
+                src, _, dst = et
+                if es.n_edges == 0 or src not in live_ids or dst not in live_ids:
+                    continue
+                edge_sets[et] = ops.EdgeSet(
+                    int(live_ids[src].numel()), int(live_ids[dst].numel()), es.n_edges, es.coo, es.edge_ptr,
+                    torch.cat([es.rowptr_dst[:-1][live_ids[dst]], es.rowptr_dst[-1:]]).contiguous(),
+                    new_id[src][es.edge_src.long()].to(torch.int32).contiguous(),
+                    new_id[dst][es.edge_dst.long()].to(torch.int32).contiguous(), es.eid_coo,
+                    torch.cat([es.rowptr_src[:-1][live_ids[src]], es.rowptr_src[-1:]]).contiguous(), es.src_eid)
+            self._homo_cache["hetero_pruned"] = PrunedHetero(live_ids, edge_sets, sum(int(v.numel()) for v in live_ids.values()))
+        return self._homo_cache["hetero_pruned"]

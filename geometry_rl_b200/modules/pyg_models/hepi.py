@@ -57,31 +57,63 @@ class HEPi(nn.Module):
                         level_processor[(_plain(src), _plain(level), _plain(dest))] = pl.to(device)
             self.processor.append(HeteroFiberConv(level_processor))
         self.decoder = nn.Linear(latent_dim, output_dim + output_dim_vec)
+        # Skip the rows that cannot reach the readout: nodes without any edge outside the output node type (zero-padded
+        # object points, isolated target nodes) are neither embedded nor convolved.  The reference computes and then
+        # never reads them; outputs and every parameter gradient are unchanged.  False = all padded rows.
+        self.prune_dead_rows = True
 
     def fiber_basis(self) -> torch.Tensor:
         g = self.ori_grid
         inv3 = (g[None, :, :] * g[:, None, :]).sum(-1, keepdim=True)  # hepi.py:119
         return self.fiber_basis_fn(inv3)
 
+    def calibration_pending(self, graph) -> bool:
+        """True until every convolution that runs on this graph did its one-time calibration (conv.py:104-105,151-157),
+        which takes statistics over ALL rows of its inputs: those calls are evaluated densely.  Convolutions of edge
+        types without edges never run (hetero_fiber_conv.py:48-49) and never calibrate."""
+        if not self.training:
+            return False
+        from .ponita.hetero_fiber_conv import key_edge_type
+        procs = [self.processor] if self.shared_processor else list(self.processor)
+        for p in procs:
+            for key, c in p.convs.items():
+                es = graph.edge_sets.get(key_edge_type(key))
+                if es is not None and es.n_edges > 0 and not c._is_callibrated():
+                    return True
+        return False
+
     def one_step(self, graph, u_dict, u: torch.Tensor = None, u_properties: torch.Tensor = None):
         scalar_dict, vector_dict = u_dict
         ori3 = pad_ori3(self.ori_grid)
+        node_types, edge_sets = list(graph.node_types), graph.edge_sets
+        pos = {nt: graph[nt].pos for nt in node_types}
+        if self.prune_dead_rows and graph.output_mask_key is not None and not self.calibration_pending(graph):
+            pr = graph.hetero_pruned()
+            node_types = [nt for nt in node_types if nt in pr.live_ids]
+            edge_sets = {et: pr.edge_sets.get(et, graph.edge_sets[et]) for et in graph.edge_types}
+            with torch.no_grad():
+                scalar_dict = {nt: scalar_dict[nt][pr.live_ids[nt]] for nt in node_types}
+                vector_dict = {nt: vector_dict[nt][pr.live_ids[nt]] for nt in node_types}
+                pos = {nt: pos[nt][pr.live_ids[nt]] for nt in node_types}
+            live_edge_types = [et for et in graph.edge_types if et in pr.edge_sets]
+        else:
+            live_edge_types = list(graph.edge_types)
         latent_dict = {nt: ops.EmbedFn.apply(scalar_dict[nt], vector_dict[nt], self.node_encoder.weight, ori3, self.dim)
-                       for nt in graph.node_types}
+                       for nt in node_types}
         bf = self.basis_fn
         fiber = self.fiber_basis()
         kernel_basis_dict, fiber_dict = {}, {}
-        for et in graph.edge_types:
+        for et in live_edge_types:
             src, _, dst = et
-            es = graph.edge_sets[et]
-            kernel_basis_dict[et] = ops.EdgeBasisFn.apply(graph[src].pos, graph[dst].pos, bf[1].weight, bf[1].bias,
+            es = edge_sets[et]
+            kernel_basis_dict[et] = ops.EdgeBasisFn.apply(pos[src], pos[dst], bf[1].weight, bf[1].bias,
                                                           bf[3].weight, bf[3].bias, ori3, self.dim, es)
             fiber_dict[et] = fiber
         for i in range(self.num_messages):
             processor = self.processor if self.shared_processor else self.processor[i]
             latent_dict = processor(latent_dict=latent_dict, edge_index_dict=graph.edge_index_dict,
                                     edge_attr_dict=kernel_basis_dict, fiber_attr_dict=fiber_dict,
-                                    edge_set_dict=graph.edge_sets)
+                                    edge_set_dict=edge_sets)
         latent = latent_dict[graph.output_mask_key]
         return equivariant_readout(latent, self.decoder, self.ori_grid, self.output_dim, self.output_dim_vec, self.dim)
 

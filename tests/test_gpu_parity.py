@@ -165,15 +165,17 @@ def test_policy_body_matches_oracle(cfg_name, B):
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("bf16", 4e-3)])
-def test_empn_pruned_rows_equal_dense_evaluation(precision, tol):
-    """PonitaGCN.prune_dead_rows (drop edge-less padded nodes, last layer at the output nodes only) changes neither
-    the outputs nor any parameter gradient: compared with the dense evaluation of all B*n rows by the same kernels.
-    fp32: only the grouping of the weight-gradient partial sums differs.  bf16: the fp16 gradient scale of the last
-    layer is taken from fewer (but all non-zero) rows and basis-gradient rows are rounded in a different order."""
+@pytest.mark.parametrize("cfg_name,B", [("rigid_pushing_multi_empn_trpl_cfg", 72), ("rigid_insertion_multi_hepi_trpl_cfg", 56),
+                                        ("rope_shaping_hepi_trpl_cfg", 10)])
+def test_pruned_rows_equal_dense_evaluation(cfg_name, B, precision, tol):
+    """`prune_dead_rows` (EMPN: drop edge-less padded nodes, last layer at the output nodes only; HEPi: drop edge-less
+    nodes outside the output type, e.g. padded object points and isolated target nodes) changes neither the outputs
+    nor any parameter gradient: compared with the dense evaluation of all padded rows by the same kernels.
+    fp32: only the grouping of the weight-gradient partial sums differs.  bf16: the fp16 gradient scales are taken
+    from fewer (but all non-zero) rows and basis-gradient rows are rounded in a different order."""
     from geometry_rl_b200 import ops
-    cfg = CONFIGS["rigid_pushing_multi_empn_trpl_cfg"]
+    cfg = CONFIGS[cfg_name]
     gen = torch.Generator().manual_seed(21)
-    B = 72
     obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
     torch.manual_seed(5)
     net = G.make_policy_body(cfg)
@@ -184,10 +186,16 @@ def test_empn_pruned_rows_equal_dense_evaluation(precision, tol):
     net.eval()
     data = G.make_data(cfg, policy=True)
     graph, u = data.build_data(*G.obs_args(cfg, obs, policy=True), train=False)
-    pr = graph.homogeneous_pruned()
-    n_valid = obs["infos"][:, 0].long()  # object_num_points
-    assert pr.es.n_src == int(n_valid.sum()) + B < graph.num_nodes  # valid points + one gripper per graph
-    assert pr.sub.n_dst == B and pr.sub.n_edges == int(n_valid.sum())  # TASK edges: every valid point -> the gripper
+    if cfg.model == "empn":
+        pr = graph.homogeneous_pruned()
+        n_valid = obs["infos"][:, 0].long()  # object_num_points
+        assert pr.es.n_src == int(n_valid.sum()) + B < graph.num_nodes  # valid points + one gripper per graph
+        assert pr.sub.n_dst == B and pr.sub.n_edges == int(n_valid.sum())  # TASK edges: every valid point -> the gripper
+    else:
+        pr = graph.hetero_pruned()
+        assert pr.num_nodes < graph.num_nodes
+        if cfg.task == "rope":
+            assert "target_geometry" not in pr.live_ids  # isolated target nodes are not even embedded
     res = {}
     ops.set_precision(precision)
     try:

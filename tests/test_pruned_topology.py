@@ -26,6 +26,61 @@ def _edge_set_cpu(coo, n_nodes):
                        order.to(torch.int32), rowptr(src), so.to(torch.int32))
 
 
+def _edge_set_bipartite_cpu(coo, n_src, n_dst):
+    order = torch.sort(coo[1], stable=True).indices
+    src, dst = coo[0][order], coo[1][order]
+
+    def rowptr(keys, n):
+        rp = torch.zeros(n + 1, dtype=torch.int64)
+        rp[1:] = torch.cumsum(torch.bincount(keys, minlength=n), 0)
+        return rp.to(torch.int32)
+
+    so = torch.sort(src, stable=True).indices
+    return ops.EdgeSet(n_src, n_dst, coo.shape[1], coo, None, rowptr(dst, n_dst), src.to(torch.int32), dst.to(torch.int32),
+                       order.to(torch.int32), rowptr(src, n_src), so.to(torch.int32))
+
+
+def test_hetero_pruned_equals_dense_at_the_output_type():
+    """HEPi schedule on a toy graph: step 0 object->object, step 1 object->gripper; a third node type is isolated."""
+    gen = torch.Generator().manual_seed(3)
+    B, P, A, T = 6, 8, 2, 5
+    internal, task = [], []
+    for g in range(B):
+        nv = int(torch.randint(0, P + 1, (1,), generator=gen))
+        for i in range(nv):
+            for j in torch.randperm(nv, generator=gen)[:3].tolist():
+                if j != i:
+                    internal.append((g * P + j, g * P + i))
+            for a in range(A):
+                task.append((g * P + i, g * A + a))
+    graph = GraphBatch(B, {"obj": P, "grip": A, "target": T}, torch.device("cpu"))
+    graph.output_mask_key = "grip"
+    e_int, e_task = ("obj", "internal", "obj"), ("obj", "task", "grip")
+    graph.edge_types = [e_int, e_task]
+    graph.edge_sets[e_int] = _edge_set_bipartite_cpu(torch.tensor(internal).t().contiguous(), B * P, B * P)
+    graph.edge_sets[e_task] = _edge_set_bipartite_cpu(torch.tensor(task).t().contiguous(), B * P, B * A)
+    pr = graph.hetero_pruned()
+    assert set(pr.live_ids) == {"obj", "grip"} and len(pr.live_ids["grip"]) == B * A
+    assert len(pr.live_ids["obj"]) < B * P
+    x_obj = torch.randn(B * P, 3, generator=gen, dtype=torch.float64)
+    x_grip = torch.randn(B * A, 3, generator=gen, dtype=torch.float64)
+    w_int = torch.randn(len(internal), generator=gen, dtype=torch.float64)
+    w_task = torch.randn(len(task), generator=gen, dtype=torch.float64)
+    es_i, es_t = graph.edge_sets[e_int], graph.edge_sets[e_task]
+    h = _layer(x_obj, x_obj, es_i.edge_src, es_i.edge_dst, w_int)
+    dense = _layer(h, x_grip, es_t.edge_src, es_t.edge_dst, w_task)
+    ci, ct = pr.edge_sets[e_int], pr.edge_sets[e_task]
+    xo = x_obj[pr.live_ids["obj"]]
+    h1 = _layer(xo, xo, ci.edge_src, ci.edge_dst, w_int)
+    pruned = _layer(h1, x_grip[pr.live_ids["grip"]], ct.edge_src, ct.edge_dst, w_task)
+    assert torch.equal(pruned, dense)
+    for es in (ci, ct):  # CSR rows consistent with the renumbered edge lists
+        assert torch.equal((es.rowptr_dst[1:] - es.rowptr_dst[:-1]).long(), torch.bincount(es.edge_dst.long(), minlength=es.n_dst))
+        assert torch.equal((es.rowptr_src[1:] - es.rowptr_src[:-1]).long(), torch.bincount(es.edge_src.long(), minlength=es.n_src))
+        ss = es.edge_src[es.src_eid.long()]
+        assert bool((ss[1:] >= ss[:-1]).all()) and bool((es.edge_dst[1:] >= es.edge_dst[:-1]).all())
+
+
 def _random_batch(B, P, A, gen):
     n_tot = P + A
     coo = []
