@@ -140,6 +140,11 @@ def workload_shape(cfg, actor, batch, dev, precision):
         elif cfg.model == "empn":
             es = graph.homogeneous()
             n, e, rows = es.n_src, es.n_edges, "dense (all padded nodes, every layer)"
+        elif cfg.model == "hepi" and getattr(policy.gnn, "prune_dead_rows", False):
+            pr = graph.hetero_pruned()
+            n, e = pr.num_nodes, sum(es.n_edges for es in pr.edge_sets.values())
+            rows = (f"HEPi rows that reach the readout only: {n} live of {graph.num_nodes} padded nodes, {e} edges (outputs and "
+                    f"gradients identical to the dense evaluation)")
         else:
             n = graph.num_nodes
             e = sum(es.n_edges for es in graph.edge_sets.values())

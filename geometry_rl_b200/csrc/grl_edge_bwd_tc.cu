@@ -42,6 +42,8 @@ struct EdgeBwd2Smem {
   float GX[kTileFloats];        // g_x1 rows gathered by dst, then g_x1 * kern in place
   float XS[kTileFloats];        // x_src rows gathered by src
   int eid[4][kTE], src[4][kTE], dst[4][kTE];  // index ring: slot (t & 3) holds tile t
+  int acc[4][kTE];              // per edge: add to the basis-gradient row already in HBM (1) or overwrite it (0)
+  int lead[4][kTE];             // first edge of the tile with the same source node: its x_src row is staged once and shared
   uint64_t bar[2];
   uint32_t tmem_base;
 };
@@ -56,6 +58,24 @@ __device__ __forceinline__ int node_lower_bound_src(const int32_t* __restrict__ 
     if (2ll * __ldg(rowptr + mid) + mid < target) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+
+// stage_rows_gather for a src-sorted tile: only the first edge of a run of equal sources copies its row (the others read
+// the leader's copy); rows past `cnt` are zero-filled (they meet zero g_x1 rows in the g_kern product, 0 * garbage != 0)
+__device__ __forceinline__ void stage_rows_gather_lead(float* __restrict__ tile, const float* __restrict__ base,
+                                                       const int* __restrict__ idx, const int* __restrict__ lead, int cnt) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = threadIdx.x + kThreads * i;
+    const int row = f >> 4, c4 = f & 15;
+    const int j = row >> 4;
+    float* d = tile + row * kLDT + 4 * c4;
+    if (j < cnt) {
+      if (lead[j] == j) cp_async16(d, base + (size_t)idx[j] * kRow + (row & 15) * kC + 4 * c4);
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const GrlConvDesc d) {
@@ -87,24 +107,40 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
     const int p = p0 + t * kTE + tid;
     return (tid < kTE && t < n_tiles && p < p1) ? __ldg(d.src_eid + p) : -1;
   };
-  auto load_sd = [&](int e, int& es, int& ed) {
-    es = 0; ed = 0;
-    if (e >= 0) { es = __ldg(d.edge_src + e); ed = __ldg(d.edge_dst + e); }
+  // accumulate_grad_basis: 0 = overwrite every row, 1 = add to every row, 2 = add where grad_basis_acc_mask[e] >= 0
+  // (rows a sub layer of the same basis wrote before this launch), overwrite elsewhere
+  const int acc_mode = d.accumulate_grad_basis;
+  auto load_sd = [&](int e, int& es, int& ed, int& ea) {
+    es = 0; ed = 0; ea = acc_mode == 1;
+    if (e >= 0) {
+      es = __ldg(d.edge_src + e);
+      ed = __ldg(d.edge_dst + e);
+      if (acc_mode == 2) ea = __ldg(d.grad_basis_acc_mask + e) >= 0;
+    }
   };
-  auto publish = [&](int slot, int e, int es, int ed) {
-    if (tid < kTE) { s.eid[slot][tid] = e < 0 ? 0 : e; s.src[slot][tid] = es; s.dst[slot][tid] = ed; }
+  auto publish = [&](int slot, int e, int es, int ed, int ea) {
+    if (warp == 0) {  // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row
+      const int prev = __shfl_up_sync(0xffffffffu, es, 1);
+      const bool starts = lane == 0 || lane >= kTE || es != prev;
+      const unsigned heads = __ballot_sync(0xffffffffu, starts);
+      const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
+      if (tid < kTE) {
+        s.eid[slot][tid] = e < 0 ? 0 : e; s.src[slot][tid] = es; s.dst[slot][tid] = ed; s.acc[slot][tid] = ea;
+        s.lead[slot][tid] = ld;
+      }
+    }
   };
-  int e_2, es_2, ed_2;  // tile t+2: complete
-  int e_3;              // tile t+3: eid requested, (src, dst) not yet
+  int e_2, es_2, ed_2, ea_2;  // tile t+2: complete
+  int e_3;                    // tile t+3: eid requested, (src, dst) not yet
   {
-    int e0 = load_eid(0), e1 = load_eid(1), es, ed;
+    int e0 = load_eid(0), e1 = load_eid(1), es, ed, ea;
     e_2 = load_eid(2);
     e_3 = load_eid(3);
-    load_sd(e0, es, ed);
-    publish(0, e0, es, ed);
-    load_sd(e1, es, ed);
-    publish(1, e1, es, ed);
-    load_sd(e_2, es_2, ed_2);
+    load_sd(e0, es, ed, ea);
+    publish(0, e0, es, ed, ea);
+    load_sd(e1, es, ed, ea);
+    publish(1, e1, es, ed, ea);
+    load_sd(e_2, es_2, ed_2, ea_2);
   }
   tc::fence_async_smem();
   tc::tc_fence_before();
@@ -122,8 +158,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
       if (p0 + t * kTE + j < p1) {
         if (which == 0) tc::prefetch_l2(basis + (size_t)s.eid[t & 3][j] * kRow, kRow * 2u);
         else if (which == 1) tc::prefetch_l2(d.grad_x1 + (size_t)s.dst[t & 3][j] * kRow, kRow * 4u);
-        else if (which == 2) tc::prefetch_l2(d.x_src + (size_t)s.src[t & 3][j] * kRow, kRow * 4u);
-        else if (d.accumulate_grad_basis) tc::prefetch_l2(g_basis + (size_t)s.eid[t & 3][j] * kRow, kRow * 2u);
+        else if (which == 2) { if (s.lead[t & 3][j] == j) tc::prefetch_l2(d.x_src + (size_t)s.src[t & 3][j] * kRow, kRow * 4u); }
+        else if (s.acc[t & 3][j]) tc::prefetch_l2(g_basis + (size_t)s.eid[t & 3][j] * kRow, kRow * 2u);
       }
     }
   };
@@ -165,9 +201,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
     const int slot = t & 3;
     const int base = p0 + t * kTE;
     const int cnt = min(kTE, p1 - base);
-    publish((t + 2) & 3, e_2, es_2, ed_2);  // slot (t+2)&3 was last read by tile t-2, two barriers ago
+    publish((t + 2) & 3, e_2, es_2, ed_2, ea_2);  // slot (t+2)&3 was last read by tile t-2, two barriers ago
     e_2 = e_3;
-    load_sd(e_2, es_2, ed_2);               // eid(t+3) was requested one iteration ago
+    load_sd(e_2, es_2, ed_2, ea_2);               // eid(t+3) was requested one iteration ago
     e_3 = load_eid(t + 4);
     __syncthreads();  // everyone is done with tile t-1's buffers; slot (t+1)&3 (published last iteration) is visible
     prefetch_tile(t + 1);
@@ -183,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
       else *reinterpret_cast<uint4*>(dpt) = make_uint4(0u, 0u, 0u, 0u);
     }
     stage_rows_gather(s.GX, d.grad_x1, s.dst[slot], cnt);
-    stage_rows_gather(s.XS, d.x_src, s.src[slot], cnt);
+    stage_rows_gather_lead(s.XS, d.x_src, s.src[slot], s.lead[slot], cnt);
     cp_async_commit();
     cp_async_wait_all();
     tc::fence_async_smem();
@@ -203,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
       float v[16], gkv[16];
       tc::tmem_ld16(lane_addr + c0, v);
       float* gx = s.GX + row * kLDT + c0;
-      const float* xs = s.XS + row * kLDT + c0;
+      const float* xs = s.XS + (16 * s.lead[slot][row >> 4] + (row & 15)) * kLDT + c0;
 #pragma unroll
       for (int e = 0; e < 16; e += 4) {
         const float4 gm = ld4(gx + e), x = ld4(xs + e);
@@ -227,7 +263,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
     first = false;
     // another layer's share of the basis gradient (accumulate mode): requested before the segmented sum, used after the MMA wait
     uint4 og[4];
-    if (d.accumulate_grad_basis && (row >> 4) < cnt) {
+    const bool acc_row = (row >> 4) < cnt && s.acc[slot][row >> 4] != 0;
+    if (acc_row) {
       const uint4* p = reinterpret_cast<const uint4*>(g_basis + (size_t)s.eid[slot][row >> 4] * kRow + (row & 15) * kC + 32 * ch);
 #pragma unroll
       for (int i = 0; i < 4; ++i) og[i] = p[i];
@@ -254,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
         tc::tmem_ld16(lane_addr + 64 + c0, v);
         if (j < cnt) {
           __nv_bfloat16* p = g_basis + (size_t)s.eid[slot][j] * kRow + (row & 15) * kC + c0;
-          if (d.accumulate_grad_basis) {  // add in fp32, round once
+          if (acc_row) {  // add in fp32, round once
             const uint4 o0 = og[2 * i], o1 = og[2 * i + 1];
             const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&o0);
             const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&o1);
@@ -519,6 +556,9 @@ int grl_fbconv_edge_bwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
                   (d->n_edges == 0 || (d->src_eid && d->edge_src && d->edge_dst && d->basis_bf16 && d->grad_basis_bf16)),
               GRL_EINVAL, "grl_fbconv_edge_bwd_tc: null pointer");
   GRL_REQUIRE(d->n_partials_edge > 0, GRL_EINVAL, "grl_fbconv_edge_bwd_tc: n_partials_edge must be > 0");
+  GRL_REQUIRE(d->accumulate_grad_basis >= 0 && d->accumulate_grad_basis <= 2 &&
+                  (d->accumulate_grad_basis != 2 || d->grad_basis_acc_mask), GRL_EINVAL,
+              "grl_fbconv_edge_bwd_tc: accumulate_grad_basis=%d (2 needs grad_basis_acc_mask)", d->accumulate_grad_basis);
   static bool attr2 = false;
   const int smem2 = (int)sizeof(grl::EdgeBwd2Smem);
   if (!attr2) {

@@ -76,5 +76,7 @@ def err_report(name, a, b):
 
 
 def rel(a, b):
+    """max |a - b| / max |b|; NaN / inf anywhere -> inf, so that `rel(...) >= tol` style checks cannot pass on NaNs."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30)
+    r = float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30)
+    return r if r == r and bool(torch.isfinite(a).all()) else float("inf")

@@ -15,7 +15,8 @@ def load_golden(name):
 
 def rel_err(a, b):
     a, b = a.double(), b.double()
-    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    r = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    return r if r == r else float("inf")
 
 
 def oracle_graph_from_obs(cfg, obs, *, policy: bool):

@@ -206,7 +206,15 @@ def test_pruned_rows_equal_dense_evaluation(cfg_name, B, precision, tol):
             if not prune:
                 w_out = torch.randn(out.shape, generator=gen).cuda()
                 w_hid = torch.randn(hidden.shape, generator=gen).cuda()
-            ((out * w_out).sum() + (hidden * w_hid).sum()).backward()
+            loss = (out * w_out).sum() + (hidden * w_hid).sum()
+            # Poison the blocks the caching allocator will hand to the backward's torch.empty buffers (basis gradient,
+            # latent gradients): a row the kernels forget to write, or add to without owning, then shows up as NaN.
+            n_e = sum(es.n_edges for es in graph.edge_sets.values())
+            for numel, dt in ((n_e * 1024, torch.bfloat16), (n_e * 1024, torch.float32), (graph.num_nodes * 1024, torch.float32)):
+                for frac in (1.0, 0.5, 0.25):
+                    junk = torch.full((max(1, int(numel * frac)),), float("nan"), dtype=dt, device="cuda")
+                    del junk
+            loss.backward()
             res[prune] = (out.detach().clone(), hidden.detach().clone(),
                           {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None})
     finally:

@@ -54,7 +54,7 @@ def test_update_step_matches_oracle(cfg_name, proj_type):
     for k in ("loss_objective", "loss_trust_region", "loss_entropy", "loss_critic", "ESS", "kl", "constraint",
               "mean_constraint", "mean_constraint_max", "cov_constraint", "cov_constraint_max", "entropy", "entropy_diff"):
         a, b = float(out[k]), float(ref[k])
-        if abs(a - b) > 1e-5 * abs(b) + 2e-7:
+        if not abs(a - b) <= 1e-5 * abs(b) + 2e-7:
             bad.append(f"{k}: {a} vs {b}")
     gtol = 1e-4 if proj_type == "w2" else 5e-5
     pol = dict(actor.get_submodule("0").module.named_parameters())
@@ -133,7 +133,7 @@ def test_fused_trpl_loss_matches_torch_formulation(proj_type, B, k):
     bad = []
     for key, ix in _lib.LOSS_SCALAR_INDEX.items():
         a, b = float(sc[ix]), float(ref[key])
-        if abs(a - b) > 1e-6 * abs(b) + 1e-7:
+        if not abs(a - b) <= 1e-6 * abs(b) + 1e-7:
             bad.append(f"{key}: {a} vs {b}")
     for key, t in (("loss_objective", l_obj), ("loss_trust_region", l_tr), ("loss_entropy", l_ent)):
         assert float(t) == float(sc[_lib.LOSS_SCALAR_INDEX[key]])
@@ -160,7 +160,7 @@ def test_fused_and_unfused_loss_modules_agree():
                       {k: p.grad.detach().clone() for k, p in actor.named_parameters() if p.grad is not None})
     (o1, g1), (o0, g0) = res[True], res[False]
     assert set(o1) == set(o0)
-    bad = [f"{k}: {o1[k]} vs {o0[k]}" for k in o0 if abs(o1[k] - o0[k]) > 1e-5 * abs(o0[k]) + 2e-7]
+    bad = [f"{k}: {o1[k]} vs {o0[k]}" for k in o0 if not abs(o1[k] - o0[k]) <= 1e-5 * abs(o0[k]) + 2e-7]
     assert set(g1) == set(g0)
     bad += [G.err_report(k, g1[k], g0[k]) for k in g0 if G.rel(g1[k], g0[k]) >= 2e-5]
     assert not bad, "\n".join(bad)
