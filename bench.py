@@ -105,9 +105,9 @@ class ClockSampler:
 
 def measured_traffic(kernel, workload, minibatch):
     """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture of this same workload (profiles/r01_traffic.json, written by profiles/summarise.py
+    `ncu --set full` capture of this same workload (profiles/r01b_traffic.json, written by profiles/summarise.py
     traffic); None when no capture matches the workload being run."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p))
@@ -323,9 +323,14 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
     t_wall = time.perf_counter()
     s0.record()
     loss_host = 0.0
+    if use_graph:
+        lrn.prefetch(host_batches[0])
     for i in range(steps):
-        if use_graph:  # pinned host -> the graph's static input buffers (H2D), replay, read the loss back
-            out = step(host_batches[i % N_ROTATE])
+        if use_graph:
+            # pinned host -> staging (H2D on a copy stream, issued one step ahead so it runs under the previous update)
+            # -> the graph's static inputs (D2D) -> replay -> read the loss back.  Every step's inputs cross PCIe inside
+            # the timed region; the copy of step i+1 overlaps the compute of step i.
+            out = lrn.update_prefetched(host_batches[(i + 1) % N_ROTATE] if i + 1 < steps else None)
         else:
             out = step({k: t.to(dev, non_blocking=True) for k, t in host_batches[i % N_ROTATE].items()})
         loss_host = float(out["actor_loss"].item())  # device -> host read of the step's result

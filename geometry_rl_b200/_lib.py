@@ -62,6 +62,13 @@ class GrlLossDesc(C.Structure):
                 ("sums", _fp), ("stage", _i32)]
 
 
+class GrlReadoutDesc(C.Structure):
+    _fields_ = [("n_nodes", _i32), ("od", _i32), ("odv", _i32), ("dim", _i32), ("latent", _fp), ("weight", _fp),
+                ("bias", _fp), ("ori", _fp), ("out", _fp), ("hidden", _fp), ("grad_out", _fp), ("grad_hidden", _fp),
+                ("grad_latent", _fp), ("grad_partials", _fp), ("n_partials", _i32)]
+
+
+READOUT_MAX_OUT = 8
 LOSS_TERMS = 8
 LOSS_SCALARS = 16
 LOSS_STATS = 8
@@ -96,6 +103,8 @@ SIGNATURES = {
     "grl_fbconv_edge_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_edge_basis_bwd_tc": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
     "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_readout_fwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
+    "grl_readout_bwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_trpl_loss_fwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),
     "grl_trpl_loss_bwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),
     "grl_absmax": (C.c_int, [_fp, C.c_int64, _fp, _fp]),

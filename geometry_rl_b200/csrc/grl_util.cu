@@ -37,13 +37,38 @@ int sm_count() {
   return cached[dev];
 }
 
-// out[i] (+)= sum_p partials[p][i] in fixed p order.
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int64_t n, float* __restrict__ out,
-                                       int accumulate) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < n_partials; ++p) s += partials[(int64_t)p * n + i];
-    out[i] = accumulate ? out[i] + s : s;
+// out[i] (+)= sum_p partials[p][i] in a FIXED order: the partials are split into 8 contiguous segments, each summed
+// sequentially by one thread (4 independent running sums, p = 4 q + r), and the 8 segment sums are added in segment
+// order.  A block covers 32 outputs x 8 segments, so 32 consecutive threads read 128 contiguous bytes and a
+// 296-partial reduction is 10 dependent loads deep instead of 296 (ncu r01b: 40 us for 4096 outputs before).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int n_partials, int64_t n,
+                                                              float* __restrict__ out, int accumulate) {
+  __shared__ float seg_sum[8][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int per = (n_partials + 7) / 8;
+  const int p0 = seg * per, p1 = min(n_partials, p0 + per);
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < n; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < n) {
+      int p = p0;
+      for (; p + 3 < p1; p += 4) {
+        a0 += partials[(int64_t)p * n + i];
+        a1 += partials[(int64_t)(p + 1) * n + i];
+        a2 += partials[(int64_t)(p + 2) * n + i];
+        a3 += partials[(int64_t)(p + 3) * n + i];
+      }
+      for (; p < p1; ++p) a0 += partials[(int64_t)p * n + i];
+    }
+    seg_sum[seg][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (seg == 0 && i < n) {
+      float s = seg_sum[0][lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) s += seg_sum[k][lane];
+      out[i] = accumulate ? out[i] + s : s;
+    }
+    __syncthreads();
   }
 }
 
@@ -81,11 +106,9 @@ int grl_sm_count(void) { return grl::sm_count(); }
 int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,
                         grl_stream_t stream) {
   GRL_REQUIRE(partials && out && n_partials > 0 && n_floats > 0, GRL_EINVAL, "grl_reduce_partials: bad arguments");
-  const int threads = 256;
-  int64_t blocks = (n_floats + threads - 1) / threads;
-  if (blocks > 4 * grl::sm_count()) blocks = 4 * grl::sm_count();
-  grl::reduce_partials_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(partials, n_partials, n_floats, out,
-                                                                                  accumulate);
+  int64_t blocks = (n_floats + 31) / 32;
+  if (blocks > 16 * grl::sm_count()) blocks = 16 * grl::sm_count();
+  grl::reduce_partials_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(partials, n_partials, n_floats, out, accumulate);
   return grl::check_launch("grl_reduce_partials");
 }
 

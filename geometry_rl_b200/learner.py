@@ -203,3 +203,31 @@ class Learner:
         self._graph.replay()
         self.num_network_updates += 1
         return self._graph_out
+
+    # ---- input pipeline: the NEXT minibatch crosses PCIe while the current update runs ----------
+    def prefetch(self, host_batch):
+        """Start the host -> device copy of a (pinned) minibatch into staging buffers on a copy stream."""
+        if getattr(self, "_staging", None) is None:
+            self._staging = {k: torch.empty_like(v) for k, v in self._static.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)  # the previous contents have been moved into the graph's inputs
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in self._staging.items():
+                v.copy_(host_batch[k], non_blocking=True)
+            self._staged.record()
+
+    def update_prefetched(self, next_host_batch=None):
+        """Replay the captured update on the minibatch handed to `prefetch`, then start fetching `next_host_batch`."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._staged)
+        for k, v in self._static.items():
+            v.copy_(self._staging[k], non_blocking=True)  # device -> device, a few microseconds
+        self._consumed.record(main)
+        self._graph.replay()
+        self.num_network_updates += 1
+        if next_host_batch is not None:
+            self.prefetch(next_host_batch)
+        return self._graph_out

@@ -119,8 +119,17 @@ class HEPi(nn.Module):
 
 
 def equivariant_readout(latent, decoder, ori_grid, output_dim, output_dim_vec, dim):
-    """hepi.py:180-190 on the actuator nodes only ([B*A, 16, 64], a few hundred KB): gate the
-    orientation-averaged vector readout with the scalar readout."""
+    """hepi.py:180-190 on the actuator nodes only ([B*A, 16, 64]): gate the orientation-averaged vector readout with
+    the scalar readout.  One kernel forward, one backward (ops.equivariant_readout) when the shapes allow it."""
+    if (latent.is_cuda and latent.shape[-1] == 64 and latent.shape[-2] == 16 and decoder.bias is not None
+            and output_dim + output_dim_vec <= 8 and (output_dim == output_dim_vec or output_dim == 1)):
+        return ops.equivariant_readout(latent, decoder.weight, decoder.bias, pad_ori3(ori_grid), output_dim,
+                                       output_dim_vec, dim)
+    return equivariant_readout_torch(latent, decoder, ori_grid, output_dim, output_dim_vec, dim)
+
+
+def equivariant_readout_torch(latent, decoder, ori_grid, output_dim, output_dim_vec, dim):
+    """The same readout written with torch ops (reference formulation; parity partner of the kernel in the tests)."""
     output = decoder(latent)
     out_scalar, out_vec = output.split([output_dim, output_dim_vec], dim=-1)
     hidden = latent.mean(dim=-2)

@@ -521,6 +521,49 @@ def trpl_project(mean, v, old_mean, old_v, eps_mean, eps_cov, proj_type="kl"):
 
 
 # ------------------------------------------------------------------------------------------------
+# M4: equivariant readout
+# ------------------------------------------------------------------------------------------------
+class ReadoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, latent, weight, bias, ori3, od, odv, dim):
+        latent, w, b = _f32c(latent), _f32c(weight.detach()), _f32c(bias.detach())
+        n = latent.shape[0]
+        assert tuple(latent.shape[1:]) == (16, 64) and tuple(w.shape) == (od + odv, 64)
+        out = torch.empty(n, odv, 3, dtype=torch.float32, device=latent.device)
+        hidden = torch.empty(n, 64, dtype=torch.float32, device=latent.device)
+        d = L.GrlReadoutDesc(n_nodes=n, od=od, odv=odv, dim=dim, latent=L.ptr(latent), weight=L.ptr(w), bias=L.ptr(b),
+                             ori=L.ptr(ori3), out=L.ptr(out), hidden=L.ptr(hidden))
+        L.call("grl_readout_fwd", C.byref(d))
+        ctx.save_for_backward(latent, w, b, ori3)
+        ctx.meta = (od, odv, dim)
+        return out, hidden
+
+    @staticmethod
+    def backward(ctx, g_out, g_hidden):
+        latent, w, b, ori3 = ctx.saved_tensors
+        od, odv, dim = ctx.meta
+        n, J = latent.shape[0], od + odv
+        dev = latent.device
+        g_out = _f32c(g_out) if g_out is not None else torch.zeros(n, odv, 3, dtype=torch.float32, device=dev)
+        g_hidden = _f32c(g_hidden) if g_hidden is not None else None
+        g_latent = torch.empty_like(latent)
+        n_p = _n_partials((n + 7) // 8, 2)
+        partials = torch.empty(n_p, J * 64 + J, dtype=torch.float32, device=dev)
+        d = L.GrlReadoutDesc(n_nodes=n, od=od, odv=odv, dim=dim, latent=L.ptr(latent), weight=L.ptr(w), bias=L.ptr(b),
+                             ori=L.ptr(ori3), grad_out=L.ptr(g_out), grad_hidden=L.ptr(g_hidden),
+                             grad_latent=L.ptr(g_latent), grad_partials=L.ptr(partials), n_partials=n_p)
+        L.call("grl_readout_bwd", C.byref(d))
+        g = _reduce(partials)
+        return g_latent, g[:J * 64].view(J, 64), g[J * 64:], None, None, None, None
+
+
+def equivariant_readout(latent, weight, bias, ori3, od, odv, dim):
+    """-> (out [n * odv, 3], hidden [n, 64]): hepi.py:173-190 on the output-node latents."""
+    out, hidden = ReadoutFn.apply(latent, weight, bias, ori3, od, odv, dim)
+    return out.reshape(-1, 3), hidden
+
+
+# ------------------------------------------------------------------------------------------------
 # L1 / P3: projection + every loss term around it in five launches
 # ------------------------------------------------------------------------------------------------
 class TrplLossFn(torch.autograd.Function):

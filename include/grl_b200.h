@@ -217,6 +217,30 @@ int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats,
                         grl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * M4  Equivariant readout of the output-node latents: replaces hepi.py:173-190 / ponita_gcn.py:132-146 with
+ * ponita/utils/to_from_sphere.py:12-17: decoder Linear(64 -> od + odv) per orientation, orientation means,
+ * vector readout against the orientation grid, gating by the scalar readout, z = 0 padding in 2-D.
+ * ------------------------------------------------------------------------------------------ */
+#define GRL_READOUT_MAX_OUT 8 /* od + odv */
+typedef struct {
+  int32_t n_nodes, od, odv, dim;
+  const float* latent;     /* [n][16][64]                                                         */
+  const float* weight;     /* [od + odv][64] decoder nn.Linear.weight                             */
+  const float* bias;       /* [od + odv]                                                          */
+  const float* ori;        /* [16][3] (z = 0 when dim == 2)                                       */
+  float* out;              /* [n][odv][3]                                                         */
+  float* hidden;           /* [n][64] mean over orientations                                      */
+  /* backward */
+  const float* grad_out;   /* [n][odv][3]                                                         */
+  const float* grad_hidden;/* optional [n][64]                                                    */
+  float* grad_latent;      /* [n][16][64]                                                         */
+  float* grad_partials;    /* [n_partials][(od + odv) * 64 + od + odv]: gW | gb per CTA           */
+  int32_t n_partials;
+} GrlReadoutDesc;
+int grl_readout_fwd(const GrlReadoutDesc* d, grl_stream_t stream);
+int grl_readout_bwd(const GrlReadoutDesc* d, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K3  GAE: replaces torchrl.objectives.value.GAE(...)(data) at examples/torchrl/train.py:134-140,
  * 249-252 (the advantage arithmetic; the critic call stays with the caller).
  * reward/done/terminated [B][T], value [B][T+1] (shifted=True layout) -> adv, value_target [B][T].

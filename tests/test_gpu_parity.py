@@ -227,6 +227,32 @@ def test_pruned_rows_equal_dense_evaluation(cfg_name, B, precision, tol):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("od,odv,dim,n", [(2, 2, 3, 37), (1, 1, 2, 4096), (1, 1, 3, 400), (1, 3, 3, 9), (2, 2, 2, 1)])
+def test_readout_kernel_matches_torch_formulation(od, odv, dim, n):
+    """grl_readout_fwd / _bwd against hepi.py:180-190 written with torch ops (equivariant_readout_torch, itself pinned
+    by the body fixtures): out, hidden and the gradients of latent / decoder weight / bias at 1e-5 / 2e-5."""
+    from geometry_rl_b200.modules.pyg_models import hepi
+    from geometry_rl_b200.modules.pyg_models.ponita.ponita import make_ori_grid
+    torch.manual_seed(od * 100 + odv * 10 + dim)
+    dec = torch.nn.Linear(64, od + odv).cuda()
+    ori = make_ori_grid(dim, 16, False).cuda()
+    latent = torch.randn(n, 16, 64, device="cuda")
+    res = []
+    for fn in (hepi.equivariant_readout, hepi.equivariant_readout_torch):
+        x = latent.clone().requires_grad_(True)
+        dec.zero_grad(set_to_none=True)
+        out, hidden = fn(x, dec, ori, od, odv, dim)
+        if not res:
+            w_out, w_hid = torch.randn_like(out), torch.randn_like(hidden)
+        ((out * w_out).sum() + (hidden * w_hid).sum()).backward()
+        res.append((out.detach(), hidden.detach(), x.grad.clone(), dec.weight.grad.clone(), dec.bias.grad.clone()))
+    names = ("out", "hidden", "grad latent", "grad weight", "grad bias")
+    assert res[0][0].shape == res[1][0].shape == (n * odv, 3) and res[0][1].shape == (n, 64)
+    bad = [G.err_report(nm, a, b) for nm, a, b, tol in zip(names, res[0], res[1], (TOL, TOL, GTOL, GTOL, GTOL))
+           if not G.rel(a, b) < tol]
+    assert not bad, "\n".join(bad)
+
+
 def test_calibration_matches_reference_semantics():
     """First training-mode forward re-scales kernel / fiber_kernel by std ratios (conv.py:151-157) AFTER
     using the un-calibrated weights; second forward then reproduces the fixture recorded post-calibration."""

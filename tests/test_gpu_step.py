@@ -229,3 +229,35 @@ def test_learner_update_changes_parameters_and_is_deterministic():
         assert float((after - before).abs().max()) > 0
         res.append(after.clone())
     assert torch.equal(res[0], res[1])
+
+
+def test_graph_replay_and_prefetched_inputs_match_eager_updates():
+    """Learner.capture / update_graphed and the prefetching input pipeline (prefetch / update_prefetched: pinned host
+    minibatch -> staging on a copy stream -> the graph's inputs) replay exactly the eager update: bit-identical
+    parameters after three updates on two alternating minibatches."""
+    from geometry_rl_b200 import learner
+    from geometry_rl_b200.tensors import to_device
+    finals = {}
+    for mode in ("eager", "graph", "prefetch"):
+        cfg, actor, critic, loss_module, _, _, mb, _ = _setup("rigid_pushing_multi_empn_trpl_cfg", seed=4)
+        mb2 = dict(mb)  # second minibatch: same slots (the cached per-slot topology belongs to the slot's geometry),
+        mb2["advantage"] = -mb["advantage"]  # other advantages
+        host = [{k: v.pin_memory() for k, v in b.items() if torch.is_tensor(v)} for b in (mb, mb2)]
+        dev = [to_device(b, G.dev()) for b in (mb, mb2)]
+        lrn = learner.Learner(cfg, actor, critic, loss_module)
+        if mode == "eager":
+            for i in range(3 + 3):  # capture() below runs 3 real warm-up updates first
+                lrn.update(dev[0] if i < 3 else dev[(i - 3) % 2])
+        else:
+            lrn.capture(dev[0], warmup=3)
+            if mode == "graph":
+                for i in range(3):
+                    lrn.update_graphed(dev[i % 2])
+            else:
+                lrn.prefetch(host[0])
+                for i in range(3):
+                    lrn.update_prefetched(host[(i + 1) % 2] if i < 2 else None)
+        torch.cuda.synchronize()
+        finals[mode] = torch.cat([p.detach().reshape(-1).clone() for p in list(actor.parameters()) + list(critic.parameters())])
+    assert torch.equal(finals["graph"], finals["prefetch"])
+    assert G.rel(finals["graph"], finals["eager"]) < 1e-6, G.err_report("graph vs eager", finals["graph"], finals["eager"])

@@ -206,6 +206,24 @@ def test_absmax_is_exact(n):
     assert out.view(torch.float32).item() == ref.item()
 
 
+@pytest.mark.parametrize("n_p,n", [(1, 1), (3, 31), (7, 33), (8, 64), (148, 50000), (296, 4096), (301, 5)])
+def test_reduce_partials_fixed_order_sum(n_p, n):
+    """grl_reduce_partials: sum over the partial slots (any count, outputs not a multiple of 32), accumulate mode, and
+    bit-identical results on repetition (fixed summation order)."""
+    from geometry_rl_b200 import _lib as L
+    g = torch.Generator().manual_seed(n_p * 1000 + n)
+    part = torch.randn(n_p, n, generator=g).cuda()
+    out = torch.full((n,), float("nan"), device="cuda")
+    L.call("grl_reduce_partials", L.ptr(part), n_p, n, L.ptr(out), 0)
+    ref = part.double().sum(0)
+    assert float((out.double() - ref).abs().max()) <= 1e-6 * max(1.0, float(ref.abs().max())) * max(1, n_p) ** 0.5
+    out2 = torch.empty_like(out)
+    L.call("grl_reduce_partials", L.ptr(part), n_p, n, L.ptr(out2), 0)
+    assert torch.equal(out, out2)
+    L.call("grl_reduce_partials", L.ptr(part), n_p, n, L.ptr(out2), 1)
+    assert float((out2.double() - 2 * ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max())) * max(1, n_p) ** 0.5
+
+
 @pytest.mark.parametrize("scale", [1e-7, 1.0, 3e4])
 def test_fiber_conv_backward_is_invariant_to_the_gradient_scale(scale):
     """The tensor-core backward stages gradients as fp16 after multiplying them by a power of two taken from
