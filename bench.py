@@ -59,7 +59,7 @@ def parse():
 # helpers
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -136,7 +136,7 @@ def workload_shape(cfg, actor, batch, dev, precision):
             n, e = pr.es.n_src, pr.es.n_edges
             rows = (f"EMPN rows that reach the readout only: {n} live of {graph.num_nodes} padded nodes, {e} edges; last layer at "
                     f"{pr.sub.n_dst} output nodes over {pr.sub.n_edges} edges (outputs and gradients identical to the dense "
-                    f"evaluation, tests/test_gpu_parity.py::test_empn_pruned_rows_equal_dense_evaluation)")
+                    f"evaluation, tests/test_gpu_parity.py::test_pruned_rows_equal_dense_evaluation)")
         elif cfg.model == "empn":
             es = graph.homogeneous()
             n, e, rows = es.n_src, es.n_edges, "dense (all padded nodes, every layer)"
