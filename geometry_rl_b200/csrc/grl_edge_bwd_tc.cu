@@ -45,8 +45,16 @@ struct EdgeBwd2Smem {
   int acc[4][kTE];              // per edge: add to the basis-gradient row already in HBM (1) or overwrite it (0)
   int lead[4][kTE];             // first edge of the tile with the same source node: its x_src row is staged once and shared
   uint64_t bar[2];
+  uint64_t bar_g;               // transaction barrier of the bulk row gathers (GX, XS)
   uint32_t tmem_base;
 };
+
+// The fp32 row gathers (g_x1 by dst, x_src by src) go through the bulk-copy engine: one `cp.async.bulk` per 256-byte
+// orientation row instead of sixteen 16-byte cp.async per thread, which was 35 % of the kernel's instructions and 40 %
+// of its stall samples (profiles/r01b_full.md).  0 = the cp.async path.
+#ifndef GRL_BULK_GATHER
+#define GRL_BULK_GATHER 1
+#endif
 
 // first node n in [0, n_nodes] with cost(n) = 2 * rowptr[n] + n >= target: a node costs about half an edge (its
 // flush moves 8 KB, an edge ~12 KB plus the MMAs), so ranges are balanced on edges AND nodes (padded / isolated
@@ -87,6 +95,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
   if (tid == 0) {
     tc::mbar_init(&s.bar[0], 1);
     tc::mbar_init(&s.bar[1], 1);
+    tc::mbar_init(&s.bar_g, 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&s.tmem_base, 256);
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
   tc::tc_fence_after();
   const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
   const uint32_t bz = tc::smem_u32(s.BZ), gk = tc::smem_u32(s.GK), wk = tc::smem_u32(s.Wkb);
-  uint32_t par0 = 0, par1 = 0;
+  uint32_t par0 = 0, par1 = 0, par_g = 0;
   bool first = true;
 
   // rows of tile t -> L2 (threads 0..23: 8 edges x {basis, g_x1, x_src}); slot (t & 3) must be visible
@@ -205,6 +214,9 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
     e_2 = e_3;
     load_sd(e_2, es_2, ed_2, ea_2);               // eid(t+3) was requested one iteration ago
     e_3 = load_eid(t + 4);
+#if GRL_BULK_GATHER
+    tc::fence_async_smem();  // this thread's generic-proxy accesses to GX / XS (tile t-1) before the async-proxy rewrites
+#endif
     __syncthreads();  // everyone is done with tile t-1's buffers; slot (t+1)&3 (published last iteration) is visible
     prefetch_tile(t + 1);
     if (tid == 32 && d.grad_x_src_init && cur + 2 < n_hi)  // residual rows of the next few nodes -> L2
@@ -218,10 +230,35 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_bwd_tc2_kernel(const 
       if (j < cnt) cp_async16_any(dpt, basis + (size_t)s.eid[slot][j] * kRow + (r & 15) * kC + 8 * c8);
       else *reinterpret_cast<uint4*>(dpt) = make_uint4(0u, 0u, 0u, 0u);
     }
+#if GRL_BULK_GATHER
+    {
+      // thread r < 128 owns row r of GX (g_x1 by dst), thread 128 + r row r of XS (x_src by src, run leaders only)
+      const int rr = tid & 127, j = rr >> 4, oo = rr & 15;
+      const bool is_x = tid >= 128;
+      float* drow = (is_x ? s.XS : s.GX) + rr * kLDT;
+      if (j < cnt) {
+        if (!is_x) tc::bulk_g2s(drow, d.grad_x1 + (size_t)s.dst[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
+        else if (s.lead[slot][j] == j) tc::bulk_g2s(drow, d.x_src + (size_t)s.src[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
+      } else {  // rows past the end of the list: zeros (they meet zero rows in the products, 0 * garbage != 0)
+#pragma unroll
+        for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid == 0) {
+        int n_lead = 0;
+        for (int jj = 0; jj < cnt; ++jj) n_lead += s.lead[slot][jj] == jj;
+        tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + n_lead) * kO * kC * 4u);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    tc::mbar_wait(&s.bar_g, par_g);
+    par_g ^= 1u;
+#else
     stage_rows_gather(s.GX, d.grad_x1, s.dst[slot], cnt);
     stage_rows_gather_lead(s.XS, d.x_src, s.src[slot], s.lead[slot], cnt);
     cp_async_commit();
     cp_async_wait_all();
+#endif
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
