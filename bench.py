@@ -370,6 +370,27 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
     return res
 
 
+def gae_rate(dev, B, T, iters=50):
+    """grl_gae_scan alone ('GAE reported separately'): frames/s and achieved GB/s at 18 B per frame."""
+    from geometry_rl_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    r, v = torch.randn(B, T, generator=g).to(dev), torch.randn(B, T + 1, generator=g).to(dev)
+    done = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    done[:, -1] = True
+    for _ in range(3):
+        ops.gae(r, v, done, done, 0.99, 0.95)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.gae(r, v, done, done, 0.99, 0.95)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / iters
+    return {"frames_per_s": B * T / sec, "B_env": B, "T": T, "us_per_call": sec * 1e6, "GBps_at_18B_per_frame": 18 * B * T / sec / 1e9,
+            "note": "launch-latency bound at these rollout sizes (one warp per env, Kogge-Stone scan along T)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from geometry_rl_b200 import _lib
@@ -424,6 +445,12 @@ def run_ours(args):
             "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
             "roofline": main_res["roofline"], "cpu_baseline": cpu,
         }
+        try:
+            # BASELINE.json quotes config 2 at 4096 envs x 16 steps; the other configs use their own rollout shape
+            line["gae"] = gae_rate(dev, 4096 if args.config == DEFAULT_CONFIG else cfg.num_envs,
+                                   16 if args.config == DEFAULT_CONFIG else cfg.rollout_len)
+        except Exception as exc:  # reporting only
+            line["gae"] = {"error": str(exc)}
         if other_res is not None:
             line["other_precision"] = {"mlp_precision": other, "dtype": "f32" if other == "fp32" else "bf16",
                                        "value": other_res["value"], "unit": "samples/s", "ms_per_step": other_res["ms_per_step"],

@@ -41,16 +41,24 @@ struct NodeFwd2Smem {
   NodeFwd2Group g[2];
   float b2[kC], bias[kC], lng[kC], lnb[kC];
   uint64_t bar[2][2];
+  uint64_t bar_x[2];         // per group: transaction barrier of the bulk copy that stages its x1 tile
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void stage_x1_dense(float* __restrict__ X1, const float* __restrict__ src, int cnt, int gt) {
+// x1 tile ([cnt <= 8 nodes][16][64] fp32, contiguous in HBM) -> dense X1: ONE bulk copy of cnt * 4 KB issued by the
+// group's first thread (completion counted in bytes on `bar`), rows of missing nodes zero-filled by everybody.
+__device__ __forceinline__ void stage_x1_dense(float* __restrict__ X1, const float* __restrict__ src, int cnt, int gt,
+                                               uint64_t* bar) {
+  if (gt == 0) {
+    tc::mbar_expect_tx(bar, (uint32_t)cnt * kRow * 4u);
+    tc::bulk_g2s(X1, src, (uint32_t)cnt * kRow * 4u, bar);
+  }
+  if (cnt < kTE) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int f = gt + 256 * i;  // float4 index 0..2047 of the [128][64] tile
-    float* d = X1 + 4 * f;
-    if ((f >> 8) < cnt) cp_async16(d, src + 4 * f);
-    else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 8; ++i) {
+      const int f = gt + 256 * i;  // float4 index 0..2047 of the [128][64] tile
+      if ((f >> 8) >= cnt) *reinterpret_cast<float4*>(X1 + 4 * f) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -69,6 +77,8 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
     tc::mbar_init(&s.bar[0][1], 1);
     tc::mbar_init(&s.bar[1][0], 1);
     tc::mbar_init(&s.bar[1][1], 1);
+    tc::mbar_init(&s.bar_x[0], 1);
+    tc::mbar_init(&s.bar_x[1], 1);
     tc::fence_mbar_init();
   }
   if (tid < 32) tc::tmem_alloc(&s.tmem_base, 512);
@@ -95,14 +105,12 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
   const int n_tiles = (d.n_dst + kTE - 1) / kTE;
   const int tile_stride = 2 * gridDim.x;
   int tile = 2 * blockIdx.x + grp;
-  if (tile < n_tiles) {
-    stage_x1_dense(G.u.x.X1, d.x1 + (size_t)tile * kTE * kRow, min(kTE, d.n_dst - tile * kTE), gt);
-    cp_async_commit();
-  }
   tc::fence_async_smem();
   tc::tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // weight images, mbarriers and the TMEM base are visible to everybody
   tc::tc_fence_after();
+  if (tile < n_tiles)
+    stage_x1_dense(G.u.x.X1, d.x1 + (size_t)tile * kTE * kRow, min(kTE, d.n_dst - tile * kTE), gt, &s.bar_x[grp]);
   const uint32_t tmem = s.tmem_base + 256u * grp;
   const uint32_t a1_addr = tc::smem_u32(G.u.A1), a2_addr = tc::smem_u32(G.u.A2);
   const uint32_t w1_addr = tc::smem_u32(s.W1h), w2_addr = tc::smem_u32(s.W2h);
@@ -118,8 +126,8 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
       const int nt = tile + tile_stride;
       if (nt < n_tiles) tc::prefetch_l2(d.x1 + (size_t)nt * kTE * kRow, (uint32_t)min(kTE, d.n_dst - nt * kTE) * kRow * 4u);
     }
-    cp_async_wait_all();
-    tc::group_sync(bar_id, 256);  // X1 of this tile visible to the group
+    tc::mbar_wait(&s.bar_x[grp], parity);  // the bulk copy of this tile's x1 rows has landed
+    tc::group_sync(bar_id, 256);           // (and the zero rows of a partial tile are visible to the group)
 
     // ---- A: fibre convolution + bias -------------------------------------------------------------
     {
@@ -241,8 +249,7 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
     {
       const int nt = tile + tile_stride;
       if (nt < n_tiles) {
-        stage_x1_dense(G.u.x.X1, d.x1 + (size_t)nt * kTE * kRow, min(kTE, d.n_dst - nt * kTE), gt);
-        cp_async_commit();
+        stage_x1_dense(G.u.x.X1, d.x1 + (size_t)nt * kTE * kRow, min(kTE, d.n_dst - nt * kTE), gt, &s.bar_x[grp]);
       }
     }
     // ---- F: out = x_dst + D2 + b2 -------------------------------------------------------------------

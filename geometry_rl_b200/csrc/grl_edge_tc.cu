@@ -150,6 +150,7 @@ struct EdgeFwdTcSmem {
   __nv_bfloat16 Wkb[kC * kC];     // [8 chunks][64 rows c][8 j]
   int src[4][kTE], dst[4][kTE];   // 4-deep index ring: slot (t & 3) holds the edges of tile t
   int brow[4][kTE];               // row of each edge in the basis tensor (= edge position unless d.basis_row is given)
+  uint64_t bar_x[2];              // transaction barriers of the bulk x_src row gathers, one per ring stage
   uint64_t bar;
   uint32_t tmem_base;
 };
@@ -191,6 +192,8 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
   const int o = tid >> 4, cg = tid & 15;  // mapping of the segmented-sum phase
   if (tid == 0) {
     tc::mbar_init(&s.bar, 1);
+    tc::mbar_init(&s.bar_x[0], 1);
+    tc::mbar_init(&s.bar_x[1], 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&s.tmem_base, 64);
@@ -216,7 +219,19 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
   auto stage = [&](int t, int buf) {  // requires index slot (t & 3) to be visible
     const int cnt = min(kTE, p1 - (p0 + t * kTE));
     stage_basis_image(s.BZ[buf], basis, s.brow[t & 3], cnt);
-    stage_rows_gather(s.XS[buf], d.x_src, s.src[t & 3], cnt);
+    // x_src rows through the bulk-copy engine: thread r < 128 requests the 256-byte orientation row r of the tile
+    // (one cp.async.bulk instead of eight 16-byte cp.async per thread); completion is counted in bytes on bar_x[buf]
+    if (tid < kTM) {
+      const int j = tid >> 4, oo = tid & 15;
+      float* drow = s.XS[buf] + tid * kLDT;
+      if (j < cnt) {
+        tc::bulk_g2s(drow, d.x_src + (size_t)s.src[t & 3][j] * kRow + oo * kC, kC * 4u, &s.bar_x[buf]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid == 0) tc::mbar_expect_tx(&s.bar_x[buf], (uint32_t)cnt * kO * kC * 4u);
+    }
   };
   int es_a, ed_a, eb_a, es_b, ed_b, eb_b;  // a: tile t+2 (published in iteration t), b: tile t+3
   load_idx(0, es_a, ed_a, eb_a);
@@ -244,10 +259,12 @@ __global__ void __launch_bounds__(kThreads, 2) fbconv_edge_fwd_tc_kernel(const G
     if (tid < kTE) { s.src[(t + 2) & 3][tid] = es_a; s.dst[(t + 2) & 3][tid] = ed_a; s.brow[(t + 2) & 3][tid] = eb_a; }
     es_a = es_b; ed_a = ed_b; eb_a = eb_b;
     load_idx(t + 4, es_b, ed_b, eb_b);
+    tc::fence_async_smem();  // generic-proxy accesses to XS[buf ^ 1] (tile t-1) before the bulk engine rewrites it
     __syncthreads();  // everyone is done reducing tile t-1: its data buffers (buf ^ 1) may be overwritten
     if (t + 1 < n_tiles) stage(t + 1, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();  // tile t has landed (this thread's copies); the barrier below makes it CTA-wide
+    tc::mbar_wait(&s.bar_x[buf], (uint32_t)(t >> 1) & 1u);  // ... and so have its x_src rows
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
