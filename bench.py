@@ -388,7 +388,7 @@ def gae_rate(dev, B, T, iters=50):
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) * 1e-3 / iters
     return {"frames_per_s": B * T / sec, "B_env": B, "T": T, "us_per_call": sec * 1e6, "GBps_at_18B_per_frame": 18 * B * T / sec / 1e9,
-            "note": "launch-latency bound at these rollout sizes (one warp per env, Kogge-Stone scan along T)"}
+            "note": "host call included (dtype conversions + one launch): launch-latency bound at these rollout sizes; kernel = one warp per env, Kogge-Stone scan along T"}
 
 
 def run_ours(args):

@@ -23,7 +23,7 @@ _i32 = C.c_int32
 class GrlEmbedDesc(C.Structure):
     _fields_ = [("n_nodes", _i32), ("n_scalars", _i32), ("n_vectors", _i32), ("dim", _i32),
                 ("scalars", _fp), ("vectors", _fp), ("ori", _fp), ("weight", _fp), ("x", _fp),
-                ("grad_x", _fp), ("grad_weight_partials", _fp), ("n_partials", _i32)]
+                ("grad_x", _fp), ("grad_weight_partials", _fp), ("n_partials", _i32), ("node_ids", _fp)]
 
 
 class GrlBasisDesc(C.Structure):

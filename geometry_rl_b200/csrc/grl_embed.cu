@@ -13,8 +13,13 @@ constexpr int kEmbTile = 16;  // nodes staged per CTA iteration
 // Stage scalars [T][S] and vectors [T][V][3] of `cnt` consecutive nodes into shared memory (coalesced).
 __device__ __forceinline__ void embed_stage(const GrlEmbedDesc& d, int n0, int cnt, float* __restrict__ sc, float* __restrict__ vc) {
   const int S = d.n_scalars, V3 = 3 * d.n_vectors;
-  for (int i = threadIdx.x; i < cnt * S; i += kThreads) sc[i] = d.scalars[(size_t)n0 * S + i];
-  for (int i = threadIdx.x; i < cnt * V3; i += kThreads) vc[i] = d.vectors[(size_t)n0 * V3 + i];
+  if (d.node_ids == nullptr) {
+    for (int i = threadIdx.x; i < cnt * S; i += kThreads) sc[i] = d.scalars[(size_t)n0 * S + i];
+    for (int i = threadIdx.x; i < cnt * V3; i += kThreads) vc[i] = d.vectors[(size_t)n0 * V3 + i];
+  } else {  // live-row evaluation: node n0 + j of the compact batch is row node_ids[n0 + j] of the padded feature arrays
+    for (int i = threadIdx.x; i < cnt * S; i += kThreads) sc[i] = d.scalars[(size_t)__ldg(d.node_ids + n0 + i / S) * S + i % S];
+    for (int i = threadIdx.x; i < cnt * V3; i += kThreads) vc[i] = d.vectors[(size_t)__ldg(d.node_ids + n0 + i / V3) * V3 + i % V3];
+  }
 }
 
 // Features of (staged node j, orientation o) -> feat[j][o][0..15] in shared memory (entries >= S + V are zero).

@@ -38,6 +38,7 @@ class PrunedHomo:
     `sub` is the bipartite set "live nodes -> output nodes" of the LAST layer, whose result is only read at the
     output nodes (ponita_gcn.py:132-146 slices `output_mask` out of the last latent)."""
     live_ids: torch.Tensor  # [n_live] int64: full (padded) node index of every live node, ascending
+    live_ids32: torch.Tensor  # the same as int32 (GrlEmbedDesc.node_ids)
     es: ops.EdgeSet  # n_src = n_dst = n_live, all E edges, compact node ids
     sub: ops.SubEdgeSet
 
@@ -48,6 +49,7 @@ class PrunedHetero:
     of any type (as source or destination) or belongs to the output node type.  Per node type the renumbering is
     monotone, so every edge set keeps its edge order; node types left without nodes (isolated target nodes) vanish."""
     live_ids: Dict[str, torch.Tensor]  # node type -> [n_live] int64 indices into the padded per-type node order
+    live_ids32: Dict[str, torch.Tensor]  # the same as int32 (GrlEmbedDesc.node_ids)
     edge_sets: Dict[EdgeType, ops.EdgeSet]  # compact node ids; edge types whose endpoints vanished are omitted
     num_nodes: int  # total live nodes
 
@@ -161,7 +163,7 @@ class GraphBatch:
                                   es.eid_coo, rowptr_src, es.src_eid)
             out_ids = new_id[is_out.nonzero().squeeze(1)]
             sub = ops.build_sub_edge_set(compact, out_ids)
-            self._homo_cache["pruned"] = PrunedHomo(live_ids, compact, sub)
+            self._homo_cache["pruned"] = PrunedHomo(live_ids, live_ids.to(torch.int32).contiguous(), compact, sub)
         return self._homo_cache["pruned"]
 
     # -- heterogeneous view without dead rows (HEPi) ---------------------------------------------------
@@ -195,5 +197,7 @@ class GraphBatch:
                     new_id[src][es.edge_src.long()].to(torch.int32).contiguous(),
                     new_id[dst][es.edge_dst.long()].to(torch.int32).contiguous(), es.eid_coo,
                     torch.cat([es.rowptr_src[:-1][live_ids[src]], es.rowptr_src[-1:]]).contiguous(), es.src_eid)
-            self._homo_cache["hetero_pruned"] = PrunedHetero(live_ids, edge_sets, sum(int(v.numel()) for v in live_ids.values()))
+            self._homo_cache["hetero_pruned"] = PrunedHetero(
+                live_ids, {t: v.to(torch.int32).contiguous() for t, v in live_ids.items()}, edge_sets,
+                sum(int(v.numel()) for v in live_ids.values()))
         return self._homo_cache["hetero_pruned"]

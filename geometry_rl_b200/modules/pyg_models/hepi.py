@@ -92,13 +92,14 @@ class HEPi(nn.Module):
             node_types = [nt for nt in node_types if nt in pr.live_ids]
             edge_sets = {et: pr.edge_sets.get(et, graph.edge_sets[et]) for et in graph.edge_types}
             with torch.no_grad():
-                scalar_dict = {nt: scalar_dict[nt][pr.live_ids[nt]] for nt in node_types}
-                vector_dict = {nt: vector_dict[nt][pr.live_ids[nt]] for nt in node_types}
                 pos = {nt: pos[nt][pr.live_ids[nt]] for nt in node_types}
+            node_ids = pr.live_ids32  # the embed kernel reads the padded feature rows in place
             live_edge_types = [et for et in graph.edge_types if et in pr.edge_sets]
         else:
+            node_ids = {}
             live_edge_types = list(graph.edge_types)
-        latent_dict = {nt: ops.EmbedFn.apply(scalar_dict[nt], vector_dict[nt], self.node_encoder.weight, ori3, self.dim)
+        latent_dict = {nt: ops.EmbedFn.apply(scalar_dict[nt], vector_dict[nt], self.node_encoder.weight, ori3, self.dim,
+                                             node_ids.get(nt))
                        for nt in node_types}
         bf = self.basis_fn
         fiber = self.fiber_basis()

@@ -180,15 +180,17 @@ class Ponita(nn.Module):
     def calibration_pending(self) -> bool:
         return self.training and any(not l.conv.is_callibrated() for l in self.interaction_layers)
 
-    def forward(self, scalars, vectors, pos, edge_set: ops.EdgeSet, batch=None, last_sub: Optional[ops.SubEdgeSet] = None):
+    def forward(self, scalars, vectors, pos, edge_set: ops.EdgeSet, batch=None, last_sub: Optional[ops.SubEdgeSet] = None,
+                node_ids: Optional[torch.Tensor] = None):
         """scalars [N,S], vectors [N,3V] (un-lifted), pos [N,3] -> latent [N,16,64]; with `last_sub` the last layer is
-        evaluated at `last_sub.out_ids` only and the result is [len(out_ids),16,64]."""
+        evaluated at `last_sub.out_ids` only and the result is [len(out_ids),16,64].  `node_ids` (int32): scalars / vectors
+        are the PADDED arrays and node n of the (compact) graph is their row node_ids[n]; pos is already compact."""
         ori3 = pad_ori3(self.ori_grid)
         bf = self.basis_fn
         kernel_basis = ops.EdgeBasisFn.apply(pos, pos, bf[1].weight, bf[1].bias, bf[3].weight, bf[3].bias, ori3, self.dim,
                                              edge_set)
         fiber_kernel_basis = self.fiber_basis()
-        x = ops.EmbedFn.apply(scalars, vectors, self.x_embedder.weight, ori3, self.dim)
+        x = ops.EmbedFn.apply(scalars, vectors, self.x_embedder.weight, ori3, self.dim, node_ids)
         n_layers = len(self.interaction_layers)
         for i, layer in enumerate(self.interaction_layers):
             x = layer(x, kernel_basis, fiber_kernel_basis, edge_set, last_sub if i == n_layers - 1 else None)

@@ -49,12 +49,12 @@ class PonitaGCN(torch.nn.Module):
             # the one-time calibration (ponita.py:178-192) takes statistics over ALL rows: that call runs dense
             pruned = graph.homogeneous_pruned() if (self.prune_dead_rows and not self.ponita.calibration_pending()) else None
             if pruned is not None:
-                sc, vc, pos = sc[pruned.live_ids], vc[pruned.live_ids], pos[pruned.live_ids]
+                pos = pos[pruned.live_ids]  # the embed kernel reads sc / vc rows in place through live_ids32
             else:
                 edge_set = graph.homogeneous()
         if pruned is not None:
             # [B*A, 16, 64]: rows of the output nodes, graph-major like the masked slice below
-            latent = self.ponita(sc, vc, pos, pruned.es, last_sub=pruned.sub)
+            latent = self.ponita(sc, vc, pos, pruned.es, last_sub=pruned.sub, node_ids=pruned.live_ids32)
         else:
             hidden = self.ponita(sc, vc, pos, edge_set)  # [B*n, 16, 64]
             # ponita_gcn.py:132-146 reads out every node and then masks; reading out the masked nodes is the same

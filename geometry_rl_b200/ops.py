@@ -203,17 +203,18 @@ def _n_partials(n_units: int, per_sm: int = 1) -> int:
 # ------------------------------------------------------------------------------------------------
 class EmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scalars, vectors, weight, ori3, dim):
+    def forward(ctx, scalars, vectors, weight, ori3, dim, node_ids=None):
+        """`node_ids` (int32 [N]): embed rows node_ids[n] of the (padded) feature arrays as node n of a compact batch."""
         scalars, vectors, weight = _f32c(scalars), _f32c(vectors), _f32c(weight)
-        N, S = scalars.shape
+        N, S = (scalars.shape[0] if node_ids is None else int(node_ids.numel())), scalars.shape[1]
         V = vectors.shape[1] // 3
         assert weight.shape == (64, S + V), f"node encoder weight {tuple(weight.shape)} vs S+V={S + V}"
         x = torch.empty(N, 16, 64, dtype=torch.float32, device=scalars.device)
         d = L.GrlEmbedDesc(n_nodes=N, n_scalars=S, n_vectors=V, dim=dim, scalars=L.ptr(scalars), vectors=L.ptr(vectors),
-                           ori=L.ptr(ori3), weight=L.ptr(weight), x=L.ptr(x))
+                           ori=L.ptr(ori3), weight=L.ptr(weight), x=L.ptr(x), node_ids=L.ptr(node_ids))
         L.call("grl_embed_fwd", C.byref(d))
         ctx.save_for_backward(scalars, vectors, ori3)
-        ctx.meta = (N, S, V, dim)
+        ctx.meta, ctx.node_ids = (N, S, V, dim), node_ids
         return x
 
     @staticmethod
@@ -224,9 +225,10 @@ class EmbedFn(torch.autograd.Function):
         n_p = _n_partials((N + 15) // 16, 2)
         partials = torch.empty(n_p, 64 * (S + V), dtype=torch.float32, device=gx.device)
         d = L.GrlEmbedDesc(n_nodes=N, n_scalars=S, n_vectors=V, dim=dim, scalars=L.ptr(scalars), vectors=L.ptr(vectors),
-                           ori=L.ptr(ori3), grad_x=L.ptr(gx), grad_weight_partials=L.ptr(partials), n_partials=n_p)
+                           ori=L.ptr(ori3), grad_x=L.ptr(gx), grad_weight_partials=L.ptr(partials), n_partials=n_p,
+                           node_ids=L.ptr(ctx.node_ids))
         L.call("grl_embed_bwd", C.byref(d))
-        return None, None, _reduce(partials).view(64, S + V), None, None
+        return None, None, _reduce(partials).view(64, S + V), None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -105,6 +105,8 @@ typedef struct {
   const float* grad_x;                         /* [N][16][64]                                   */
   float* grad_weight_partials;                 /* [n_partials][64][S+V]                         */
   int32_t n_partials;
+  const int32_t* node_ids;                     /* optional [N]: row of node n in scalars / vectors (NULL = n); lets a
+                                                  compacted batch read the padded feature arrays in place      */
 } GrlEmbedDesc;
 int grl_embed_fwd(const GrlEmbedDesc* d, grl_stream_t stream);
 int grl_embed_bwd(const GrlEmbedDesc* d, grl_stream_t stream);
