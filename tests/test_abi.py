@@ -77,3 +77,24 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_loss_scalar_indices_match_the_header_enum(lib):
+    """_lib.LOSS_SCALAR_INDEX (used by TRPLLoss to pick scalars out of grl_trpl_loss_fwd's output) mirrors the
+    GRL_LS_* enum of include/grl_b200.h, and the size macros agree."""
+    src = open(HEADER).read()
+    body = re.search(r"enum\s*\{(.*?)\};", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip().split("=")[0].strip() for n in body.split(",") if n.strip()]
+    assert names[0] == "GRL_LS_LOSS_OBJECTIVE"
+    header_index = {n[len("GRL_LS_"):].lower(): i for i, n in enumerate(names)}
+    mine = {k.lower(): v for k, v in lib.LOSS_SCALAR_INDEX.items()}
+    assert mine == header_index
+
+    def macro(name):
+        return int(re.search(rf"#define\s+{name}\s+(\d+)", src).group(1))
+
+    assert macro("GRL_LOSS_TERMS") == lib.LOSS_TERMS and macro("GRL_LOSS_SCALARS") == lib.LOSS_SCALARS
+    assert macro("GRL_LOSS_STATS") == lib.LOSS_STATS and macro("GRL_LOSS_SUMS") == lib.LOSS_SUMS
+    assert macro("GRL_READOUT_MAX_OUT") == lib.READOUT_MAX_OUT
+    assert len(names) <= lib.LOSS_SCALARS
