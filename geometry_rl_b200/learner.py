@@ -204,23 +204,6 @@ class Learner:
         self.num_network_updates += 1
         return self._graph_out
 
-    # ---- epoch loop over a device-resident rollout buffer (train.py:258-316) ---------------------
-    def fit(self, buffer, epochs: int):
-        """`epochs` passes over a `rollout.DeviceRolloutBuffer`.  After `capture`, full-size minibatches are gathered
-        straight into the graph's static inputs and replayed; a short tail chunk runs as an eager update."""
-        from .rollout import run_minibatch_epochs
-        if self._graph is None:
-            return run_minibatch_epochs(self.update, buffer, epochs)
-
-        def step(mb):
-            if mb is not self._static:
-                return self.update(mb)
-            self._graph.replay()
-            self.num_network_updates += 1
-            return self._graph_out
-
-        return run_minibatch_epochs(step, buffer, epochs, self._static)
-
     # ---- input pipeline: the NEXT minibatch crosses PCIe while the current update runs (SURVEY 8(f) N3) ----------
     def prefetch(self, host_batch):
         """Start the host -> device copy of a (pinned) minibatch into staging buffers on a copy stream."""

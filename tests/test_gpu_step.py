@@ -261,3 +261,4 @@ def test_graph_replay_and_prefetched_inputs_match_eager_updates():
         finals[mode] = torch.cat([p.detach().reshape(-1).clone() for p in list(actor.parameters()) + list(critic.parameters())])
     assert torch.equal(finals["graph"], finals["prefetch"])
     assert G.rel(finals["graph"], finals["eager"]) < 1e-6, G.err_report("graph vs eager", finals["graph"], finals["eager"])
+
