@@ -15,6 +15,7 @@ GRL_OK = 0
 BASIS_GRAD_FLOATS = 64 * 16 + 64 + 64 * 64 + 64
 NODE_GRAD_FLOATS = 256 * 64 + 256 + 64 * 256 + 64 + 64 + 64 + 64 + 16 * 16 * 64
 EDGE_GRAD_FLOATS = 64 * 64
+FUSED_EDGE_GRAD_FLOATS = 64 * 64 + 64 * 16 + 64 * 64 + 64
 
 _fp = C.c_void_p
 _i32 = C.c_int32
@@ -44,6 +45,13 @@ class GrlConvDesc(C.Structure):
                 ("n_partials_node", _i32), ("edge_grad_partials", _fp), ("n_partials_edge", _i32), ("w2", _fp),
                 ("basis_bf16", _fp), ("grad_basis_bf16", _fp), ("grad_x2", _fp), ("x2", _fp), ("grad_amax", _fp),
                 ("basis_row", _fp), ("grad_basis_acc_mask", _fp)]
+
+
+class GrlFusedEdgeDesc(C.Structure):
+    _fields_ = [("n_key", _i32), ("n_edges", _i32), ("dim", _i32), ("n_partials", _i32),
+                ("rowptr", _fp), ("e_src", _fp), ("e_dst", _fp), ("pos_src", _fp), ("pos_dst", _fp), ("ori", _fp),
+                ("w1", _fp), ("b1", _fp), ("w2", _fp), ("b2", _fp), ("wk", _fp), ("x_src", _fp), ("x1", _fp),
+                ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp), ("grad_partials", _fp)]
 
 
 class GrlProjDesc(C.Structure):
@@ -103,6 +111,8 @@ SIGNATURES = {
     "grl_fbconv_edge_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_edge_basis_bwd_tc": (C.c_int, [C.POINTER(GrlBasisDesc), _fp]),
     "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
+    "grl_fbconv_edge_fused_fwd": (C.c_int, [C.POINTER(GrlFusedEdgeDesc), _fp]),
+    "grl_fbconv_edge_fused_bwd": (C.c_int, [C.POINTER(GrlFusedEdgeDesc), _fp]),
     "grl_readout_fwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_readout_bwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_trpl_loss_fwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),

@@ -193,12 +193,8 @@ int grl_edge_basis_fwd(const GrlBasisDesc* d, grl_stream_t stream) {
               d->n_edges, d->dim);
   GRL_REQUIRE(d->edge_src && d->edge_dst && d->pos_src && d->pos_dst && d->ori && d->w1t && d->b1 && d->w2t && d->b2 &&
                   d->basis, GRL_EINVAL, "grl_edge_basis_fwd: null pointer");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::BasisSmemFwd);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::edge_basis_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_basis_fwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   const int grid = grl::basis_grid(d->n_edges, 3 * grl::sm_count());
   grl::edge_basis_fwd_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_edge_basis_fwd");
@@ -211,12 +207,8 @@ int grl_edge_basis_bwd(const GrlBasisDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d->edge_src && d->edge_dst && d->pos_src && d->pos_dst && d->ori && d->w1t && d->b1 && d->w2t && d->b2 &&
                   d->w2 && d->grad_basis && d->grad_partials, GRL_EINVAL, "grl_edge_basis_bwd: null pointer");
   GRL_REQUIRE(d->n_partials > 0, GRL_EINVAL, "grl_edge_basis_bwd: n_partials must be > 0");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::BasisSmemBwd);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::edge_basis_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_basis_bwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   // every partial slot is written exactly once -> the grid IS the number of partial slots
   grl::edge_basis_bwd_kernel<<<d->n_partials, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_edge_basis_bwd");

@@ -185,12 +185,8 @@ int grl_fbconv_edge_fwd(const GrlConvDesc* d, grl_stream_t stream) {
               d->n_src, d->n_dst, d->n_edges);
   GRL_REQUIRE(d->rowptr_dst && d->x_src && d->wk_t && d->x1 && (d->n_edges == 0 || (d->edge_src && d->edge_dst && d->basis)),
               GRL_EINVAL, "grl_fbconv_edge_fwd: null pointer");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::EdgeFwdSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::fbconv_edge_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_edge_fwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   const int n_blocks = (d->n_dst + grl::kNodesPerBlock - 1) / grl::kNodesPerBlock;
   int grid = 2 * grl::sm_count();
   if (grid > n_blocks) grid = n_blocks;
@@ -205,12 +201,8 @@ int grl_fbconv_edge_bwd(const GrlConvDesc* d, grl_stream_t stream) {
                   (d->n_edges == 0 || (d->src_eid && d->edge_src && d->edge_dst && d->basis && d->grad_basis)),
               GRL_EINVAL, "grl_fbconv_edge_bwd: null pointer");
   GRL_REQUIRE(d->n_partials_edge > 0, GRL_EINVAL, "grl_fbconv_edge_bwd: n_partials_edge must be > 0");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::EdgeBwdSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::fbconv_edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_edge_bwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   grl::fbconv_edge_bwd_kernel<<<d->n_partials_edge, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_edge_bwd");
 }

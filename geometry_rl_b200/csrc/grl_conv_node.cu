@@ -383,12 +383,8 @@ static int check_node_desc(const GrlConvDesc* d, const char* who, bool bwd) {
 int grl_fbconv_node_fwd(const GrlConvDesc* d, grl_stream_t stream) {
   const int rc = check_node_desc(d, "grl_fbconv_node_fwd", false);
   if (rc != GRL_OK) return rc;
-  static bool attr = false;
   const int smem = (int)sizeof(grl::NodeFwdSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::fbconv_node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_fwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   const int n_tiles = (d->n_dst + grl::kTE - 1) / grl::kTE;
   int grid = 2 * grl::sm_count();
   if (grid > n_tiles) grid = n_tiles;
@@ -399,12 +395,8 @@ int grl_fbconv_node_fwd(const GrlConvDesc* d, grl_stream_t stream) {
 int grl_fbconv_node_bwd(const GrlConvDesc* d, grl_stream_t stream) {
   const int rc = check_node_desc(d, "grl_fbconv_node_bwd", true);
   if (rc != GRL_OK) return rc;
-  static bool attr = false;
   const int smem = (int)sizeof(grl::NodeBwdSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::fbconv_node_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   grl::fbconv_node_bwd_kernel<<<d->n_partials_node, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_node_bwd");
 }

@@ -493,22 +493,14 @@ extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream)
               "grl_fbconv_node_bwd_tc: null pointer");
   {
     GRL_REQUIRE(d->x2, GRL_EINVAL, "grl_fbconv_node_bwd_tc: x2 (saved by grl_fbconv_node_fwd_tc) is required");
-    static bool attr = false;
     const int smem = (int)sizeof(grl::NodeBwd2Smem);
-    if (!attr) {
-      cudaFuncSetAttribute(grl::fbconv_node_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr = true;
-    }
+    if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc2_kernel, smem) != GRL_OK) return GRL_ECUDA;
     grl::fbconv_node_bwd_tc2_kernel<<<d->n_partials_node, grl::kNB2Threads, smem, (cudaStream_t)stream>>>(*d);
   }
   int rc = grl::check_launch("grl_fbconv_node_bwd_tc (mlp)");
   if (rc != GRL_OK) return rc;
-  static bool attr2 = false;
   const int smem2 = (int)sizeof(grl::FiberBwdSmem);
-  if (!attr2) {
-    cudaFuncSetAttribute(grl::fbconv_fiber_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    attr2 = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_fiber_bwd_kernel, smem2) != GRL_OK) return GRL_ECUDA;
   grl::fbconv_fiber_bwd_kernel<<<d->n_partials_node, grl::kFiberThreads, smem2, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_node_bwd_tc (fibre)");
 }

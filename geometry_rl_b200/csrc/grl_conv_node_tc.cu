@@ -283,13 +283,9 @@ extern "C" int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream)
   GRL_REQUIRE(d->x1 && d->fiber_kernel && d->bias && d->ln_g && d->ln_b && d->w1 && d->b1 && d->w2 && d->b2 && d->x_dst &&
                   d->out, GRL_EINVAL, "grl_fbconv_node_fwd_tc: null pointer");
   const int n_tiles = (d->n_dst + grl::kTE - 1) / grl::kTE;
-  static bool attr2 = false;
   const int smem2 = (int)sizeof(grl::NodeFwd2Smem);
-  if (!attr2) {
-    cudaFuncSetAttribute(grl::fbconv_node_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    cudaFuncSetAttribute(grl::fbconv_node_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    attr2 = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_fwd_tc2_kernel<false>, smem2) != GRL_OK) return GRL_ECUDA;
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_fwd_tc2_kernel<true>, smem2) != GRL_OK) return GRL_ECUDA;
   int grid = grl::sm_count();
   if (2 * grid > n_tiles) grid = (n_tiles + 1) / 2;
   if (d->accumulate_out) grl::fbconv_node_fwd_tc2_kernel<true><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d);

@@ -596,12 +596,8 @@ int grl_fbconv_edge_bwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d->accumulate_grad_basis >= 0 && d->accumulate_grad_basis <= 2 &&
                   (d->accumulate_grad_basis != 2 || d->grad_basis_acc_mask), GRL_EINVAL,
               "grl_fbconv_edge_bwd_tc: accumulate_grad_basis=%d (2 needs grad_basis_acc_mask)", d->accumulate_grad_basis);
-  static bool attr2 = false;
   const int smem2 = (int)sizeof(grl::EdgeBwd2Smem);
-  if (!attr2) {
-    cudaFuncSetAttribute(grl::fbconv_edge_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    attr2 = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_edge_bwd_tc2_kernel, smem2) != GRL_OK) return GRL_ECUDA;
   grl::fbconv_edge_bwd_tc2_kernel<<<d->n_partials_edge, grl::kThreads, smem2, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_fbconv_edge_bwd_tc");
 }
@@ -613,12 +609,8 @@ int grl_edge_basis_bwd_tc(const GrlBasisDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d->edge_src && d->edge_dst && d->pos_src && d->pos_dst && d->ori && d->w1t && d->b1 && d->w2t && d->b2 &&
                   d->grad_basis_bf16 && d->grad_partials, GRL_EINVAL, "grl_edge_basis_bwd_tc: null pointer");
   GRL_REQUIRE(d->n_partials > 0, GRL_EINVAL, "grl_edge_basis_bwd_tc: n_partials must be > 0");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::BasisBwdTcSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::edge_basis_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_basis_bwd_tc_kernel, smem) != GRL_OK) return GRL_ECUDA;
   grl::edge_basis_bwd_tc_kernel<<<d->n_partials, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
   return grl::check_launch("grl_edge_basis_bwd_tc");
 }

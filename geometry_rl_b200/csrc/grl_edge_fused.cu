@@ -1,0 +1,693 @@
+// Fused edge side of the message passing, 16-bit tensor-core path: the edge basis is RECOMPUTED inside the kernels
+// that consume it, so no [E][16][64] basis / basis-gradient tensor ever exists in HBM (SURVEY 8(d) traffic model:
+// "edge basis recomputed on the fly").
+//
+//   forward  (key = dst, entries sorted by dst, CSR order = the reference's scatter order):
+//     F      = 14 polynomial invariants of (i1, i2) per (edge, orientation)          hepi.py:109-123, ponita.py:233-244
+//     basis  = GELU(GELU(F W1^T + b1) W2^T + b2)                                     hepi.py:76-82
+//     kern   = basis Wk^T                                                            ponita/conv.py:84-87
+//     x1[d]  = sum_{e in in(d)} kern[e] * x_src[src(e)]                              ponita/conv.py:116-149
+//   backward (key = src, entries sorted by src): recompute F, H1, basis, kern, then
+//     g_xsrc[s] = init[s] + sum_{e in out(s)} g_x1[dst(e)] * kern[e]
+//     g_kern = g_x1[dst(e)] * x_src[src(e)];  gWk += g_kern^T basis;  g_basis = g_kern Wk
+//     gP2 = g_basis * GELU'(pre2);  gW2 += gP2^T H1;  gb2 += colsum gP2;  gH1 = gP2 W2
+//     gP1 = gH1 * GELU'(pre1);      [gW1 | gb1] += gP1^T [F | 1]
+//
+// A tile is 8 edges x 16 orientations = 128 rows = the 128 TMEM lanes.  All five contractions of a tile run on
+// tcgen05 (16-bit operands produced by the threads straight into the no-swizzle core-matrix layout of grl_tc.cuh,
+// fp32 accumulators in TMEM); invariants, GELU, the message products and the CSR-ordered segmented sums are fp32.
+// Weight gradients stay in TMEM for the whole persistent CTA and leave once, as one partial slot per CTA
+// (summed in fixed order by grl_reduce_partials): deterministic, no atomics.
+//
+// Forward: 256 threads, 74 KB shared memory, 128 TMEM columns -> three CTAs per SM overlap each other's MMA round
+// trips and epilogues.  The x_src rows of a tile are requested through the bulk-copy engine at the START of the tile
+// and land under its two MLP stages.
+// Backward: the live set of a tile (F, H1, basis, one gradient image, the g_x1 and x_src row tiles, three weight images)
+// is 141 KB, so one CTA per SM; it runs 16 warps in lock step, four per TMEM lane quadrant, 16 accumulator columns per
+// thread, which halves every epilogue's critical path.
+#include "grl_common.cuh"
+#include "grl_tc.cuh"
+
+namespace grl {
+
+constexpr int kFusedBwdThreads = 512;
+
+// first key node n in [0, n_nodes] with cost(n) = 8 * rowptr[n] + n >= target (a tile of 8 edges costs a few
+// microseconds of MLP work, a node's flush one 4 KB row)
+__device__ __forceinline__ int fused_lower_bound(const int32_t* __restrict__ rowptr, int n_nodes, long long target) {
+  int lo = 0, hi = n_nodes;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (8ll * __ldg(rowptr + mid) + mid < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// positions of one (edge, orientation) row, loaded one tile ahead
+struct RowPos {
+  float p[6];
+  bool valid;
+  __device__ __forceinline__ void load(const GrlFusedEdgeDesc& d, int es, int ed, bool v) {
+    valid = v;
+    if (v) {
+      const float* ps = d.pos_src + 3 * (size_t)es;
+      const float* pd = d.pos_dst + 3 * (size_t)ed;
+      p[0] = __ldg(ps); p[1] = __ldg(ps + 1); p[2] = __ldg(ps + 2);
+      p[3] = __ldg(pd); p[4] = __ldg(pd + 1); p[5] = __ldg(pd + 2);
+    }
+  }
+  // 14 invariant features + (1, 1) against the (hi, lo) split of b1 -> row r of the F image [2 chunks][128][8] bf16
+  __device__ __forceinline__ void emit(const GrlFusedEdgeDesc& d, __nv_bfloat16* __restrict__ F, int r) const {
+    const int o = r & 15;
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = 0.f;
+    if (valid) {
+      const float rx = p[0] - p[3], ry = p[1] - p[4], rz = (d.dim == 3) ? p[2] - p[5] : 0.f;
+      const float ox = __ldg(d.ori + 3 * o), oy = __ldg(d.ori + 3 * o + 1), oz = (d.dim == 3) ? __ldg(d.ori + 3 * o + 2) : 0.f;
+      const float i1 = (rx * ox + ry * oy) + rz * oz;
+      const float tx = rx - i1 * ox, ty = ry - i1 * oy, tz = rz - i1 * oz;
+      const float i2 = sqrtf((tx * tx + ty * ty) + tz * tz);
+      f[0] = i1; f[1] = i2;
+      f[2] = i1 * i1; f[3] = i1 * i2; f[4] = i2 * i1; f[5] = i2 * i2;
+      f[6] = f[2] * i1; f[7] = f[2] * i2; f[8] = f[3] * i1; f[9] = f[3] * i2;
+      f[10] = f[4] * i1; f[11] = f[4] * i2; f[12] = f[5] * i1; f[13] = f[5] * i2;
+      f[14] = 1.0f; f[15] = 1.0f;
+    }
+    *reinterpret_cast<uint4*>(F + ((size_t)0 * kTM + r) * 8) = tc::pack8(f);
+    *reinterpret_cast<uint4*>(F + ((size_t)1 * kTM + r) * 8) = tc::pack8(f + 8);
+  }
+};
+
+// W1 [64][14] row-major + b1 -> bf16 operand image [2 chunks][64 rows n][8 f]; f = 14, 15 hold the (hi, lo) split of b1
+__device__ __forceinline__ void stage_w1_bias(__nv_bfloat16* __restrict__ img, const float* __restrict__ w1,
+                                              const float* __restrict__ b1) {
+  for (int i = threadIdx.x; i < kC * 16; i += blockDim.x) {
+    const int n = i >> 4, f = i & 15;
+    float w;
+    if (f < GRL_BASIS_FEATS) {
+      w = __ldg(w1 + n * GRL_BASIS_FEATS + f);
+    } else {
+      const float b = __ldg(b1 + n);
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      w = f == GRL_BASIS_FEATS ? hi : b - hi;
+    }
+    img[tc::op_index(kC, n, f)] = __float2bfloat16_rn(w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+struct FusedFwdSmem {
+  __nv_bfloat16 F[kTM * 16];          // [2 chunks][128][8]
+  __half HB[kTM * kC];                // H1 = GELU(pre1), then (same bytes) the basis tile; [8 chunks][128][8] fp16
+  float XS[kTileFloats];              // gathered x_src rows, then the messages in place
+  __nv_bfloat16 W1b[kC * 16];
+  __half W2h[kC * kC];                // [8 chunks][64 rows n][8 k]
+  __half Wkh[kC * kC];                // [8 chunks][64 rows c][8 j]
+  float b2[kC];
+  int src[4][kTE], dst[4][kTE];       // 4-deep index ring: slot (t & 3) holds the entries of tile t
+  uint64_t bar[3];                    // MMA completions (pre1, pre2, kern)
+  uint64_t bar_x;                     // transaction barrier of the bulk x_src row gather
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFusedEdgeDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FusedFwdSmem& s = *reinterpret_cast<FusedFwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
+  const int o = tid >> 4, cg = tid & 15;  // mapping of the segmented-sum phase
+  if (tid == 0) {
+    tc::mbar_init(&s.bar[0], 1);
+    tc::mbar_init(&s.bar[1], 1);
+    tc::mbar_init(&s.bar[2], 1);
+    tc::mbar_init(&s.bar_x, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 128);
+  stage_w1_bias(s.W1b, d.w1, d.b1);
+  tc::stage_weight_f16(s.W2h, d.w2, kC, kC, kC);
+  tc::stage_weight_f16(s.Wkh, d.wk, kC, kC, kC);
+  if (tid < kC) s.b2[tid] = __ldg(d.b2 + tid);
+  // this CTA's key (dst) node range: equal cost shares
+  const long long W = 8ll * d.n_edges + d.n_key;
+  const int n_lo = blockIdx.x == 0 ? 0 : fused_lower_bound(d.rowptr, d.n_key, W * blockIdx.x / gridDim.x);
+  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_key : fused_lower_bound(d.rowptr, d.n_key, W * (blockIdx.x + 1) / gridDim.x);
+  const int p0 = d.rowptr[n_lo], p1 = d.rowptr[n_hi];
+  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
+
+  auto load_idx = [&](int t, int& es, int& ed) {
+    es = 0; ed = 0;
+    const int e = p0 + t * kTE + tid;
+    if (tid < kTE && t < n_tiles && e < p1) { es = __ldg(d.e_src + e); ed = __ldg(d.e_dst + e); }
+  };
+  int es_a, ed_a, es_b, ed_b;  // a: tile t+2 (published in iteration t), b: tile t+3
+  load_idx(0, es_a, ed_a);
+  if (tid < kTE) { s.src[0][tid] = es_a; s.dst[0][tid] = ed_a; }
+  load_idx(1, es_a, ed_a);
+  if (tid < kTE) { s.src[1][tid] = es_a; s.dst[1][tid] = ed_a; }
+  load_idx(2, es_a, ed_a);
+  load_idx(3, es_b, ed_b);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t fa = tc::smem_u32(s.F), hb = tc::smem_u32(s.HB);
+  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2h), wk = tc::smem_u32(s.Wkh);
+  constexpr uint32_t kIdF16 = tc::idesc_f16_ex(128, kC, 0, 0, 0, 0);
+
+  RowPos pos;  // positions of tile t's rows (threads 0..127), loaded during tile t-1
+  pos.valid = false;
+  if (tid < kTM && n_tiles > 0) {
+    const int j = tid >> 4;
+    pos.load(d, s.src[0][j], s.dst[0][j], p0 + j < p1);
+  }
+
+  int cur = n_lo;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < n_tiles; ++t) {
+    const int slot = t & 3;
+    const uint32_t par = (uint32_t)t & 1u;
+    const int cnt = min(kTE, p1 - (p0 + t * kTE));
+    // publish the indices of tile t+2: slot (t+2)&3 was last read by tile t-2, two barriers ago
+    if (tid < kTE) { s.src[(t + 2) & 3][tid] = es_a; s.dst[(t + 2) & 3][tid] = ed_a; }
+    es_a = es_b; ed_a = ed_b;
+    load_idx(t + 4, es_b, ed_b);
+    tc::fence_async_smem();  // generic-proxy accesses to XS (tile t-1) before the bulk engine rewrites it
+    __syncthreads();         // (A) everyone is done with tile t-1
+    // x_src rows of this tile through the bulk-copy engine: thread r < 128 requests the 256-byte orientation row r;
+    // they land under the two MLP stages below
+    if (tid < kTM) {
+      const int j = tid >> 4, oo = tid & 15;
+      float* drow = s.XS + tid * kLDT;
+      if (j < cnt) {
+        tc::bulk_g2s(drow, d.x_src + (size_t)s.src[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_x);
+      } else {
+#pragma unroll
+        for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid == 0) tc::mbar_expect_tx(&s.bar_x, (uint32_t)cnt * kO * kC * 4u);
+      pos.emit(d, s.F, tid);
+      // positions of tile t+1 (its indices were published one iteration ago)
+      const int nb = p0 + (t + 1) * kTE + j;
+      pos.load(d, s.src[(t + 1) & 3][j], s.dst[(t + 1) & 3][j], t + 1 < n_tiles && nb < p1);
+    } else if (tid < kTM + kTE && t + 1 < n_tiles) {  // next tile's x_src rows -> L2
+      const int j = tid - kTM;
+      if (p0 + (t + 1) * kTE + j < p1) tc::prefetch_l2(d.x_src + (size_t)s.src[(t + 1) & 3][j] * kRow, kRow * 4u);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (B)
+    if (tid == 0) {   // pre1 = [F | 1 1] [W1 | b1]^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
+      tc::mma_commit(&s.bar[0]);
+    }
+    tc::mbar_wait(&s.bar[0], par);
+    tc::tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + c0, v);
+      __half2 h0[4], h1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h0[e] = tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]));
+        h1[e] = tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]));
+      }
+      *reinterpret_cast<uint4*>(s.HB + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack_h8(h0);
+      *reinterpret_cast<uint4*>(s.HB + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack_h8(h1);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (C)
+    if (tid == 0) {   // pre2 = H1 W2^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem + kC, tc::view_k(hb, kTM), tc::view_k(w2, kC), kIdF16, kC / 16, false);
+      tc::mma_commit(&s.bar[1]);
+    }
+    tc::mbar_wait(&s.bar[1], par);
+    tc::tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {  // basis = GELU(pre2 + b2) over the H1 bytes (the MMA that read them has completed)
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + kC + c0, v);
+      __half2 h0[4], h1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h0[e] = tc::gelu_h2(__floats2half2_rn(v[2 * e] + s.b2[c0 + 2 * e], v[2 * e + 1] + s.b2[c0 + 2 * e + 1]));
+        h1[e] = tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e] + s.b2[c0 + 8 + 2 * e], v[8 + 2 * e + 1] + s.b2[c0 + 8 + 2 * e + 1]));
+      }
+      *reinterpret_cast<uint4*>(s.HB + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack_h8(h0);
+      *reinterpret_cast<uint4*>(s.HB + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack_h8(h1);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (D)
+    if (tid == 0) {   // kern = basis Wk^T   (pre1's columns are free again)
+      tc::tc_fence_after();
+      tc::issue_mma(tmem, tc::view_k(hb, kTM), tc::view_k(wk, kC), kIdF16, kC / 16, false);
+      tc::mma_commit(&s.bar[2]);
+    }
+    tc::mbar_wait(&s.bar_x, par);  // the x_src rows have landed
+    tc::mbar_wait(&s.bar[2], par);
+    tc::tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {  // messages in place: XS[row][c] *= kern[row][c]
+      const int c0 = 32 * ch + 16 * i;
+      float v[16];
+      tc::tmem_ld16(lane_addr + c0, v);
+      float* xs = s.XS + row * kLDT + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        float4 x = ld4(xs + e);
+        x.x *= v[e]; x.y *= v[e + 1]; x.z *= v[e + 2]; x.w *= v[e + 3];
+        st4(xs + e, x);
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();  // (E)
+    // CSR-ordered segmented sum: thread (o, 4 channels) adds the edges of the tile sequentially
+#pragma unroll
+    for (int j = 0; j < kTE; ++j) {
+      if (j < cnt) {
+        const int dn = s.dst[slot][j];
+        while (cur < dn) {
+          st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
+          sum = make_float4(0.f, 0.f, 0.f, 0.f);
+          ++cur;
+        }
+        const float4 m = ld4(s.XS + (16 * j + o) * kLDT + 4 * cg);
+        sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+      }
+    }
+  }
+  while (cur < n_hi) {
+    st4(d.x1 + (size_t)cur * kRow + o * kC + 4 * cg, sum);
+    sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    ++cur;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------
+struct FusedBwdSmem {
+  __nv_bfloat16 F[kTM * 16];     // [2 chunks][128][8]
+  __nv_bfloat16 H1[kTM * kC];    // [8 chunks][128][8]
+  __nv_bfloat16 BZ[kTM * kC];    // recomputed basis tile
+  __nv_bfloat16 G[kTM * kC];     // g_kern, then gP2, then gP1.  MUST directly follow BZ: [BZ | G] is read as one
+                                 // 128-column MN-major image, lanes 64..127 of the accumulator then hold G^T Y
+  float GX[kTileFloats];         // g_x1 rows gathered by dst, then g_x1 * kern in place
+  float XS[kTileFloats];         // x_src rows gathered by src (run leaders only)
+  __nv_bfloat16 W1b[kC * 16];
+  __nv_bfloat16 W2b[kC * kC];    // [8 chunks][64 rows n][8 k]
+  __nv_bfloat16 Wkb[kC * kC];    // [8 chunks][64 rows c][8 j]
+  float b2[kC];
+  float acc_gb2[4][kC];
+  int src[4][kTE], dst[4][kTE], lead[4][kTE];
+  uint64_t bar[6];
+  uint64_t bar_g;
+  uint32_t tmem_base;
+};
+
+// sum over the 32 lanes of a warp of 16 per-lane values by recursive halving; on return lane l holds in v[0] the
+// total of original index l >> 1 (lanes l and l ^ 1 hold the same total).  Fixed exchange pattern -> deterministic.
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int half = 8 >> step;
+    const int bit = 16 >> step;
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(kFusedBwdThreads, 1) edge_fused_bwd_kernel(const GrlFusedEdgeDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FusedBwdSmem& s = *reinterpret_cast<FusedBwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cq = warp >> 2, row = 32 * q + lane, c0 = 16 * cq;
+  const int so = warp, sl = lane;  // segmented-sum mapping: one warp per orientation, 2 channels per lane
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) tc::mbar_init(&s.bar[i], 1);
+    tc::mbar_init(&s.bar_g, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 512);
+  stage_w1_bias(s.W1b, d.w1, d.b1);
+  tc::stage_weight_bf16(s.W2b, d.w2, kC, kC, kC);
+  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
+  if (tid < kC) s.b2[tid] = __ldg(d.b2 + tid);
+  if (tid < 4 * kC) (&s.acc_gb2[0][0])[tid] = 0.f;
+  const long long W = 8ll * d.n_edges + d.n_key;
+  const int n_lo = blockIdx.x == 0 ? 0 : fused_lower_bound(d.rowptr, d.n_key, W * blockIdx.x / gridDim.x);
+  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_key : fused_lower_bound(d.rowptr, d.n_key, W * (blockIdx.x + 1) / gridDim.x);
+  const int p0 = d.rowptr[n_lo], p1 = d.rowptr[n_hi];
+  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
+
+  auto load_idx = [&](int t, int& es, int& ed) {
+    es = 0; ed = 0;
+    const int e = p0 + t * kTE + tid;
+    if (tid < kTE && t < n_tiles && e < p1) { es = __ldg(d.e_src + e); ed = __ldg(d.e_dst + e); }
+  };
+  auto publish = [&](int slot_, int t_, int es, int ed) {
+    if (warp == 0) {  // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row
+      const int prev = __shfl_up_sync(0xffffffffu, es, 1);
+      const bool valid = lane < kTE && p0 + t_ * kTE + lane < p1;
+      const bool starts = lane == 0 || !valid || es != prev;
+      const unsigned heads = __ballot_sync(0xffffffffu, starts);
+      const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
+      if (lane < kTE) { s.src[slot_][lane] = es; s.dst[slot_][lane] = ed; s.lead[slot_][lane] = ld; }
+    }
+  };
+  int es_a, ed_a, es_b, ed_b;
+  load_idx(0, es_a, ed_a);
+  publish(0, 0, es_a, ed_a);
+  load_idx(1, es_a, ed_a);
+  publish(1, 1, es_a, ed_a);
+  load_idx(2, es_a, ed_a);
+  load_idx(3, es_b, ed_b);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t fa = tc::smem_u32(s.F), ha = tc::smem_u32(s.H1), bz = tc::smem_u32(s.BZ), ga = tc::smem_u32(s.G);
+  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b), wk = tc::smem_u32(s.Wkb);
+  // TMEM columns: [0,64) pre1 -> gH1   [64,128) pre2   [128,192) kern -> g_basis
+  //               [192,256) gWk   [256,320) gW2   [320,336) [gW1 | gb1]   (lanes 64..127 of the last three)
+  constexpr uint32_t kR0 = 0, kR1 = 64, kR2 = 128, kGWk = 192, kGW2 = 256, kGW1 = 320;
+
+  RowPos pos;
+  pos.valid = false;
+  if (tid < kTM && n_tiles > 0) {
+    const int j = tid >> 4;
+    pos.load(d, s.src[0][j], s.dst[0][j], p0 + j < p1);
+  }
+  // rows of tile t -> L2 (threads 0..15: 8 entries x {g_x1, x_src}); slot (t & 3) must be visible
+  auto prefetch_tile = [&](int t_) {
+    if (tid < 2 * kTE && t_ < n_tiles) {
+      const int j = tid & 7;
+      if (p0 + t_ * kTE + j < p1) {
+        if (tid < kTE) tc::prefetch_l2(d.grad_x1 + (size_t)s.dst[t_ & 3][j] * kRow, kRow * 4u);
+        else if (s.lead[t_ & 3][j] == j) tc::prefetch_l2(d.x_src + (size_t)s.src[t_ & 3][j] * kRow, kRow * 4u);
+      }
+    }
+  };
+  prefetch_tile(0);
+
+  int cur = n_lo;
+  float2 sum = make_float2(0.f, 0.f), init = make_float2(0.f, 0.f);
+  const size_t toff = (size_t)so * kC + 2 * sl;
+  auto begin_node = [&](int node) {  // residual row of `node`, added at its flush
+    if (d.grad_x_src_init && node < n_hi) init = __ldg(reinterpret_cast<const float2*>(d.grad_x_src_init + (size_t)node * kRow + toff));
+  };
+  auto flush = [&](int node) {
+    sum.x += init.x; sum.y += init.y;
+    *reinterpret_cast<float2*>(d.grad_x_src + (size_t)node * kRow + toff) = sum;
+    sum = make_float2(0.f, 0.f);
+  };
+  // advance to node `to`: flush the current node, then copy the residual rows of the edge-less nodes in between
+  auto advance = [&](int to) {
+    flush(cur);
+    ++cur;
+    while (cur < to) {
+      const int n = min(4, to - cur);
+      float2 r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        r[i] = (d.grad_x_src_init && i < n) ? __ldg(reinterpret_cast<const float2*>(d.grad_x_src_init + (size_t)(cur + i) * kRow + toff))
+                                            : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < n) *reinterpret_cast<float2*>(d.grad_x_src + (size_t)(cur + i) * kRow + toff) = r[i];
+      cur += n;
+    }
+    begin_node(cur);
+  };
+  begin_node(cur);
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int slot = t & 3;
+    const uint32_t par = (uint32_t)t & 1u;
+    const int cnt = min(kTE, p1 - (p0 + t * kTE));
+    const bool acc = t > 0;
+    publish((t + 2) & 3, t + 2, es_a, ed_a);
+    es_a = es_b; ed_a = ed_b;
+    load_idx(t + 4, es_b, ed_b);
+    if (t > 0) {  // the [gW1 | gb1] MMA of tile t-1 still reads F and G
+      tc::mbar_wait(&s.bar[5], par ^ 1u);
+      tc::tc_fence_after();
+    }
+    tc::fence_async_smem();  // generic-proxy accesses to GX / XS (tile t-1) before the bulk engine rewrites them
+    tc::tc_fence_before();
+    __syncthreads();         // (A)
+    prefetch_tile(t + 1);
+    if (tid == 32 && d.grad_x_src_init && cur + 2 < n_hi)  // residual rows of the next few nodes -> L2
+      tc::prefetch_l2(d.grad_x_src_init + (size_t)(cur + 2) * kRow, (uint32_t)min(8, n_hi - cur - 2) * kRow * 4u);
+    if (tid < 2 * kTM) {
+      // thread r < 128 owns row r of GX (g_x1 by dst), thread 128 + r row r of XS (x_src by src, run leaders only)
+      const int rr = tid & 127, j = rr >> 4, oo = rr & 15;
+      const bool is_x = tid >= kTM;
+      float* drow = (is_x ? s.XS : s.GX) + rr * kLDT;
+      if (j < cnt) {
+        if (!is_x) tc::bulk_g2s(drow, d.grad_x1 + (size_t)s.dst[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
+        else if (s.lead[slot][j] == j) tc::bulk_g2s(drow, d.x_src + (size_t)s.src[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
+      } else {  // rows past the end of the list: zeros (they meet finite rows in the products)
+#pragma unroll
+        for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid == 0) {
+        int n_lead = 0;
+        for (int jj = 0; jj < cnt; ++jj) n_lead += s.lead[slot][jj] == jj;
+        tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + n_lead) * kO * kC * 4u);
+      }
+      if (!is_x) {
+        pos.emit(d, s.F, tid);
+        const int nb = p0 + (t + 1) * kTE + j;
+        pos.load(d, s.src[(t + 1) & 3][j], s.dst[(t + 1) & 3][j], t + 1 < n_tiles && nb < p1);
+      }
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (B)
+    if (tid == 0) {   // pre1 = [F | 1 1] [W1 | b1]^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem + kR0, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
+      tc::mma_commit(&s.bar[0]);
+    }
+    tc::mbar_wait(&s.bar[0], par);
+    tc::tc_fence_after();
+    float dG1[16], dG2[16];
+    {
+      float v[16];
+      tc::tmem_ld16(lane_addr + kR0 + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) gelu_fast(v[e], v[e], dG1[e]);
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+      *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (C)
+    if (tid == 0) {   // pre2 = H1 W2^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem + kR1, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+      tc::mma_commit(&s.bar[1]);
+    }
+    tc::mbar_wait(&s.bar[1], par);
+    tc::tc_fence_after();
+    {
+      float v[16];
+      tc::tmem_ld16(lane_addr + kR1 + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) gelu_fast(v[e] + s.b2[c0 + e], v[e], dG2[e]);
+      *reinterpret_cast<uint4*>(s.BZ + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+      *reinterpret_cast<uint4*>(s.BZ + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (D)
+    if (tid == 0) {   // kern = basis Wk^T
+      tc::tc_fence_after();
+      tc::issue_mma(tmem + kR2, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+      tc::mma_commit(&s.bar[2]);
+    }
+    tc::mbar_wait(&s.bar_g, par);  // the g_x1 / x_src rows have landed
+    tc::mbar_wait(&s.bar[2], par);
+    tc::tc_fence_after();
+    {
+      float v[16], gkv[16];
+      tc::tmem_ld16(lane_addr + kR2 + c0, v);
+      float* gx = s.GX + row * kLDT + c0;
+      const float* xs = s.XS + (16 * s.lead[slot][row >> 4] + (row & 15)) * kLDT + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const float4 gm = ld4(gx + e), x = ld4(xs + e);
+        st4(gx + e, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
+        gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
+      }
+      *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
+      *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (E)
+    if (tid == 0) {
+      tc::tc_fence_after();
+      // g_basis = g_kern Wk   (Wk image [c rows][j cols] read MN-major: K = c, N = j); kern's columns are free again
+      tc::issue_mma(tmem + kR2, tc::view_k(ga, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
+      // lanes 64..127: gWk[c][j] += sum_rows g_kern[row][c] basis[row][j]   ([BZ | G] as one 128-column image)
+      tc::issue_mma(tmem + kGWk, tc::view_mn(bz, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
+      tc::mma_commit(&s.bar[3]);
+    }
+    // src-CSR segmented sum of g_x1 * kern while the tensor core works
+#pragma unroll
+    for (int j = 0; j < kTE; ++j) {
+      if (j < cnt) {
+        const int sn = s.src[slot][j];
+        if (cur < sn) advance(sn);
+        const float2 m = *reinterpret_cast<const float2*>(s.GX + (16 * j + so) * kLDT + 2 * sl);
+        sum.x += m.x; sum.y += m.y;
+      }
+    }
+    tc::mbar_wait(&s.bar[3], par);
+    tc::tc_fence_after();
+    {
+      float v[16];
+      tc::tmem_ld16(lane_addr + kR2 + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] *= dG2[e];
+      *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+      *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+      warp_colsum16(v, lane);
+      if ((lane & 1) == 0) s.acc_gb2[q][c0 + (lane >> 1)] += v[0];
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (F)
+    if (tid == 0) {
+      tc::tc_fence_after();
+      // gH1 = gP2 W2   (W2 image [n rows][k cols] read MN-major: K = n, N = k); pre1's columns are free again
+      tc::issue_mma(tmem + kR0, tc::view_k(ga, kTM), tc::view_mn(w2, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
+      // lanes 64..127: gW2[n][k] += sum_rows gP2[row][n] H1[row][k]
+      tc::issue_mma(tmem + kGW2, tc::view_mn(bz, kTM), tc::view_mn(ha, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
+      tc::mma_commit(&s.bar[4]);
+    }
+    tc::mbar_wait(&s.bar[4], par);
+    tc::tc_fence_after();
+    {
+      float v[16];
+      tc::tmem_ld16(lane_addr + kR0 + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] *= dG1[e];
+      *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+      *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+    }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();  // (G)
+    if (tid == 0) {
+      tc::tc_fence_after();
+      // lanes 64..127: [gW1 | gb1][n][f] += sum_rows gP1[row][n] [F | 1 1][row][f]
+      tc::issue_mma(tmem + kGW1, tc::view_mn(bz, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, acc);
+      tc::mma_commit(&s.bar[5]);
+    }
+  }
+  if (n_tiles > 0) {
+    tc::mbar_wait(&s.bar[5], (uint32_t)(n_tiles - 1) & 1u);
+    tc::tc_fence_after();
+  }
+  if (cur < n_hi) advance(n_hi);
+  // partial slot of this CTA: gWk[64][64] | gW1b[64][16] (columns 14, 15 = gb1) | gW2[64][64] | gb2[64]
+  __syncthreads();
+  float* P = d.grad_partials + (size_t)blockIdx.x * GRL_FUSED_EDGE_GRAD_FLOATS;
+  {
+    float v[16];
+    auto read = [&](uint32_t col) {
+      if (n_tiles > 0) {
+        tc::tmem_ld16(lane_addr + col, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+      }
+    };
+    read(kGWk + c0);
+    if (row >= 64) {
+      float* p = P + (size_t)(row - 64) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+    read(kGW2 + c0);
+    if (row >= 64) {
+      float* p = P + kWFloats + 64 * 16 + (size_t)(row - 64) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+    read(kGW1);
+    if (row >= 64 && cq == 0) {
+      float* p = P + kWFloats + (size_t)(row - 64) * 16;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+  }
+  if (tid < kC)
+    P[2 * kWFloats + 64 * 16 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace grl
+
+extern "C" {
+
+static int fused_check(const GrlFusedEdgeDesc* d, const char* what) {
+  GRL_REQUIRE(d, GRL_EINVAL, "%s: null descriptor", what);
+  GRL_REQUIRE(d->n_key > 0 && d->n_edges >= 0 && (d->dim == 2 || d->dim == 3), GRL_EINVAL, "%s: n_key=%d n_edges=%d dim=%d",
+              what, d->n_key, d->n_edges, d->dim);
+  GRL_REQUIRE(d->rowptr && d->pos_src && d->pos_dst && d->ori && d->w1 && d->b1 && d->w2 && d->b2 && d->wk && d->x_src &&
+                  (d->n_edges == 0 || (d->e_src && d->e_dst)), GRL_EINVAL, "%s: null pointer", what);
+  return GRL_OK;
+}
+
+int grl_fbconv_edge_fused_fwd(const GrlFusedEdgeDesc* d, grl_stream_t stream) {
+  const int rc = fused_check(d, "grl_fbconv_edge_fused_fwd");
+  if (rc != GRL_OK) return rc;
+  GRL_REQUIRE(d->x1, GRL_EINVAL, "grl_fbconv_edge_fused_fwd: x1 is null");
+  const int smem = (int)sizeof(grl::FusedFwdSmem);
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_fwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
+  int grid = 3 * grl::sm_count();
+  if (grid > d->n_key) grid = d->n_key;
+  grl::edge_fused_fwd_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_fbconv_edge_fused_fwd");
+}
+
+int grl_fbconv_edge_fused_bwd(const GrlFusedEdgeDesc* d, grl_stream_t stream) {
+  const int rc = fused_check(d, "grl_fbconv_edge_fused_bwd");
+  if (rc != GRL_OK) return rc;
+  GRL_REQUIRE(d->grad_x1 && d->grad_x_src && d->grad_partials, GRL_EINVAL, "grl_fbconv_edge_fused_bwd: null pointer");
+  GRL_REQUIRE(d->n_partials > 0 && d->n_partials <= d->n_key, GRL_EINVAL,
+              "grl_fbconv_edge_fused_bwd: n_partials=%d must be in [1, n_key]", d->n_partials);
+  const int smem = (int)sizeof(grl::FusedBwdSmem);
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
+  grl::edge_fused_bwd_kernel<<<d->n_partials, grl::kFusedBwdThreads, smem, (cudaStream_t)stream>>>(*d);
+  return grl::check_launch("grl_fbconv_edge_fused_bwd");
+}
+
+}  // extern "C"

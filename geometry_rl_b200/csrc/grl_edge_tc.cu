@@ -327,12 +327,8 @@ int grl_edge_basis_fwd_tc(const GrlBasisDesc* d, grl_stream_t stream) {
               d->n_edges, d->dim);
   GRL_REQUIRE(d->edge_src && d->edge_dst && d->pos_src && d->pos_dst && d->ori && d->w1t && d->b1 && d->w2t && d->b2 &&
                   d->basis_bf16, GRL_EINVAL, "grl_edge_basis_fwd_tc: null pointer");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::BasisTcSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::edge_basis_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_basis_fwd_tc_kernel, smem) != GRL_OK) return GRL_ECUDA;
   const int n_tiles = (d->n_edges + grl::kTE - 1) / grl::kTE;
   int grid = 3 * grl::sm_count();  // 37 KB smem, 128 TMEM columns, <= 85 registers: three CTAs share an SM
   if (grid > n_tiles) grid = n_tiles;
@@ -345,12 +341,8 @@ int grl_fbconv_edge_fwd_tc(const GrlConvDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d->n_dst > 0 && d->n_src > 0 && d->n_edges >= 0, GRL_EINVAL, "grl_fbconv_edge_fwd_tc: bad sizes");
   GRL_REQUIRE(d->rowptr_dst && d->x_src && d->wk && d->x1 && (d->n_edges == 0 || (d->edge_src && d->edge_dst && d->basis_bf16)),
               GRL_EINVAL, "grl_fbconv_edge_fwd_tc: null pointer");
-  static bool attr = false;
   const int smem = (int)sizeof(grl::EdgeFwdTcSmem);
-  if (!attr) {
-    cudaFuncSetAttribute(grl::fbconv_edge_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (grl::ensure_dynamic_smem((const void*)grl::fbconv_edge_fwd_tc_kernel, smem) != GRL_OK) return GRL_ECUDA;
   int grid = 2 * grl::sm_count();
   if (grid > d->n_dst) grid = d->n_dst;
   grl::fbconv_edge_fwd_tc_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);

@@ -1,6 +1,9 @@
 // Error plumbing, device query and the deterministic cross-CTA partial reduction.
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "grl_common.cuh"
 
@@ -35,6 +38,29 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: set it once per (kernel, device)
+// pair.  (A process-wide "already set" latch breaks the second device a process drives.)  The table only ever grows
+// and an entry never changes: idempotent capability state, like sm_count()'s cache.
+int ensure_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed");
+    return GRL_ECUDA;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& e : done)
+    if (e.first == func && e.second == dev) return GRL_OK;
+  const cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d): %s", bytes, cudaGetErrorString(err));
+    return GRL_ECUDA;
+  }
+  done.emplace_back(func, dev);
+  return GRL_OK;
 }
 
 // out[i] (+)= sum_p partials[p][i] in a FIXED order: the partials are split into 8 contiguous segments, each summed

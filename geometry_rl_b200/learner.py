@@ -120,14 +120,51 @@ class Learner:
         self.critic_optim = torch.optim.Adam(critic.parameters(), lr=cfg.lr, eps=1e-5, fused=fused, capturable=fused)
         self.num_network_updates = 0
         self._graph = None
+        # ONE persistent flat fp32 gradient bucket (actor | critic); after `_finish_grads` every parameter's .grad is a
+        # view into it, so the data-parallel exchange is one all-reduce of this buffer with no copy back, and the
+        # gradients of the last update stay readable (`flat_grads`) after the optimisers have zeroed the .grad fields.
+        self._params = [p for p in list(actor.parameters()) + list(critic.parameters()) if p.requires_grad]
+        self._flat = torch.zeros(sum(p.numel() for p in self._params), dtype=torch.float32, device=self._params[0].device)
+        self._views, off = [], 0
+        for p in self._params:
+            self._views.append(self._flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
         if dp is not None:
             dp.attach(loss_module)
+            dp.sync_module_state(actor, critic)  # replicas start bit-identical whatever each rank's RNG did
 
     def compute_losses(self, batch) -> Dict[str, torch.Tensor]:
         self.loss_module._global_steps = self.num_network_updates
         loss = self.loss_module(batch)
         loss["actor_loss"] = loss["loss_objective"] + loss["loss_entropy"] + loss["loss_trust_region"]
         return loss
+
+    def _finish_grads(self):
+        """Move this step's gradients into the flat bucket (one multi-tensor copy; parameters that took no part in the
+        step, e.g. the AGENT convolution when A == 1, contribute zeros so the layout is identical on every rank),
+        all-reduce it under data parallelism, and point every .grad at its view."""
+        have = [i for i, p in enumerate(self._params) if p.grad is not None]
+        if len(have) != len(self._params):
+            self._flat.zero_()
+        torch._foreach_copy_([self._views[i] for i in have], [self._params[i].grad for i in have])
+        if self.dp is not None:
+            self.dp.all_reduce(self._flat)  # summed: the losses already divide by the global count
+        for p, v in zip(self._params, self._views):
+            p.grad = v
+
+    def flat_grads(self) -> Dict[str, torch.Tensor]:
+        """Gradients of the most recent update (after the data-parallel all-reduce), keyed like `named_parameters()` of
+        the actor ("actor.<name>") and the critic ("critic.<name>"); views into the flat bucket."""
+        names = [f"actor.{n}" for n, p in self.actor.named_parameters() if p.requires_grad] + \
+                [f"critic.{n}" for n, p in self.critic.named_parameters() if p.requires_grad]
+        return dict(zip(names, self._views))
+
+    @torch.no_grad()
+    def calibrate(self, batch):
+        """The one-time calibration forward of train.py:72-74 (FiberBundleConv rescales its kernels from the statistics of
+        the first training-mode forward, conv.py:104-105,151-157).  Under data parallelism the statistics are global
+        (every rank must call this with its shard), so replicas stay identical."""
+        self.actor.get_dist(batch)
 
     def update(self, batch) -> Dict[str, torch.Tensor]:
         if self._critic_stream is not None:
@@ -136,8 +173,7 @@ class Learner:
         self.num_network_updates += 1
         loss["actor_loss"].backward()
         loss["loss_critic"].backward()
-        if self.dp is not None:
-            self.dp.allreduce_grads(list(self.actor.parameters()) + list(self.critic.parameters()))
+        self._finish_grads()
         if self.cfg.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.cfg.max_grad_norm)
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.cfg.max_grad_norm)
@@ -168,8 +204,7 @@ class Learner:
         self.num_network_updates += 1
         loss["actor_loss"].backward()
         main.wait_stream(side)
-        if self.dp is not None:
-            self.dp.allreduce_grads(list(self.actor.parameters()) + list(self.critic.parameters()))
+        self._finish_grads()
         if self.cfg.clip_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.actor.parameters(), self.cfg.max_grad_norm)
             torch.nn.utils.clip_grad_norm_(self.critic.parameters(), self.cfg.max_grad_norm)
@@ -180,22 +215,82 @@ class Learner:
         return loss
 
     # ---- CUDA-graph replay of the whole update (launch-bound glue: ~500 launches per step) -----------------------
-    def capture(self, example_batch, warmup: int = 3):
-        """Capture `update` on static copies of `example_batch` (same shapes for every later batch).  The warm-up
-        iterations are REAL updates (they also run the one-time calibration and build the topology cache)."""
+    def capture(self, example_batch, warmup: int = 3, restore: bool = True):
+        """Capture `update` on static copies of `example_batch` (same shapes for every later batch).
+
+        The warm-up iterations (allocator / NCCL / topology-cache warm-up) run real updates; with `restore` (default)
+        parameters and optimiser state are put back afterwards, so the first replayed minibatch is the first update the
+        networks see, as in the reference loop (train.py:259-316).  The one-time calibration runs BEFORE the snapshot:
+        it belongs to the first forward, not to the warm-up.  The captured graph bakes in Python-side scalars (Adam's lr,
+        `loss_module._global_steps`): lr annealing or an entropy schedule would be frozen, so capture refuses them.
+        The graph also holds the topology tensors of this batch size: re-capture after `hyper_data.invalidate()`."""
+        proj = getattr(self.loss_module, "projection", None)
+        if getattr(proj, "entropy_schedule", False):
+            raise NotImplementedError("an entropy schedule depends on the host-side step counter, which a captured graph "
+                                      "freezes; use the eager `update`")
         # data-parallel: the NCCL all-reduces of the step are captured too (torch's ProcessGroupNCCL records them on the
         # capture stream); every rank must capture and replay in lock-step
         self._static = {k: v.clone() for k, v in example_batch.items() if torch.is_tensor(v)}
+        self.calibrate(self._static)
+        modules = [self.actor, self.critic]
+        if restore:
+            saved = [[t.detach().clone() for t in list(m.parameters()) + list(m.buffers())] for m in modules]
+            import copy
+            saved_opt = [copy.deepcopy(o.state_dict()) for o in (self.actor_optim, self.critic_optim)]
+            saved_n = self.num_network_updates
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self.update(self._static)
         torch.cuda.current_stream().wait_stream(side)
+        if restore:
+            with torch.no_grad():
+                for m, ts in zip(modules, saved):
+                    for t, s_ in zip(list(m.parameters()) + list(m.buffers()), ts):
+                        t.copy_(s_)
+            if saved_opt[0]["state"]:
+                self.actor_optim.load_state_dict(saved_opt[0])
+                self.critic_optim.load_state_dict(saved_opt[1])
+            else:  # fresh optimisers: zero the moments / step counters the warm-up created, keep their (static) tensors
+                for o in (self.actor_optim, self.critic_optim):
+                    for st in o.state.values():
+                        for v in st.values():
+                            if torch.is_tensor(v):
+                                v.zero_()
+            self.num_network_updates = saved_n
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._graph_out = self.update(self._static)
+        self.num_network_updates -= 1  # the capture pass did not execute
         return self
+
+    def update_static(self):
+        """Replay the captured update on whatever the static inputs (`self._static`) hold right now."""
+        self._graph.replay()
+        self.num_network_updates += 1
+        return self._graph_out
+
+    # ---- the epoch loop of train.py:255-316 over a device-resident rollout buffer (SURVEY 8(f) N3) ---------------
+    def fit(self, buffer, epochs: Optional[int] = None, graphed: bool = True):
+        """`epochs` passes (default cfg.ppo_epochs) over a `DeviceRolloutBuffer`; one update per minibatch of each pass's
+        permutation.  `graphed`: full-size minibatches are gathered straight into the static inputs of the captured
+        update and replayed (captured on the first call from the first minibatch — the buffer should be built with
+        `drop_last=True`, a short tail chunk falls back to the eager update).  Returns the per-update loss dicts (for a
+        replayed update these are the graph's output tensors, overwritten by the next replay: read them before it)."""
+        from .rollout import run_minibatch_epochs
+        epochs = self.cfg.ppo_epochs if epochs is None else epochs
+        if not graphed:
+            return run_minibatch_epochs(self.update, buffer, epochs)
+        if self._graph is None:
+            first = next(iter(buffer.sample_indices()))
+            if first.numel() != buffer.batch_size:
+                raise ValueError("the buffer holds less than one full minibatch; use graphed=False")
+            self.capture({k: v.index_select(0, first) for k, v in buffer._storage.items()})
+
+        def step(mb):
+            return self.update_static() if mb is self._static else self.update(mb)
+        return run_minibatch_epochs(step, buffer, epochs, static_inputs=self._static)
 
     def update_graphed(self, batch):
         for k, v in self._static.items():

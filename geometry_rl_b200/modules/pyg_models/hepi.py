@@ -107,8 +107,8 @@ class HEPi(nn.Module):
         for et in live_edge_types:
             src, _, dst = et
             es = edge_sets[et]
-            kernel_basis_dict[et] = ops.EdgeBasisFn.apply(pos[src], pos[dst], bf[1].weight, bf[1].bias,
-                                                          bf[3].weight, bf[3].bias, ori3, self.dim, es)
+            kernel_basis_dict[et] = ops.edge_basis(pos[src], pos[dst], bf[1].weight, bf[1].bias,
+                                                   bf[3].weight, bf[3].bias, ori3, self.dim, es)
             fiber_dict[et] = fiber
         for i in range(self.num_messages):
             processor = self.processor if self.shared_processor else self.processor[i]

@@ -66,6 +66,5 @@ class FiberBundleConv(torch.nn.Module):
     def _callibration_factors(self, x_src, x_dst, edge_attr, fk, edge_set):
         x1 = ops.aggregate_messages(x_src, edge_attr, self.kernel.weight, edge_set)
         x2 = torch.einsum("boc,opc->bpc", x1, fk) / fk.shape[-2]
-        print("Callibrating...")
-        std_in, std_1, std_2 = x_dst.std(), x1.std(), x2.std()
+        std_in, std_1, std_2 = ops.calibration_std(x_dst), ops.calibration_std(x1), ops.calibration_std(x2)
         return std_in / std_1, std_1 / std_2

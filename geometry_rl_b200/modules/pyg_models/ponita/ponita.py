@@ -138,8 +138,7 @@ class SeparableFiberBundleConvNext(nn.Module):
     def _callibration_factors(self, x, kernel_basis, fk_op, edge_set):
         x1 = ops.aggregate_messages(x, kernel_basis, self.conv.kernel.weight, edge_set)
         x2 = torch.einsum("boc,opc->bpc", x1, fk_op) / 16
-        print("Callibrating...")
-        std_in, std_1, std_2 = x.std(), x1.std(), x2.std()
+        std_in, std_1, std_2 = ops.calibration_std(x), ops.calibration_std(x1), ops.calibration_std(x2)
         return std_in / std_1, std_1 / std_2
 
 
@@ -187,8 +186,8 @@ class Ponita(nn.Module):
         are the PADDED arrays and node n of the (compact) graph is their row node_ids[n]; pos is already compact."""
         ori3 = pad_ori3(self.ori_grid)
         bf = self.basis_fn
-        kernel_basis = ops.EdgeBasisFn.apply(pos, pos, bf[1].weight, bf[1].bias, bf[3].weight, bf[3].bias, ori3, self.dim,
-                                             edge_set)
+        kernel_basis = ops.edge_basis(pos, pos, bf[1].weight, bf[1].bias, bf[3].weight, bf[3].bias, ori3, self.dim,
+                                      edge_set)
         fiber_kernel_basis = self.fiber_basis()
         x = ops.EmbedFn.apply(scalars, vectors, self.x_embedder.weight, ori3, self.dim, node_ids)
         n_layers = len(self.interaction_layers)

@@ -21,6 +21,10 @@ ROW = 16 * 64
 _PRECISION = "fp32"
 # debugging aid for error attribution: which halves of the bf16 path use the tensor-core kernels ("node", "edge")
 _TC_PARTS = set(os.environ.get("GRL_TC_PARTS", "node,edge").split(","))
+# 16-bit path: recompute the edge basis inside the edge kernels (grl_fbconv_edge_fused_*) instead of materialising an
+# [E,16,64] basis and its gradient in HBM.  GRL_FUSED_EDGE=0 (or set_fused_edge(False)) selects the round-1 kernels
+# (grl_edge_basis_*_tc + grl_fbconv_edge_*_tc), kept as the parity partner of the fused ones in the tests.
+_FUSED_EDGE = os.environ.get("GRL_FUSED_EDGE", "1") != "0"
 
 
 def set_precision(mode: str):
@@ -32,6 +36,30 @@ def set_precision(mode: str):
 
 def get_precision() -> str:
     return _PRECISION
+
+
+def set_fused_edge(on: bool):
+    global _FUSED_EDGE
+    _FUSED_EDGE = bool(on)
+
+
+def fused_edge_enabled() -> bool:
+    return _PRECISION == "bf16" and _FUSED_EDGE and "edge" in _TC_PARTS and "node" in _TC_PARTS
+
+
+# std() used by the one-time kernel calibration (conv.py:151-157, ponita.py:178-192).  Single process: torch's own
+# Tensor.std(), exactly like the reference.  Data parallel: DataParallel.attach installs a global version (moments
+# all-reduced over the ranks), so every replica derives the same scaling factors from the whole minibatch.
+_CALIBRATION_STD = None
+
+
+def set_calibration_std(fn):
+    global _CALIBRATION_STD
+    _CALIBRATION_STD = fn
+
+
+def calibration_std(x: torch.Tensor) -> torch.Tensor:
+    return x.std() if _CALIBRATION_STD is None else _CALIBRATION_STD(x)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -60,6 +88,8 @@ class EdgeSet:
     eid_coo: torch.Tensor  # [E] int32: edge order -> COO position
     rowptr_src: torch.Tensor  # [n_src+1] int32
     src_eid: torch.Tensor  # [E] int32: src-sorted entry -> edge-order position
+    s_src: Optional[torch.Tensor] = None  # [E] int32: source of the q-th src-sorted entry (lazy, see src_sorted_pairs)
+    s_dst: Optional[torch.Tensor] = None  # [E] int32: destination of the q-th src-sorted entry
 
 
 @dataclass
@@ -82,6 +112,22 @@ class SubEdgeSet:
     rowptr_src: torch.Tensor  # [n_src+1] int32
     src_eid_parent: torch.Tensor  # [E_sub] int32: src-sorted entry -> position in the PARENT's edge order
     edge_dst_parent: torch.Tensor  # [E_parent] int32: dst rank (0..n_dst-1) of every parent edge, -1 outside the subset
+    s_src: Optional[torch.Tensor] = None  # [E_sub] int32: source (parent node id) of the q-th src-sorted sub-edge (lazy)
+    s_dst: Optional[torch.Tensor] = None  # [E_sub] int32: destination rank of the q-th src-sorted sub-edge
+
+
+def src_sorted_pairs(es: "EdgeSet", sub: Optional[SubEdgeSet] = None):
+    """(s_src, s_dst): endpoints of the src-sorted entry list as two plain arrays, so the fused backward kernel walks it
+    without dependent index loads.  Derived once per topology and cached on the edge set."""
+    top = sub if sub is not None else es
+    if top.s_src is None:
+        if sub is None:
+            idx = es.src_eid.long()
+            top.s_src, top.s_dst = es.edge_src[idx].contiguous(), es.edge_dst[idx].contiguous()
+        else:
+            idx = sub.src_eid_parent.long()
+            top.s_src, top.s_dst = es.edge_src[idx].contiguous(), sub.edge_dst_parent[idx].contiguous()
+    return top.s_src, top.s_dst
 
 
 def build_sub_edge_set(es: "EdgeSet", out_ids: torch.Tensor) -> SubEdgeSet:
@@ -294,9 +340,134 @@ class EdgeBasisFn(torch.autograd.Function):
         return None, None, gw1, gb1, gw2, gb2, None, None, None
 
 
+class BasisSpec:
+    """What a fused convolution needs to recompute its edge basis per tile: positions of both endpoint sets and the
+    `basis_fn` parameters (hepi.py:76-82).  Stands in for the [E,16,64] `kernel_basis` tensor on the fused path."""
+
+    def __init__(self, pos_src, pos_dst, w1, b1, w2, b2, ori3, dim, es: EdgeSet):
+        self.pos_src, self.pos_dst = _f32c(pos_src.detach()), _f32c(pos_dst.detach())
+        self.w1, self.b1, self.w2, self.b2 = w1, b1, w2, b2
+        self.ori3, self.dim, self.es = ori3, dim, es
+
+    def materialize(self) -> torch.Tensor:
+        """The basis as a tensor (one-time calibration only, conv.py:151-157)."""
+        return EdgeBasisFn.apply(self.pos_src, self.pos_dst, self.w1, self.b1, self.w2, self.b2, self.ori3, self.dim,
+                                 self.es)
+
+
+def edge_basis(pos_src, pos_dst, w1, b1, w2, b2, ori3, dim, es: EdgeSet):
+    """kernel_basis of one edge type: a `BasisSpec` on the fused 16-bit path, the [E,16,64] tensor otherwise."""
+    if fused_edge_enabled():
+        return BasisSpec(pos_src, pos_dst, w1, b1, w2, b2, ori3, dim, es)
+    return EdgeBasisFn.apply(pos_src, pos_dst, w1, b1, w2, b2, ori3, dim, es)
+
+
 # ------------------------------------------------------------------------------------------------
 # separable fibre-bundle convolution + ConvNeXt update
 # ------------------------------------------------------------------------------------------------
+class FusedFiberConvFn(torch.autograd.Function):
+    """FiberConvFn with the edge basis recomputed inside the edge kernels (16-bit path): no basis tensor, no basis
+    gradient tensor; the gradients of the basis MLP leave the edge backward kernel directly."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_dst, pos_src, pos_dst, bw1, bb1, bw2, bb2, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, ori3,
+                dim, es: EdgeSet, sub: Optional[SubEdgeSet]):
+        homo = x_dst is None
+        x_src = _f32c(x_src)
+        if sub is not None:
+            assert homo and sub.n_src == es.n_src
+            xd = x_src.index_select(0, sub.out_ids)
+            pos_dst = pos_dst.index_select(0, sub.out_ids)
+        else:
+            xd = x_src if homo else _f32c(x_dst)
+        top = sub if sub is not None else es
+        assert x_src.shape[0] == top.n_src and xd.shape[0] == top.n_dst, "latent rows do not match the edge set"
+        assert tuple(x_src.shape[1:]) == (16, 64) and tuple(w1.shape) == (256, 64) and tuple(w2.shape) == (64, 256)
+        assert tuple(bw1.shape) == (64, 14) and tuple(bw2.shape) == (64, 64)
+        dev = x_src.device
+        pos_src, pos_dst = _f32c(pos_src), _f32c(pos_dst)
+        bw1_c, bb1_c, bw2_c, bb2_c = _f32c(bw1.detach()), _f32c(bb1.detach()), _f32c(bw2.detach()), _f32c(bb2.detach())
+        fk = _f32c(fk)
+        wk_c, w1_c, w2_rm = _f32c(wk.detach()), _f32c(w1.detach()), _f32c(w2.detach())
+        bias_c, lng_c, lnb_c = _f32c(bias.detach()), _f32c(ln_g.detach()), _f32c(ln_b.detach())
+        b1_c, b2_c = _f32c(b1.detach()), _f32c(b2.detach())
+        x1 = torch.empty(top.n_dst, 16, 64, dtype=torch.float32, device=dev)
+        out = torch.empty(top.n_dst, 16, 64, dtype=torch.float32, device=dev)
+        shape = (top.n_src, top.n_dst, top.n_edges)
+        fd = L.GrlFusedEdgeDesc(n_key=top.n_dst, n_edges=top.n_edges, dim=dim, n_partials=0, rowptr=L.ptr(top.rowptr_dst),
+                                e_src=L.ptr(top.edge_src), e_dst=L.ptr(top.edge_dst), pos_src=L.ptr(pos_src),
+                                pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1=L.ptr(bw1_c), b1=L.ptr(bb1_c), w2=L.ptr(bw2_c),
+                                b2=L.ptr(bb2_c), wk=L.ptr(wk_c), x_src=L.ptr(x_src), x1=L.ptr(x1))
+        L.call("grl_fbconv_edge_fused_fwd", C.byref(fd), shape=shape)
+        # the tensor-core node backward reads the pre-LayerNorm tensor instead of recomputing the fibre convolution
+        x2 = torch.empty_like(x1) if any(ctx.needs_input_grad) else None
+        d = L.GrlConvDesc(n_src=top.n_src, n_dst=top.n_dst, n_edges=top.n_edges, rowptr_dst=L.ptr(top.rowptr_dst),
+                          x_src=L.ptr(x_src), x_dst=L.ptr(xd), fiber_kernel=L.ptr(fk), wk=L.ptr(wk_c), bias=L.ptr(bias_c),
+                          ln_g=L.ptr(lng_c), ln_b=L.ptr(lnb_c), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2=L.ptr(w2_rm),
+                          b2=L.ptr(b2_c), x1=L.ptr(x1), out=L.ptr(out), accumulate_out=0, x2=L.ptr(x2),
+                          # operands of the strict kernels only; the descriptor check wants them non-null
+                          wk_t=L.ptr(wk_c), w1_t=L.ptr(w1_c), w2_t=L.ptr(w1_c), w2_c=L.ptr(w1_c))
+        L.call("grl_fbconv_node_fwd_tc", C.byref(d), shape=shape)
+        ctx.save_for_backward(x_src, pos_src, pos_dst, bw1_c, bb1_c, bw2_c, bb2_c, fk, wk_c, bias_c, lng_c, lnb_c, w1_c,
+                              b1_c, w2_rm, b2_c, x1, x2 if x2 is not None else x1, ori3)
+        ctx.es, ctx.sub, ctx.homo, ctx.dim = es, sub, homo, dim
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (x_src, pos_src, pos_dst, bw1_c, bb1_c, bw2_c, bb2_c, fk, wk_c, bias_c, lng_c, lnb_c, w1_c, b1_c, w2_rm, b2_c, x1,
+         x2, ori3) = ctx.saved_tensors
+        es, sub, homo, dim = ctx.es, ctx.sub, ctx.homo, ctx.dim
+        top = sub if sub is not None else es
+        dev = x_src.device
+        g_out = _f32c(g_out)
+        g_x1, g_x2 = torch.empty_like(x1), torch.empty_like(x1)
+        g_xsrc = torch.empty_like(x_src)
+        shape = (top.n_src, top.n_dst, top.n_edges)
+        n_pn = _n_partials((top.n_dst + 7) // 8)
+        node_part = torch.empty(n_pn, L.NODE_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        amax = torch.empty(1, dtype=torch.int32, device=dev)  # bit pattern of max |grad_out| (fp16 gradient scale)
+        L.call("grl_absmax", L.ptr(g_out), g_out.numel(), L.ptr(amax), shape=shape)
+        d = L.GrlConvDesc(n_src=top.n_src, n_dst=top.n_dst, n_edges=top.n_edges, rowptr_dst=L.ptr(top.rowptr_dst),
+                          x_src=L.ptr(x_src), fiber_kernel=L.ptr(fk), wk=L.ptr(wk_c), bias=L.ptr(bias_c), ln_g=L.ptr(lng_c),
+                          ln_b=L.ptr(lnb_c), w1=L.ptr(w1_c), b1=L.ptr(b1_c), w2=L.ptr(w2_rm), x1=L.ptr(x1), x2=L.ptr(x2),
+                          grad_out=L.ptr(g_out), grad_x1=L.ptr(g_x1), grad_x2=L.ptr(g_x2), grad_amax=L.ptr(amax),
+                          node_grad_partials=L.ptr(node_part), n_partials_node=n_pn,
+                          wk_t=L.ptr(wk_c), w1_t=L.ptr(w1_c), w2_c=L.ptr(w1_c))
+        L.call("grl_fbconv_node_bwd_tc", C.byref(d), shape=shape)
+        s_src, s_dst = src_sorted_pairs(es, sub)
+        n_pe = _n_partials(top.n_src)
+        edge_part = torch.empty(n_pe, L.FUSED_EDGE_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        fd = L.GrlFusedEdgeDesc(n_key=top.n_src, n_edges=top.n_edges, dim=dim, n_partials=n_pe, rowptr=L.ptr(top.rowptr_src),
+                                e_src=L.ptr(s_src), e_dst=L.ptr(s_dst), pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst),
+                                ori=L.ptr(ori3), w1=L.ptr(bw1_c), b1=L.ptr(bb1_c), w2=L.ptr(bw2_c), b2=L.ptr(bb2_c),
+                                wk=L.ptr(wk_c), x_src=L.ptr(x_src), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),
+                                grad_x_src_init=L.ptr(g_out) if (homo and sub is None) else None,
+                                grad_partials=L.ptr(edge_part))
+        L.call("grl_fbconv_edge_fused_bwd", C.byref(fd), shape=shape)
+        g = _reduce(node_part)
+        o = 0
+        gw1 = g[o:o + 256 * 64].view(256, 64); o += 256 * 64
+        gb1 = g[o:o + 256]; o += 256
+        gw2 = g[o:o + 64 * 256].view(64, 256); o += 64 * 256
+        gb2 = g[o:o + 64]; o += 64
+        glng = g[o:o + 64]; o += 64
+        glnb = g[o:o + 64]; o += 64
+        gbias = g[o:o + 64]; o += 64
+        gfk = g[o:o + 16 * 16 * 64].view(16, 16, 64)
+        ge = _reduce(edge_part)
+        gwk = ge[:4096].view(64, 64)
+        gw1b = ge[4096:4096 + 1024].view(64, 16)
+        g_bw1, g_bb1 = gw1b[:, :14].contiguous(), gw1b[:, 14].contiguous()
+        g_bw2 = ge[5120:5120 + 4096].view(64, 64)
+        g_bb2 = ge[9216:9280]
+        g_xdst = None if homo else g_out
+        if sub is not None:  # residual path of the output rows (out_ids are unique: plain read-modify-write)
+            g_xsrc.index_copy_(0, sub.out_ids, g_xsrc.index_select(0, sub.out_ids) + g_out)
+        return (g_xsrc, g_xdst, None, None, g_bw1, g_bb1, g_bw2, g_bb2, gfk, gwk, gbias, glng, glnb, gw1, gb1, gw2, gb2,
+                None, None, None, None)
+
+
 class FiberConvFn(torch.autograd.Function):
     """out = x_dst + MLP(LN(fibre(scatter(kernel(basis) * x_src[src])) + bias)).
 
@@ -451,11 +622,18 @@ class FiberConvFn(torch.autograd.Function):
 
 def fiber_conv(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es: EdgeSet,
                sub: Optional[SubEdgeSet] = None):
+    """`basis`: the [E,16,64] kernel_basis tensor, or a `BasisSpec` (fused 16-bit path: recomputed inside the kernels)."""
+    if isinstance(basis, BasisSpec):
+        assert basis.es is es, "the BasisSpec belongs to another edge set"
+        return FusedFiberConvFn.apply(x_src, x_dst, basis.pos_src, basis.pos_dst, basis.w1, basis.b1, basis.w2, basis.b2,
+                                      fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, basis.ori3, basis.dim, es, sub)
     return FiberConvFn.apply(x_src, x_dst, basis, fk, wk, bias, ln_g, ln_b, w1, b1, w2, b2, es, sub)
 
 
 def aggregate_messages(x_src, basis, wk, es: EdgeSet) -> torch.Tensor:
     """x1 only (no grad): used by the one-time calibration of conv.py:104-105,151-157."""
+    if isinstance(basis, BasisSpec):
+        basis = basis.materialize()
     x_src, basis = _f32c(x_src.detach()), _f32c(basis.detach())
     wk_t = wk.detach().t().contiguous()
     x1 = torch.empty(es.n_dst, 16, 64, dtype=torch.float32, device=x_src.device)

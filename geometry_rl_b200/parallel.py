@@ -105,6 +105,24 @@ class DataParallel:
             res[k] = t[i]
         return res
 
+    # ---- replica consistency ---------------------------------------------------------------------------
+    def sync_module_state(self, *modules):
+        """Broadcast every parameter and buffer from rank 0 (construction time).  Afterwards replicas only stay identical
+        if every state change is a function of GLOBAL quantities: gradients are all-reduced, and the one-time kernel
+        calibration of FiberBundleConv (conv.py:151-157) takes its std() over all ranks' rows (`global_std`)."""
+        for m in modules:
+            for t in list(m.parameters()) + list(m.buffers()):
+                dist.broadcast(t.data, 0, group=self.group)
+
+    def global_std(self, x: torch.Tensor) -> torch.Tensor:
+        """Unbiased std of the concatenation of every rank's `x` (torch.Tensor.std() semantics) from fp64 moments."""
+        x = x.detach().double()
+        s = torch.stack([x.sum(), (x * x).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+        self.all_reduce(s)
+        n = s[2]
+        var = (s[1] - s[0] * s[0] / n) / (n - 1)
+        return var.clamp_min(0).sqrt().float()
+
     # ---- gradient exchange -----------------------------------------------------------------------------
     def allreduce_grads(self, params: Iterable[torch.nn.Parameter]):
         """ONE flat fp32 bucket, summed (losses already divide by the global count)."""
@@ -124,7 +142,9 @@ class DataParallel:
     def attach(self, loss_module):
         """Install the global-statistics hooks on a TRPLLoss and on every GraphLayerNorm of its critic."""
         from .modules.pyg_models.pyg_compat import GraphLayerNorm
+        from . import ops
         loss_module.dp = self
+        ops.set_calibration_std(self.global_std)  # conv.py:151-157 / ponita.py:178-192 statistics become global
         critic_dp = self.side if self.side is not None else self
         for m in loss_module.critic_network.modules():
             if isinstance(m, GraphLayerNorm):

@@ -211,6 +211,42 @@ int grl_edge_basis_bwd_tc(const GrlBasisDesc* d, grl_stream_t stream);   /* grad
 /* grad_out -> grad_x1 + node partials (two launches: tensor-core MLP/LayerNorm backward, fp32 fibre backward) */
 int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream);
 
+/* Fused edge side of one convolution on the 16-bit tensor-core path (round 2): invariants -> basis MLP -> `kernel`
+ * Linear -> gather * mul -> CSR-ordered segmented sum in ONE kernel, and the mirrored backward.  The edge basis is
+ * recomputed per tile in shared memory; no [E][16][64] basis or basis-gradient tensor exists in HBM.
+ * Replaces hepi.py:76-82,109-123 + ponita/conv.py:84-87,116-149 (forward) and their autograd (backward); supersedes
+ * grl_edge_basis_{fwd,bwd}_tc + grl_fbconv_edge_{fwd,bwd}_tc on the product path.
+ *   forward : entries sorted by DST (edge order), rowptr = dst CSR, n_key = n_dst:
+ *             x1[d] = sum_{e in in(d)} (basis(e) Wk^T) * x_src[src(e)]
+ *   backward: entries sorted by SRC (ties in edge order), rowptr = src CSR, n_key = n_src:
+ *             grad_x_src[s] = grad_x_src_init[s] + sum_{e in out(s)} (basis(e) Wk^T) * grad_x1[dst(e)]
+ *             + one partial slot per CTA with the gradients of kernel.weight and of the basis MLP.
+ * Both directions take the entry list as two plain arrays (e_src[p], e_dst[p]): no dependent index loads.       */
+typedef struct {
+  int32_t n_key, n_edges, dim, n_partials;
+  const int32_t* rowptr;      /* [n_key+1] CSR over the key-sorted entry list                                  */
+  const int32_t* e_src;       /* [E] source node of entry p (row of x_src / pos_src)                           */
+  const int32_t* e_dst;       /* [E] destination node of entry p (row of x1 / grad_x1 / pos_dst)               */
+  const float* pos_src;       /* [n_src][3]                                                                    */
+  const float* pos_dst;       /* [n_dst][3]                                                                    */
+  const float* ori;           /* [16][3] (z = 0 when dim == 2)                                                 */
+  const float* w1;            /* [64][14] basis_fn[1].weight, row-major                                        */
+  const float* b1;            /* [64]                                                                          */
+  const float* w2;            /* [64][64] basis_fn[3].weight, row-major                                        */
+  const float* b2;            /* [64]                                                                          */
+  const float* wk;            /* [64][64] kernel.weight, row-major                                             */
+  const float* x_src;         /* [n_src][16][64]                                                               */
+  float* x1;                  /* forward out: [n_dst][16][64]                                                  */
+  const float* grad_x1;       /* backward in: [n_dst][16][64]                                                  */
+  float* grad_x_src;          /* backward out: [n_src][16][64]                                                 */
+  const float* grad_x_src_init; /* optional [n_src][16][64] added in                                           */
+  float* grad_partials;       /* [n_partials][GRL_FUSED_EDGE_GRAD_FLOATS]; the backward launches n_partials CTAs */
+} GrlFusedEdgeDesc;
+/* partial layout: gWk[64][64] | gW1b[64][16] (columns 0..13 = gW1, column 14 = gb1) | gW2[64][64] | gb2[64] */
+#define GRL_FUSED_EDGE_GRAD_FLOATS (64 * 64 + 64 * 16 + 64 * 64 + 64)
+int grl_fbconv_edge_fused_fwd(const GrlFusedEdgeDesc* d, grl_stream_t stream);
+int grl_fbconv_edge_fused_bwd(const GrlFusedEdgeDesc* d, grl_stream_t stream);
+
 /* *out_bits = bit pattern of max_i |x[i]| (NaNs ignored); feeds GrlConvDesc.grad_amax.  x must be 16-byte aligned. */
 int grl_absmax(const float* x, int64_t n, uint32_t* out_bits, grl_stream_t stream);
 
