@@ -7,9 +7,10 @@ A "step" is one minibatch iteration of examples/torchrl/train.py:259-316 on synt
 config's graph shape: policy forward (graph features -> EMPN/HEPi/transformer -> Gaussian head), TRPL
 projection, TRPLLoss, DeepSets critic forward, both backward passes, (DP: one NCCL gradient all-reduce),
 optional grad-norm clip, two Adam steps.  Prints ONE JSON line (see the task contract): `value` = samples/s
-with minibatches resident in HBM, `e2e` = the same step fed from pinned HOST memory with the loss read back,
-`roofline` = the dominant kernel's algorithmic bytes / CUDA-event duration against MEASURED_PEAKS.json,
-`cpu_baseline` = the CPU oracle port of the same step on this box's host cores (bounded sample).
+with minibatches resident in HBM (default workload: the HEPi headline config), `e2e` = the same
+step fed from pinned HOST memory with a loss read back, `roofline` = the dominant kernel's algorithmic bytes (SURVEY
+8(d) accounting) / CUDA-event duration against MEASURED_PEAKS.json, `cpu_baseline` = the CPU oracle port of the same
+step on this box's host cores (bounded sample), `configs` = the other message-passing workloads, device-timed.
 
 `--impl reference` times that CPU port alone (the reference itself is pure Python on top of torchrl / PyG /
 ITPAL wheels that are not installable offline, so it cannot run unmodified here)."""
@@ -26,7 +27,20 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-DEFAULT_CONFIG = "rigid_pushing_multi_empn_trpl_cfg"  # BASELINE.json configs[1]: 4096 envs x 16 steps, 1 B200
+# BASELINE.json's metric is "HEPi fwd+bwd+TRPL update samples/sec" and BASELINE.md section 4 names config 1
+# (rigid_insertion_multi_hepi_trpl_cfg) as the headline; the other message-passing configs are reported in the same
+# JSON line under "configs".
+DEFAULT_CONFIG = "rigid_insertion_multi_hepi_trpl_cfg"
+# Samples per GPU per step.  The config's own mini_batch_size (1000, configs/rigid_insertion_multi_hepi_trpl_cfg.yaml:138)
+# is launch/latency-bound on a B200 (2.3 ms per step, every kernel a fraction of a wave); the headline fills the machine with
+# 8192 graphs per step (8 of the reference's minibatches: its 1000 x 100 rollout holds 12 such steps per epoch) and the
+# config's own size is reported next to it (configs["...@1000"]).
+DEFAULT_MINIBATCH = {"rigid_insertion_multi_hepi_trpl_cfg": 8192, "rigid_pushing_multi_empn_trpl_cfg": 4096,
+                     "cloth_hanging_multi_hepi_trpl_cfg": 8192, "rope_shaping_hepi_trpl_cfg": 2048}
+# workloads reported under "configs" next to the headline: (config, samples per GPU per step)
+SIDE_WORKLOADS = [("rigid_insertion_multi_hepi_trpl_cfg", 1000), ("rigid_pushing_multi_empn_trpl_cfg", 4096),
+                  ("cloth_hanging_multi_hepi_trpl_cfg", 8192), ("rope_shaping_hepi_trpl_cfg", 2048)]
+MIN_TIMED_STEPS = 200  # the K-step timed region is repeated until at least this many steps were timed; median region reported
 METRIC = "fwd+bwd+TRPL update samples/sec (policy fwd+bwd, TRPL projection, losses, critic, Adam)"  # BASELINE.json metric
 N_ROTATE = 8  # distinct minibatches cycled through the timed region
 _emit = print
@@ -39,7 +53,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)
-    ap.add_argument("--minibatch", type=int, default=0, help="samples per GPU per step (default: the config's)")
+    ap.add_argument("--minibatch", type=int, default=0, help="samples per GPU per step (default: DEFAULT_MINIBATCH, else the config's)")
+    ap.add_argument("--no-side-workloads", action="store_true", help="skip the other configs reported under \"configs\"")
+    ap.add_argument("--repeats", type=int, default=0, help="timed regions of --steps steps each (default: enough for 200 steps)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -105,15 +121,16 @@ class ClockSampler:
 
 def measured_traffic(kernel, workload, minibatch):
     """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture of this same workload (profiles/r01b_traffic.json, written by profiles/summarise.py
+    `ncu --set full` capture of this same workload (profiles/r02_traffic.json, written by profiles/summarise.py
     traffic); None when no capture matches the workload being run."""
-    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
-    if not os.path.exists(p):
-        return None
-    t = json.load(open(p))
-    if t.get("workload") != workload or t.get("minibatch_per_gpu") != minibatch:
-        return None
-    return t.get("kernels", {}).get(kernel)
+    for name in ("r02_traffic.json", "r01b_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        t = json.load(open(p))
+        if t.get("workload") == workload and t.get("minibatch_per_gpu") == minibatch and kernel in t.get("kernels", {}):
+            return t["kernels"][kernel]
+    return None
 
 
 def measured_peaks():
@@ -154,32 +171,47 @@ def workload_shape(cfg, actor, batch, dev, precision):
         return {"latent_mb": float("nan"), "basis_mb": float("nan"), "rows": f"unavailable ({exc})"}
 
 
-# algorithmic HBM bytes of ONE launch of each kernel (DESIGN.md "Kernels"): R = 4096 B latent row
+# algorithmic HBM bytes of ONE launch of each kernel: SURVEY 8(d)'s per-unit figures x the units the launch processes
+# (R = 4096 B fp32 latent row, weights L2-resident and not counted, the edge basis recomputed on the fly and therefore
+# worth ZERO bytes; 40 B per edge = two int64 indices + two positions as SURVEY counts them)
 R = 16 * 64 * 4
 
 
 def kernel_bytes(name, shape):
     n_src, n_dst, E = shape
     return {
-        # basis is recomputable from 2 positions + 2 indices per edge; the materialised [E,R] write is real traffic
-        "grl_edge_basis_fwd": E * (R + 32),
-        "grl_edge_basis_bwd": E * (R + 32),
-        "grl_fbconv_edge_fwd": E * R + n_src * R + n_dst * R + E * 8,
-        "grl_fbconv_node_fwd": 3 * n_dst * R,
-        # x1 read, x_dst read, out write; the x2 row the kernel also saves for the backward pass is a design choice of
-        # this implementation, not compulsory traffic, and is NOT counted (it shows up in `traffic`)
+        # fused 16-bit edge kernels (round 2): unique src rows read + x1 written / g_x1 read, x_src read, g_x_src written
+        "grl_fbconv_edge_fused_fwd": n_src * R + n_dst * R + 40 * E,
+        "grl_fbconv_edge_fused_bwd": 2 * n_src * R + n_dst * R + 40 * E,
+        # node update: x1 read, x_dst read, out write (forward); grad_out read, x2 read, g_x1 write (backward).  The x2 row
+        # the forward saves and the g_x2 round trip between the two backward kernels are implementation choices and are
+        # NOT counted (they show up in `traffic`)
         "grl_fbconv_node_fwd_tc": 3 * n_dst * R,
-        "grl_absmax": n_dst * R,
-        # bf16 path: basis / grad_basis rows are 2 KB (R / 2)
-        "grl_edge_basis_fwd_tc": E * (R // 2 + 32),
-        "grl_edge_basis_bwd_tc": E * (R // 2 + 32),
-        "grl_fbconv_edge_fwd_tc": E * R // 2 + n_src * R + n_dst * R + E * 8,
-        "grl_fbconv_edge_bwd_tc": 2 * E * R // 2 + 2 * n_src * R + n_dst * R + E * 12,
+        "grl_fbconv_node_bwd_tc": 3 * n_dst * R,
+        "grl_fbconv_node_fwd": 3 * n_dst * R,
         "grl_fbconv_node_bwd": 3 * n_dst * R,
-        "grl_fbconv_node_bwd_tc": 5 * n_dst * R,  # x2, grad_out read, g_x2 write + (fibre kernel) g_x2 re-read, g_x1 write
-                                                   # (the fibre kernel's x1 read, 1 more R per node, is not counted)
-        "grl_fbconv_edge_bwd": 2 * E * R + 2 * n_src * R + n_dst * R + E * 12,
+        "grl_absmax": n_dst * R,
+        # round-1 kernels with a materialised basis (GRL_FUSED_EDGE=0 / strict fp32 path): by SURVEY 8(d) the basis rows are
+        # not compulsory traffic, so they are not counted here either
+        "grl_edge_basis_fwd": 40 * E, "grl_edge_basis_bwd": 40 * E,
+        "grl_edge_basis_fwd_tc": 40 * E, "grl_edge_basis_bwd_tc": 40 * E,
+        "grl_fbconv_edge_fwd": n_src * R + n_dst * R + 8 * E,
+        "grl_fbconv_edge_fwd_tc": n_src * R + n_dst * R + 8 * E,
+        "grl_fbconv_edge_bwd": 2 * n_src * R + n_dst * R + 12 * E,
+        "grl_fbconv_edge_bwd_tc": 2 * n_src * R + n_dst * R + 12 * E,
     }.get(name)
+
+
+def resolve_minibatch(args, cfg_name, cfg):
+    return args.minibatch or DEFAULT_MINIBATCH.get(cfg_name, cfg.mini_batch_size)
+
+
+def config_block(args, cfg_name, cfg, B, world):
+    """The `config` object of the JSON line; identical for our arm and the reference arm (same workload, same sizes)."""
+    return {"workload": cfg_name, "body": cfg.model, "minibatch_per_gpu": B, "global_minibatch": B * world,
+            "parallelism": f"dp{world}",
+            "inputs": f"{N_ROTATE} distinct synthetic minibatches rotated through the timed region; the per-step working "
+                      f"set (hundreds of MB of latents) exceeds the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,7 +226,7 @@ def cpu_step_rate(cfg, sample, steps, warmup, seed=0):
     actor, critic, _, _, _ = learner.build_agent(cfg, "cpu", seed=seed)
     agent = OracleAgent(cfg, actor.state_dict(), critic.state_dict())
     gen = torch.Generator().manual_seed(1234)
-    obs = synthetic_obs(cfg, sample, gen, env_ids=torch.arange(sample) * max(1, cfg.num_envs // sample))
+    obs = synthetic_obs(cfg, sample, gen, env_ids=torch.arange(sample) * max(1, cfg.num_envs // sample) % cfg.num_envs)
     mb = make_minibatch(cfg, agent, obs, gen)
     params = [p for p in list(agent.actor.values()) + list(agent.critic.values()) if p.is_floating_point()]
     opt = torch.optim.Adam(params, lr=cfg.lr, eps=1e-5)
@@ -212,21 +244,28 @@ def cpu_step_rate(cfg, sample, steps, warmup, seed=0):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path, timed on the box's host cores with every thread torch can
+    use.  The reference cannot be installed or imported here (torchrl / tensordict / PyG / ITPAL wheels are absent and
+    /root/reference does not exist on the GPU box), so this is the CPU oracle port of the same step (kind = "port").
+    Same workload, sizes, K and W as our arm; each step is a bounded sample (`--cpu-sample` graphs of the same synthetic
+    minibatch) so that the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     from geometry_rl_b200.synthetic import CONFIGS
     cfg = CONFIGS[args.config]
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
-    rate, cores, sec = cpu_step_rate(cfg, args.cpu_sample, steps, warmup)
+    B = resolve_minibatch(args, args.config, cfg)
+    rate, cores, sec = cpu_step_rate(cfg, args.cpu_sample, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "minibatch_per_step": args.cpu_sample},
+        "config": config_block(args, args.config, cfg, B, world),
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} update steps of {args.cpu_sample} samples (oracle/step.py, torch CPU fp32, "
-                                   f"fp64 KL dual solve instead of ITPAL)"},
+                         "sample": f"{args.steps} update steps of {args.cpu_sample} graphs each after {args.warmup} warm-up steps "
+                                   f"(a bounded sample of the {B}-graph minibatch; oracle/step.py = torch CPU fp32 restatement "
+                                   f"of the reference step, fp64 KL dual solve instead of ITPAL)"},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -236,21 +275,21 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=True):
-    """Build a fresh agent for `precision`, time `steps` updates device-resident and end-to-end, and (rank 0)
-    time every kernel with CUDA events.  Returns a dict of results (meaningful on rank 0)."""
+def measure(args, cfg_name, B, precision, dev, dp, rank, world, local, steps, full=True):
+    """Build a fresh agent, capture the update, time `repeats` regions of exactly `steps` replayed updates with inputs
+    resident in HBM (median region reported) and, with `full`, the end-to-end figure from pinned host memory plus the
+    per-kernel CUDA-event pass.  Returns a dict of results (meaningful on rank 0)."""
     import torch.distributed as dist
     from geometry_rl_b200 import _lib, learner, ops
     from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs
     from geometry_rl_b200.tensors import to_device
 
-    # strict mode: fp32 everywhere.  bf16 mode: the library GEMMs of the DeepSets critic / heads may use TF32, as the
-    # reference itself does on GPU (examples/torchrl/train.py:29-30)
-    torch.backends.cuda.matmul.allow_tf32 = precision == "bf16"
-    torch.backends.cudnn.allow_tf32 = precision == "bf16"
+    # only the message-passing MLP contractions are 16-bit (north_star); the library GEMMs of the DeepSets critic and of
+    # the Gaussian head stay fp32 (no TF32), so the critic branch keeps fp32 parity in both modes
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     ops.set_precision(precision)
-    cfg = CONFIGS[args.config]
-    B = args.minibatch or cfg.mini_batch_size
+    cfg = CONFIGS[cfg_name]
     actor, critic, projection, loss_module, adv_module = learner.build_agent(cfg, dev, seed=0)  # same init on all ranks
     lrn = learner.Learner(cfg, actor, critic, loss_module, dp=dp)
 
@@ -261,14 +300,13 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
         # slot j always belongs to the same env block -> the same geometry as the cached topology of slot j
         env_ids = (torch.arange(B) * max(1, cfg.num_envs // B) + rank) % cfg.num_envs
         obs = synthetic_obs(cfg, B, gen, env_ids=env_ids)
+        if i == 0:
+            lrn.calibrate(to_device(obs, dev))  # one-time kernel calibration (global statistics under DP)
         with torch.no_grad():
-            dist_ = actor.get_dist(to_device(obs, dev))  # first call also runs the one-time calibration
+            dist_ = actor.get_dist(to_device(obs, dev))
             v = critic.module(*[obs[k].to(dev) for k in critic.in_keys])
         mb = synthetic_minibatch(obs, dist_.mean, dist_.var_diag, v, gen)
         host_batches.append({k: t.pin_memory() for k, t in mb.items()})
-    if dp is not None:  # calibration changed kernel weights from rank-local data: make replicas identical again
-        for p in list(actor.parameters()) + list(critic.parameters()):
-            dist.broadcast(p.data, 0)
     dev_batches = [to_device(b, dev) for b in host_batches]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0].values())
 
@@ -290,105 +328,136 @@ def measure(args, precision, dev, dp, rank, world, local, steps, with_profile=Tr
     launches_per_step = None
     if use_graph:
         c0 = _lib.launch_count
-        lrn.capture(dev_batches[0], warmup=max(args.warmup, 3))
-        launches_per_step = (_lib.launch_count - c0) // (max(args.warmup, 3) + 1)
+        n_cap = max(args.warmup, 3)
+        lrn.capture(dev_batches[0], warmup=n_cap)
+        launches_per_step = (_lib.launch_count - c0) // (n_cap + 1)
         step = lrn.update_graphed
     else:
         step = lrn.update
     for i in range(args.warmup):
         step(dev_batches[i % N_ROTATE])
+    repeats = args.repeats or max(1, -(-MIN_TIMED_STEPS // steps))
+    if not full:
+        repeats = min(repeats, 3)
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
+    if rank == 0 and full:
         sampler.start()
     launches0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    regions = []
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed steps
-    e0.record()
-    for i in range(steps):
-        out = step(dev_batches[i % N_ROTATE])
-    e1.record()
-    barrier()
+    for r in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            out = step(dev_batches[i % N_ROTATE])
+        e1.record()
+        barrier()
+        regions.append(max_over_ranks(e0.elapsed_time(e1)))
     torch.cuda.profiler.stop()
-    launches = launches_per_step * steps if use_graph else _lib.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = launches_per_step * steps if use_graph else (_lib.launch_count - launches0) // repeats
+    clocks = sampler.stop() if (rank == 0 and full) else None
+    ms = sorted(regions)[len(regions) // 2]  # median K-step region (each region is exactly K steps, max over ranks)
     res = {"precision": precision, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
-           "clocks": clocks, "gpu_launches": launches, "cuda_graph": use_graph, "B": B, "model": cfg.model}
+           "clocks": clocks, "gpu_launches": launches, "cuda_graph": use_graph, "B": B, "model": cfg.model,
+           "regions_ms": [round(x, 3) for x in regions]}
     res.update(workload_shape(cfg, actor, host_batches[0], dev, precision))
+    if not full:
+        del lrn, actor, critic, loss_module, dev_batches, host_batches
+        torch.cuda.empty_cache()
+        return res
 
     # ---- end to end: pinned host minibatch -> H2D -> step -> loss scalar D2H, every step ----------------
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
-    s0.record()
+    e2e_regions = []
     loss_host = 0.0
-    if use_graph:
-        lrn.prefetch(host_batches[0])
-    for i in range(steps):
+    for r in range(min(repeats, 5)):
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        s0.record()
         if use_graph:
-            # pinned host -> staging (H2D on a copy stream, issued one step ahead so it runs under the previous update)
-            # -> the graph's static inputs (D2D) -> replay -> read the loss back.  Every step's inputs cross PCIe inside
-            # the timed region; the copy of step i+1 overlaps the compute of step i.
-            out = lrn.update_prefetched(host_batches[(i + 1) % N_ROTATE] if i + 1 < steps else None)
-        else:
-            out = step({k: t.to(dev, non_blocking=True) for k, t in host_batches[i % N_ROTATE].items()})
-        loss_host = float(out["actor_loss"].item())  # device -> host read of the step's result
-    s1.record()
-    barrier()
-    e2e_ms = max_over_ranks(max(s0.elapsed_time(s1), (time.perf_counter() - t_wall) * 1e3 if dp is None else 0.0))
+            lrn.prefetch(host_batches[0])
+        for i in range(steps):
+            if use_graph:
+                # pinned host -> staging (H2D on a copy stream, issued one step ahead so it runs under the previous update)
+                # -> the graph's static inputs (D2D) -> replay -> read the loss back.  Every step's inputs cross PCIe inside
+                # the timed region; the copy of step i+1 overlaps the compute of step i.
+                out = lrn.update_prefetched(host_batches[(i + 1) % N_ROTATE] if i + 1 < steps else None)
+            else:
+                out = step({k: t.to(dev, non_blocking=True) for k, t in host_batches[i % N_ROTATE].items()})
+            loss_host = float(out["loss_trust_region"].item())  # device -> host read of the step's result
+        s1.record()
+        barrier()
+        e2e_regions.append(max_over_ranks(max(s0.elapsed_time(s1), (time.perf_counter() - t_wall) * 1e3 if dp is None else 0.0)))
+    e2e_ms = sorted(e2e_regions)[len(e2e_regions) // 2]
     res["e2e"] = {"value": B * world * steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
-                  "d2h_bytes_per_step": 4, "last_actor_loss": loss_host}
+                  "d2h_bytes_per_step": 4, "last_loss_trust_region": loss_host}
 
     # ---- per-kernel CUDA-event pass (same steps, eager, events around every C-ABI launch) -------------------
     res["roofline"] = None
-    if with_profile:
-        n_prof = min(steps, 5)
-        if rank == 0:
-            _lib.event_timing(True)
-        for i in range(n_prof):  # every rank runs the steps (they contain collectives); only rank 0 records events
-            lrn.update(dev_batches[i % N_ROTATE])
-        torch.cuda.synchronize()
-        if rank == 0:
-            per_kernel = _lib.event_timing(False)  # name -> list of (ms, n_src, n_dst, n_edges)
-            tot = {k: sum(x[0] for x in v) for k, v in per_kernel.items()}
-            step_kernel_ms = sum(tot.values())
-            top = max(tot, key=tot.get)
-            peak, peak_src = measured_peaks()
-            # average over the launches of the dominant kernel: algorithmic bytes of each launch / its duration
-            ab = sum(kernel_bytes(top, x[1:]) or 0 for x in per_kernel[top])
-            dur = tot[top] * 1e-3
-            achieved = ab / dur / 1e9 if dur > 0 else 0.0
-            res["roofline"] = {
-                "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic(top, args.config, B), "peak_source": peak_src, "avg_launch_ms": tot[top] / len(per_kernel[top]),
-                "launches_per_step": len(per_kernel[top]) / n_prof, "algorithmic_bytes_per_launch": ab / len(per_kernel[top]),
-                "share_of_kernel_time": tot[top] / step_kernel_ms,
-                "kernel_ms_per_step": {k: round(v / n_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}}
+    n_prof = min(steps, 5)
+    if rank == 0:
+        _lib.event_timing(True)
+    for i in range(n_prof):  # every rank runs the steps (they contain collectives); only rank 0 records events
+        lrn.update(dev_batches[i % N_ROTATE])
+    torch.cuda.synchronize()
+    if rank == 0:
+        per_kernel = _lib.event_timing(False)  # name -> list of (ms, n_src, n_dst, n_edges)
+        tot = {k: sum(x[0] for x in v) for k, v in per_kernel.items()}
+        step_kernel_ms = sum(tot.values())
+        top = max(tot, key=tot.get)
+        peak, peak_src = measured_peaks()
+        # average over the launches of the dominant kernel: algorithmic bytes of each launch / its duration
+        ab = sum(kernel_bytes(top, x[1:]) or 0 for x in per_kernel[top])
+        dur = tot[top] * 1e-3
+        achieved = ab / dur / 1e9 if dur > 0 else 0.0
+        fracs = {}
+        for k, v in per_kernel.items():
+            kb = sum(kernel_bytes(k, x[1:]) or 0 for x in v)
+            if kb:
+                fracs[k] = round(kb / (tot[k] * 1e-3) / 1e9 / peak, 4)
+        res["roofline"] = {
+            "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": measured_traffic(top, cfg_name, B), "peak_source": peak_src,
+            "accounting": "SURVEY 8(d): unique latent rows in/out + 40 B per edge; the recomputed edge basis counts zero bytes",
+            "avg_launch_ms": tot[top] / len(per_kernel[top]), "launches_per_step": len(per_kernel[top]) / n_prof,
+            "algorithmic_bytes_per_launch": ab / len(per_kernel[top]), "share_of_kernel_time": tot[top] / step_kernel_ms,
+            "kernel_ms_per_step": {k: round(v / n_prof, 4) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])},
+            "frac_by_kernel": fracs}
     del lrn, actor, critic, loss_module, dev_batches, host_batches
     torch.cuda.empty_cache()
     return res
 
 
 def gae_rate(dev, B, T, iters=50):
-    """grl_gae_scan alone ('GAE reported separately'): frames/s and achieved GB/s at 18 B per frame."""
-    from geometry_rl_b200 import ops
+    """grl_gae_scan alone through the C ABI on pre-converted inputs ('GAE reported separately'), at a size
+    whose 18 B per frame exceed the L2: frames/s and achieved GB/s against the measured HBM peak."""
+    import ctypes as C  # noqa: F401
+    from geometry_rl_b200 import _lib as L
     g = torch.Generator().manual_seed(3)
     r, v = torch.randn(B, T, generator=g).to(dev), torch.randn(B, T + 1, generator=g).to(dev)
-    done = torch.zeros(B, T, dtype=torch.bool, device=dev)
-    done[:, -1] = True
+    done = torch.zeros(B, T, dtype=torch.uint8, device=dev)
+    done[:, -1] = 1
+    adv, vt = torch.empty_like(r), torch.empty_like(r)
+
+    def call():
+        L.call("grl_gae_scan", L.ptr(r), L.ptr(v), L.ptr(done), L.ptr(done), 0.99, 0.95, B, T, L.ptr(adv), L.ptr(vt))
     for _ in range(3):
-        ops.gae(r, v, done, done, 0.99, 0.95)
+        call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(iters):
-        ops.gae(r, v, done, done, 0.99, 0.95)
+        call()
     e1.record()
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) * 1e-3 / iters
-    return {"frames_per_s": B * T / sec, "B_env": B, "T": T, "us_per_call": sec * 1e6, "GBps_at_18B_per_frame": 18 * B * T / sec / 1e9,
-            "note": "host call included (dtype conversions + one launch): launch-latency bound at these rollout sizes; kernel = one warp per env, Kogge-Stone scan along T"}
+    peak, _ = measured_peaks()
+    gbs = 18 * B * T / sec / 1e9
+    return {"frames_per_s": B * T / sec, "B_env": B, "T": T, "us_per_call": sec * 1e6, "GBps_at_18B_per_frame": gbs,
+            "frac_of_hbm_peak": gbs / peak,
+            "note": "kernel alone (one warp per env, Kogge-Stone scan of affine maps along T); 18 B per frame = 151 MB per call"}
 
 
 def run_ours(args):
@@ -411,50 +480,62 @@ def run_ours(args):
         from geometry_rl_b200.parallel import DataParallel
         dp = DataParallel(side_group=not args.no_dp_overlap)
     cfg = CONFIGS[args.config]
+    B = resolve_minibatch(args, args.config, cfg)
 
-    main_res = measure(args, args.precision, dev, dp, rank, world, local, args.steps)
-    # the other precision mode of the same path, measured in the same run (fewer steps; no per-kernel pass)
+    main_res = measure(args, args.config, B, args.precision, dev, dp, rank, world, local, args.steps)
+    # the other precision mode of the same path, measured in the same run (one region; no per-kernel pass)
     other = "fp32" if args.precision == "bf16" else "bf16"
     other_res = None
     if not args.single_precision and cfg.model != "transformer":
-        other_res = measure(args, other, dev, dp, rank, world, local, min(args.steps, 5), with_profile=False)
+        other_res = measure(args, args.config, B, other, dev, dp, rank, world, local, min(args.steps, 5), full=False)
+    side = {}
+    if not args.no_side_workloads:
+        for name, b in SIDE_WORKLOADS:
+            if (name, b) == (args.config, B):
+                continue
+            try:
+                r = measure(args, name, b, args.precision, dev, dp, rank, world, local, args.steps, full=False)
+                side[f"{name}@{b}"] = {"value": r["value"], "unit": "samples/s", "ms_per_step": r["ms_per_step"],
+                                       "minibatch_per_gpu": b, "global_minibatch": b * world, "steps": r["steps"],
+                                       "regions_ms": r["regions_ms"], "rows": r["rows"]}
+            except Exception as exc:  # a side workload must not take the headline down
+                side[f"{name}@{b}"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rate, cores, sec = cpu_step_rate(cfg, args.cpu_sample, 2, 1)
+        rate, cores, sec = cpu_step_rate(cfg, args.cpu_sample, 3, 1)
         cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"2 update steps of {args.cpu_sample} samples after 1 warm-up (oracle/step.py: torch CPU fp32 "
-                         f"restatement of the reference step, fp64 KL dual solve instead of ITPAL), {sec:.2f} s/step"}
+               "sample": f"3 update steps of {args.cpu_sample} graphs after 1 warm-up (a bounded sample of the {B}-graph minibatch; "
+                         f"oracle/step.py: torch CPU fp32 restatement of the reference step, fp64 KL dual solve instead of "
+                         f"ITPAL), {sec:.2f} s/step"}
 
     if rank == 0:
-        B = main_res["B"]
         line = {
             "metric": METRIC, "value": main_res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": args.config, "model": cfg.model, "mlp_precision": args.precision,
-                       "parity": "1e-5 vs reference fp32" if args.precision == "fp32" else
-                                 "1e-2 vs reference fp32 (north_star bf16 MLP path: 16-bit tcgen05 operands - fp16 in the node kernels with "
-                                 "power-of-two scaled gradients, bf16 in the edge kernels - fp32 accumulation; latents, LayerNorm, "
-                                 "segmented sums, projection, losses fp32)",
-                       "cuda_graph": main_res["cuda_graph"], "minibatch_per_gpu": B, "global_minibatch": B * world,
-                       "parallelism": f"dp{world}", "l2": f"rotating {N_ROTATE} minibatches; per-step working set "
-                       f"(latent tensors of {main_res['latent_mb']:.0f} MB each, edge basis {main_res['basis_mb']:.0f} MB) "
-                       f"exceeds the 126 MB L2",
-                       "rows": main_res["rows"]},
+            "config": config_block(args, args.config, cfg, B, world),
+            "details": {"mlp_precision": args.precision,
+                        "parity": "1e-5 vs reference fp32" if args.precision == "fp32" else
+                                  "1e-2 vs reference fp32 (north_star 16-bit MLP path: tcgen05 operands in fp16 / bf16, fp32 "
+                                  "accumulation; latents, LayerNorm, segmented sums, projection, losses fp32; "
+                                  "tests/test_gpu_step16.py)",
+                        "cuda_graph": main_res["cuda_graph"], "rows": main_res["rows"],
+                        "timing": f"{len(main_res['regions_ms'])} timed regions of exactly {args.steps} steps each (barrier + "
+                                  f"synchronize on both sides, CUDA events, max over ranks); value = median region",
+                        "regions_ms": main_res["regions_ms"],
+                        "latent_mb": main_res["latent_mb"]},
             "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
-            "roofline": main_res["roofline"], "cpu_baseline": cpu,
+            "roofline": main_res["roofline"], "cpu_baseline": cpu, "configs": side,
         }
         try:
-            # BASELINE.json quotes config 2 at 4096 envs x 16 steps; the other configs use their own rollout shape
-            line["gae"] = gae_rate(dev, 4096 if args.config == DEFAULT_CONFIG else cfg.num_envs,
-                                   16 if args.config == DEFAULT_CONFIG else cfg.rollout_len)
+            line["gae"] = gae_rate(dev, 65536, 128)
         except Exception as exc:  # reporting only
             line["gae"] = {"error": str(exc)}
         if other_res is not None:
             line["other_precision"] = {"mlp_precision": other, "dtype": "f32" if other == "fp32" else "bf16",
                                        "value": other_res["value"], "unit": "samples/s", "ms_per_step": other_res["ms_per_step"],
-                                       "steps": other_res["steps"], "e2e": other_res["e2e"]["value"],
+                                       "steps": other_res["steps"],
                                        "parity": "1e-5 vs reference fp32" if other == "fp32" else "1e-2 vs reference fp32"}
         _emit(json.dumps(line))
     if dp is not None:
@@ -463,7 +544,7 @@ def run_ours(args):
 
 def main():
     args = parse()
-    # the contract is ONE JSON line on stdout: library chatter (e.g. the reference's "Callibrating...") goes to stderr
+    # the contract is ONE JSON line on stdout: library chatter goes to stderr
     real_stdout = sys.stdout
     sys.stdout = sys.stderr
     global _emit

@@ -51,7 +51,7 @@ class GrlFusedEdgeDesc(C.Structure):
     _fields_ = [("n_key", _i32), ("n_edges", _i32), ("dim", _i32), ("n_partials", _i32),
                 ("rowptr", _fp), ("e_src", _fp), ("e_dst", _fp), ("pos_src", _fp), ("pos_dst", _fp), ("ori", _fp),
                 ("w1", _fp), ("b1", _fp), ("w2", _fp), ("b2", _fp), ("wk", _fp), ("x_src", _fp), ("x1", _fp),
-                ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp), ("grad_partials", _fp)]
+                ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp), ("grad_partials", _fp), ("n_other", _i32)]
 
 
 class GrlProjDesc(C.Structure):
@@ -117,6 +117,7 @@ SIGNATURES = {
     "grl_readout_bwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_trpl_loss_fwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),
     "grl_trpl_loss_bwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),
+    "grl_dp_combine": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     "grl_absmax": (C.c_int, [_fp, C.c_int64, _fp, _fp]),
     "grl_reduce_partials": (C.c_int, [_fp, C.c_int, C.c_int64, _fp, C.c_int, _fp]),
     "grl_gae_scan": (C.c_int, [_fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_int, C.c_int, _fp, _fp, _fp]),

@@ -110,7 +110,7 @@ class TRPLLoss(nn.Module):
             td_get(td, "sample_log_prob"), advantage, pr.mean_bound, pr.cov_bound, pr.KERNEL_TYPE,
             self.entropy_coef if self.entropy_bonus else 0.0, pr.trust_region_coeff,
             self.normalize_advantage and advantage.numel() * (1 if self.dp is None else self.dp.world_size) > 1,
-            None if self.dp is None else self.dp.all_reduce_named)
+            None if self.dp is None else self.dp.all_gather_small)
         ix = _lib.LOSS_SCALAR_INDEX
         out = {"loss_objective": l_obj, "loss_trust_region": l_tr}
         if self.entropy_bonus:

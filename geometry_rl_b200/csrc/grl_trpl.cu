@@ -291,13 +291,27 @@ __device__ __forceinline__ double block_max(double x, double* sh) {
   return x;
 }
 
+// Data parallel: out[i] = sum_r gathered[r][i] (i < n_sum) | max_r gathered[r][i] (i >= n_sum), ranks visited in rank
+// order, so every rank computes bit-identical statistics from ONE all-gather per loss stage.
+__global__ void dp_combine_kernel(const double* __restrict__ gathered, int world, int n, int n_sum, double* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  double acc = gathered[i];
+  for (int r = 1; r < world; ++r) {
+    const double v = gathered[(size_t)r * n + i];
+    acc = i < n_sum ? acc + v : fmax(acc, v);
+  }
+  out[i] = acc;
+}
+
 // stats  = { sum A, sum A^2, n, max log_w, loc, 1 / scale }          (entries 0-3: stage 1; 4-5: stage 2)
 // sums   = { [0] sum exp(lw) A_hat, [1] sum (tr_mean + tr_cov), [2] sum H_dist      -> this rank's share of the losses
 //            [3] sum e, [4] sum e^2 (e = exp(lw - max)), [5] sum tr_mean, [6] sum tr_cov, [7] sum kl, [8] sum H_p,
 //            [9] sum (H_proj - H_p)                                                   -> summed over ranks
 //            [10] max tr_mean, [11] max tr_cov }                                      -> max over ranks
-// Between the stages a data-parallel caller all-reduces stats[0:3] (sum), stats[3] (max), sums[3:10] (sum) and
-// sums[10:12] (max); a single process runs the three stages back to back.
+// Between the stages a data-parallel caller makes stats[0:3] (sum), stats[3] (max), sums[3:10] (sum) and sums[10:12] (max)
+// global: one all-gather of stats[0:4] resp. sums[3:12] + grl_dp_combine per stage; a single process runs the three
+// stages back to back.
 __global__ void __launch_bounds__(kLossThreads) trpl_loss_stats_kernel(const GrlLossDesc d) {
   __shared__ double sh[32];
   const int B = d.batch, tid = threadIdx.x;
@@ -468,6 +482,13 @@ int grl_trpl_loss_fwd(const GrlLossDesc* d, grl_stream_t stream) {
   if (d->stage == 0 || d->stage == 2) grl::trpl_loss_sums_kernel<<<1, grl::kLossThreads, 0, st>>>(*d);
   if (d->stage == 0 || d->stage == 3) grl::trpl_loss_finalize_kernel<<<1, 32, 0, st>>>(*d);
   return grl::check_launch("grl_trpl_loss_fwd");
+}
+
+int grl_dp_combine(const double* gathered, int world, int n, int n_sum, double* out, grl_stream_t stream) {
+  GRL_REQUIRE(gathered && out && world > 0 && n > 0 && n <= 32 && n_sum >= 0 && n_sum <= n, GRL_EINVAL,
+              "grl_dp_combine: world=%d n=%d n_sum=%d", world, n, n_sum);
+  grl::dp_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered, world, n, n_sum, out);
+  return grl::check_launch("grl_dp_combine");
 }
 
 int grl_trpl_loss_bwd(const GrlLossDesc* d, grl_stream_t stream) {

@@ -5,9 +5,51 @@
 #include <utility>
 #include <vector>
 
+#include <cuda.h>
+
 #include "grl_common.cuh"
 
 namespace grl {
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query: the library links no libcuda symbol.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Tensor map over a latent tensor viewed as [n_nodes * 16 orientation rows][64 fp32]: box = 16 rows x 32 channels
+// (one node, one channel half = 2 KB), SWIZZLE_128B: the 16-byte chunk c of row r lands at chunk position c ^ (r & 7)
+// of its 128-byte line, so threads that own one ROW each (TMEM lane = row) read any chunk conflict-free.
+int make_row_tensor_map(void* out, const float* base, long long n_nodes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GRL_ECUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)kC, (cuuint64_t)n_nodes * kO};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kC * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)kO};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, %lld nodes)", (int)r, (const void*)base, n_nodes);
+    return GRL_ECUDA;
+  }
+  return GRL_OK;
+}
 
 static thread_local char g_err[512] = "";
 

@@ -263,6 +263,10 @@ class Learner:
         with torch.cuda.graph(self._graph):
             self._graph_out = self.update(self._static)
         self.num_network_updates -= 1  # the capture pass did not execute
+        # the graph replays kernels that read the topology tensors of THIS batch size: keep them alive even if the data
+        # builders later drop their placeholder (batch-size change, invalidate())
+        self._captured_topology = [m.hyper_data.example_data for net in modules for m in net.modules()
+                                   if getattr(m, "hyper_data", None) is not None]
         return self
 
     def update_static(self):
@@ -283,10 +287,11 @@ class Learner:
         if not graphed:
             return run_minibatch_epochs(self.update, buffer, epochs)
         if self._graph is None:
-            first = next(iter(buffer.sample_indices()))
-            if first.numel() != buffer.batch_size:
+            if len(buffer) < buffer.batch_size:
                 raise ValueError("the buffer holds less than one full minibatch; use graphed=False")
-            self.capture({k: v.index_select(0, first) for k, v in buffer._storage.items()})
+            # example batch = the first stored frames (shapes and topology slots only; capture() undoes its warm-up
+            # updates, and the sampler's random stream is left untouched)
+            self.capture({k: v[:buffer.batch_size] for k, v in buffer._storage.items()})
 
         def step(mb):
             return self.update_static() if mb is self._static else self.update(mb)

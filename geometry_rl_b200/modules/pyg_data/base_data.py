@@ -55,8 +55,12 @@ class BaseData:
             # (rigid_tasks_data.py:302-312) and no shipped config selects it
             raise NotImplementedError("knn_to_actuators_k > 0 is not reachable with the shipped configs")
         self.node_type_list = self._kept_node_types()
-        # one cached topology per batch size (the reference keeps only the last one and rebuilds whenever the
-        # batch size changes, rigid_tasks_data.py:254-255; each is still "built once from the first batch seen")
+        # The reference keeps ONE placeholder and rebuilds it whenever the incoming batch size differs from the last one
+        # (rigid_tasks_data.py:254-255), i.e. at every rollout <-> minibatch size alternation.  Same rule here: the dict
+        # holds a single entry unless `cache_all_sizes` is switched on (then the caller owns staleness: `invalidate()` at
+        # every rollout -> update boundary restores the reference's refresh points).  A captured CUDA graph
+        # (Learner.capture) holds the topology tensors it was recorded with: re-capture after an invalidation.
+        self.cache_all_sizes = False
         self._placeholders: Dict[int, GraphBatch] = {}
         self._example_data: Optional[GraphBatch] = None
 
@@ -89,7 +93,14 @@ class BaseData:
         if cached is not None:
             self._example_data = cached
             return False
+        if not self.cache_all_sizes:
+            self._placeholders.clear()  # `len(self.example_data) != batch_size` -> rebuild, the old one is dropped
         return True
+
+    def invalidate(self) -> None:
+        """Drop every cached topology: the next `build_data` rebuilds it from the batch it is given."""
+        self._placeholders.clear()
+        self._example_data = None
 
     # ---- obs splitting (rigid_tasks_data.py:93-150) ---------------------------------------------------
     def _preprocess_input(self, scalars, position_vectors, velocity_vectors, norm_position_vectors,

@@ -164,7 +164,9 @@ def knn_graph(pos: torch.Tensor, num_valid: Optional[torch.Tensor], k: int):
     pos = _f32c(pos)
     B, P, _ = pos.shape
     if num_valid is not None:
-        num_valid = num_valid.to(torch.int32).contiguous()
+        num_valid = num_valid.to(torch.int32).clamp(0, P).contiguous()  # the kernels clamp too: keep the edge counts in step
+    if not bool(torch.isfinite(pos).all()):  # a NaN distance never wins a comparison: edge_ptr would count edges that are not written
+        raise ValueError("knn_graph: non-finite positions (topology is built off the step path, so this check is free)")
     edge_ptr = knn_edge_ptr(num_valid, B, P, k, pos.device)
     E = int(edge_ptr[-1].item())  # topology is built once per batch size; this sync is off the step path
     coo = torch.empty(2, max(E, 1), dtype=torch.int64, device=pos.device)
@@ -190,7 +192,7 @@ def dense_edges(mode: int, B: int, n_src: int, n_dst: int, device, num_valid: Op
     if mode == 0:
         counts = torch.full((B,), n_src * (n_src - 1), dtype=torch.int64, device=device)
     else:
-        nv = (num_valid.to(torch.int64) if num_valid is not None
+        nv = (num_valid.to(torch.int64).clamp(0, n_src) if num_valid is not None  # the kernel clamps to [0, n_src] as well
               else torch.full((B,), n_src, dtype=torch.int64, device=device))
         counts = nv * n_dst
     edge_ptr = torch.zeros(B + 1, dtype=torch.int64, device=device)
@@ -198,7 +200,7 @@ def dense_edges(mode: int, B: int, n_src: int, n_dst: int, device, num_valid: Op
     E = int(edge_ptr[-1].item())
     coo = torch.empty(2, max(E, 1), dtype=torch.int64, device=device)
     if E > 0:
-        nvp = num_valid.to(torch.int32).contiguous() if num_valid is not None else None
+        nvp = num_valid.to(torch.int32).clamp(0, n_src).contiguous() if num_valid is not None else None
         L.call("grl_dense_edges", mode, L.ptr(nvp), L.ptr(edge_ptr), B, n_src, n_dst, L.ptr(coo), coo.stride(0))
     return coo[:, :E], edge_ptr
 
@@ -394,7 +396,7 @@ class FusedFiberConvFn(torch.autograd.Function):
         x1 = torch.empty(top.n_dst, 16, 64, dtype=torch.float32, device=dev)
         out = torch.empty(top.n_dst, 16, 64, dtype=torch.float32, device=dev)
         shape = (top.n_src, top.n_dst, top.n_edges)
-        fd = L.GrlFusedEdgeDesc(n_key=top.n_dst, n_edges=top.n_edges, dim=dim, n_partials=0, rowptr=L.ptr(top.rowptr_dst),
+        fd = L.GrlFusedEdgeDesc(n_key=top.n_dst, n_other=top.n_src, n_edges=top.n_edges, dim=dim, n_partials=0, rowptr=L.ptr(top.rowptr_dst),
                                 e_src=L.ptr(top.edge_src), e_dst=L.ptr(top.edge_dst), pos_src=L.ptr(pos_src),
                                 pos_dst=L.ptr(pos_dst), ori=L.ptr(ori3), w1=L.ptr(bw1_c), b1=L.ptr(bb1_c), w2=L.ptr(bw2_c),
                                 b2=L.ptr(bb2_c), wk=L.ptr(wk_c), x_src=L.ptr(x_src), x1=L.ptr(x1))
@@ -438,7 +440,7 @@ class FusedFiberConvFn(torch.autograd.Function):
         s_src, s_dst = src_sorted_pairs(es, sub)
         n_pe = _n_partials(top.n_src)
         edge_part = torch.empty(n_pe, L.FUSED_EDGE_GRAD_FLOATS, dtype=torch.float32, device=dev)
-        fd = L.GrlFusedEdgeDesc(n_key=top.n_src, n_edges=top.n_edges, dim=dim, n_partials=n_pe, rowptr=L.ptr(top.rowptr_src),
+        fd = L.GrlFusedEdgeDesc(n_key=top.n_src, n_other=top.n_dst, n_edges=top.n_edges, dim=dim, n_partials=n_pe, rowptr=L.ptr(top.rowptr_src),
                                 e_src=L.ptr(s_src), e_dst=L.ptr(s_dst), pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst),
                                 ori=L.ptr(ori3), w1=L.ptr(bw1_c), b1=L.ptr(bb1_c), w2=L.ptr(bw2_c), b2=L.ptr(bb2_c),
                                 wk=L.ptr(wk_c), x_src=L.ptr(x_src), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),
@@ -779,15 +781,18 @@ class TrplLossFn(torch.autograd.Function):
                            stats=L.ptr_any(stats), scalars=L.ptr(scalars), sums=L.ptr_any(sums), stage=0)
         if all_reduce is None:
             L.call("grl_trpl_loss_fwd", C.byref(ld))
-        else:  # data parallel: `all_reduce(tensor, "sum" | "max")` makes the cross-sample reductions global
+        else:
+            # data parallel: `all_reduce` is the hook `gather(tensor[n]) -> [world, n]` (one all-gather); the slice is then
+            # combined in rank order by grl_dp_combine (sums first, maxima last): ONE collective per stage, deterministic
+            def make_global(buf, lo, hi, n_sum):
+                g = all_reduce(buf[lo:hi])
+                L.call("grl_dp_combine", L.ptr_any(g), g.shape[0], hi - lo, n_sum, buf[lo:hi].data_ptr())
             ld.stage = 1
             L.call("grl_trpl_loss_fwd", C.byref(ld))
-            all_reduce(stats[0:3], "sum")
-            all_reduce(stats[3:4], "max")
+            make_global(stats, 0, 4, 3)
             ld.stage = 2
             L.call("grl_trpl_loss_fwd", C.byref(ld))
-            all_reduce(sums[3:10], "sum")
-            all_reduce(sums[10:12], "max")
+            make_global(sums, 3, 12, 7)
             ld.stage = 3
             L.call("grl_trpl_loss_fwd", C.byref(ld))
         ctx.save_for_backward(mean, v, old_mean, old_v, action, pm, pv, eta, terms, stats)
@@ -823,8 +828,8 @@ class TrplLossFn(torch.autograd.Function):
 def trpl_loss(mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, proj_type, entropy_coef,
               trust_region_coeff, normalize_advantage=True, all_reduce=None):
     """-> (loss_objective, loss_trust_region, loss_entropy, scalars) with scalars indexed by _lib.LOSS_SCALAR_INDEX.
-    `all_reduce(tensor, "sum" | "max")` (data parallel, equal shards): advantage statistics, ESS and metrics become
-    global, the three losses are this rank's share (local sum / global count)."""
+    `all_reduce` (data parallel, equal shards) = the hook `gather(tensor[n]) -> [world, n]`: advantage statistics, ESS and
+    metrics become global, the three losses are this rank's share (local sum / global count)."""
     code = {"kl": 0, "w2": 1}[proj_type]
     return TrplLossFn.apply(mean, v, old_mean, old_v, action, prev_log_prob, advantage, eps_mean, eps_cov, code,
                             entropy_coef, trust_region_coeff, normalize_advantage, all_reduce)

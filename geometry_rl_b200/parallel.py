@@ -59,6 +59,13 @@ class DataParallel:
         self.collectives += 1
         return t
 
+    def all_gather_small(self, t: torch.Tensor) -> torch.Tensor:
+        """[n] -> [world, n] (ops.trpl_loss hook: one collective per loss stage, combined in rank order on the device)."""
+        out = torch.empty(self.world_size * t.numel(), dtype=t.dtype, device=t.device)  # concatenated layout (gloo wants it flat)
+        dist.all_gather_into_tensor(out, t.contiguous().reshape(-1), group=self.group)
+        self.collectives += 1
+        return out.view((self.world_size,) + tuple(t.shape))
+
     def all_reduce_named(self, t: torch.Tensor, op: str) -> torch.Tensor:
         """In-place all-reduce of a (view of a) small statistics tensor; `op` = "sum" | "max" (ops.trpl_loss hook)."""
         return self.all_reduce(t, dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX)

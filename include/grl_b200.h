@@ -241,6 +241,8 @@ typedef struct {
   float* grad_x_src;          /* backward out: [n_src][16][64]                                                 */
   const float* grad_x_src_init; /* optional [n_src][16][64] added in                                           */
   float* grad_partials;       /* [n_partials][GRL_FUSED_EDGE_GRAD_FLOATS]; the backward launches n_partials CTAs */
+  int32_t n_other;            /* rows on the non-key side (n_src in the forward, n_dst in the backward): extent of the
+                                 tensor maps the backward builds over x_src / grad_x1                              */
 } GrlFusedEdgeDesc;
 /* partial layout: gWk[64][64] | gW1b[64][16] (columns 0..13 = gW1, column 14 = gb1) | gW2[64][64] | gb2[64] */
 #define GRL_FUSED_EDGE_GRAD_FLOATS (64 * 64 + 64 * 16 + 64 * 64 + 64)
@@ -370,6 +372,10 @@ typedef struct {
 } GrlLossDesc;
 int grl_trpl_loss_fwd(const GrlLossDesc* d, grl_stream_t stream);
 int grl_trpl_loss_bwd(const GrlLossDesc* d, grl_stream_t stream);
+/* Data-parallel glue of the staged forward: `gathered` is the all-gather [world][n] (n <= 32 doubles per rank) of a
+ * statistics slice; out[i] = sum over ranks for i < n_sum, max over ranks for i >= n_sum, ranks visited in rank order
+ * (bit-identical on every rank).  ONE all-gather + this per stage replaces a SUM and a MAX all-reduce. */
+int grl_dp_combine(const double* gathered, int world, int n, int n_sum, double* out, grl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core building-block self-test: D[128][N] = bf16(A[128][K]) * bf16(B[N][K])^T, fp32 accumulate in

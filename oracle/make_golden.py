@@ -292,6 +292,69 @@ def golden_head(seed, tag):
     _save(rec, tag)
     print(tag, list(rec.keys()))
 
+def golden_policy_wrapper(cfg_name, B, seed, tag):
+    """The reference's own CALLER of the policy body: the unmodified `GNNGaussianPolicyDiag` wrapping the unmodified HEPi
+    and data builder, called as ProbabilisticActor calls it, `module(*obs) -> (loc, covariance_matrix)`
+    (abstract_gnn_gaussian_policy.py:95-109, gnn_gaussian_policy_diag.py:26-87, utils_algo_graph.py:146-158)."""
+    from geometry_rl.algorithms.trust_region_projections.models.policy.gnn_gaussian_policy_diag import (
+        GNNGaussianPolicyDiag)
+    cfg = CONFIGS[cfg_name]
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed)
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) * max(1, cfg.num_envs // B))
+    data, NodeType, EdgeType, EdgeLevel = _ref_data(cfg, full_graph_obs=False, dist_as_pos=True,
+                                                    output_mask_key="grippers", concat_input_vector=False)
+    net = _ref_hepi(cfg, NodeType, EdgeType, EdgeLevel)
+    pol = GNNGaussianPolicyDiag(gnn=net, hyper_data=data, action_dim=cfg.total_action_dim, num_actuators=cfg.num_actuators,
+                                init="orthogonal", hidden_sizes=(64, 64), contextual_std=True, init_std=1.0,
+                                minimal_std=1e-5, share_action_dim=True, post_fc=cfg.post_fc)
+    with torch.no_grad():
+        for n, p in pol.named_parameters():
+            if n.endswith("bias") and p.abs().max() == 0:
+                p.normal_(0, 0.05, generator=gen)
+        pol._pre_std.weight.normal_(0, 0.3, generator=gen)
+    args = _obs_list(cfg, obs)
+    pol(*args)  # first training-mode forward: callibrate() fires (conv.py:104-105)
+    sd = _sd(pol)
+    loc, cov = pol(*args)
+    w_loc = torch.randn(loc.shape, generator=gen)
+    w_cov = torch.randn(loc.shape, generator=gen)
+    loss = (loc * w_loc).sum() + (cov.diagonal(dim1=-2, dim2=-1) * w_cov).sum()
+    pol.zero_grad()
+    loss.backward()
+    _save({"config": cfg_name, "B": B, "obs": obs, "state_dict": sd, "loc": loc.detach(), "cov": cov.detach(),
+           "w_loc": w_loc, "w_cov": w_cov, "grads": _grads(pol)}, tag)
+    print(tag, "loc", tuple(loc.shape), "cov", tuple(cov.shape))
+
+
+def golden_value_wrapper(cfg_name, B, T, seed, tag):
+    """The reference's own CALLER of the critic body: the unmodified `GNNVFNet` around the unmodified DeepSets and data
+    builder, with 2-D observations ([B,F] -> [B,1]) and with 3-D ones ([B,T,F] -> [B,T,1], the per-time-step Python loop of
+    value/gnn_vf_net.py:65-86 that GAE(shifted=True) drives)."""
+    from geometry_rl.algorithms.trust_region_projections.models.value.gnn_vf_net import GNNVFNet
+    from geometry_rl.modules.pyg_models.deepsets import DeepSets
+    cfg = CONFIGS[cfg_name]
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed)
+    data, NodeType, _, _ = _ref_data(cfg, full_graph_obs=True, dist_as_pos=False, output_mask_key=None,
+                                     concat_input_vector=True)
+    aux = 12 if cfg.task == "rigid" else 9
+    vf = GNNVFNet(gnn=DeepSets(input_dim_node=len(NodeType) + aux, output_dim=64, hidden_dim=64,
+                               norm=["layer_norm", "layer_norm"]), hyper_data=data, init="orthogonal", hidden_sizes=(64, 64))
+    with torch.no_grad():
+        vf.final.weight.normal_(0, 0.2, generator=gen)
+    env_ids = torch.arange(B) * max(1, cfg.num_envs // B)
+    frames = [synthetic_obs(cfg, B, gen, env_ids=env_ids) for _ in range(T)]
+    obs3 = {k: torch.stack([f[k] for f in frames], dim=1) for k in obs_keys(cfg)}
+    v2 = vf(*[obs3[k][:, 0] for k in obs_keys(cfg)])
+    v3 = vf(*[obs3[k] for k in obs_keys(cfg)])
+    w = torch.randn(v3.shape, generator=gen)
+    vf.zero_grad()
+    (v3 * w).sum().backward()
+    _save({"config": cfg_name, "B": B, "T": T, "obs3": obs3, "state_dict": _sd(vf), "v2": v2.detach(), "v3": v3.detach(),
+           "w": w, "grads": _grads(vf)}, tag)
+    print(tag, "v2", tuple(v2.shape), "v3", tuple(v3.shape))
+
 
 def golden_equivariance(tag):
     """Ponita.main() (ponita/ponita.py:372-449) with asserts added externally: four graphs that are
@@ -335,6 +398,9 @@ def main():
     golden_projection(18, "projection")
     golden_head(19, "gaussian_head")
     golden_equivariance("ponita_equivariance")
+    golden_policy_wrapper("rigid_insertion_multi_hepi_trpl_cfg", 5, 21, "policy_wrapper_rigid_insertion")
+    golden_policy_wrapper("cloth_hanging_multi_hepi_trpl_cfg", 3, 22, "policy_wrapper_cloth_hanging")
+    golden_value_wrapper("rigid_insertion_multi_hepi_trpl_cfg", 4, 3, 23, "value_wrapper_rigid")
 
 
 if __name__ == "__main__":

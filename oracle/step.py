@@ -9,8 +9,8 @@ Follows examples/torchrl/train.py:134-146,249-316 for one collected batch:
   * actor_loss.backward(); critic_loss.backward() (train.py:296-305); optional grad-norm clip; Adam.
 
 Parameters are plain state-dict tensors (the product modules' own `state_dict()` keys, prefixes stripped).
-The topology cache mirrors the reference's: one placeholder per batch size, built from the FIRST batch of
-that size and re-used for every later batch (rigid_tasks_data.py:254-255; SURVEY 3.4 per-slot quirk).
+The topology cache mirrors the reference's: ONE placeholder, built from the first batch of a size and re-used for
+every later batch of that size, rebuilt when the size changes (rigid_tasks_data.py:254-255; SURVEY 3.4 per-slot quirk).
 
 ITPAL is unavailable -> the KL covariance step uses the restated fp64 dual solve (parity unpinned)."""
 from typing import Dict, Mapping, Optional
@@ -54,6 +54,7 @@ class OracleAgent:
         B = sel["scalars"].shape[0]
         cache = self._topo[policy]
         if B not in cache:
+            cache.clear()  # the reference keeps only the latest placeholder (rigid_tasks_data.py:254-255)
             num_points = parts["infos"]["object_num_points"].long().reshape(-1) if cfg.task == "rigid" else None
             cache[B] = og.build_topology(self.task, parts["position_vectors"], full_graph_obs=not policy,
                                          output_mask_key="grippers" if policy else None, num_points=num_points)

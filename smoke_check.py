@@ -41,6 +41,32 @@ def run_smoke(cfg_name: str = "rigid_insertion_multi_hepi_trpl_cfg", B: int = 32
     lrn.actor_optim.step()
     lrn.critic_optim.step()
 
+    # the same step on the BENCHED path: 16-bit tensor-core kernels (fused edge kernels + tcgen05 node kernels),
+    # gradients within north_star's 1e-2 of the CPU oracle at the same (updated) parameters
+    from geometry_rl_b200 import ops
+    lrn.actor_optim.zero_grad()
+    lrn.critic_optim.zero_grad()
+    oracle16 = OracleAgent(cfg, actor.state_dict(), critic.state_dict())
+    ref16, ga16, _ = oracle16.step_grads(mb)
+    ops.set_precision("bf16")
+    try:
+        out16 = lrn.compute_losses(to_device(mb, dev))
+        out16["actor_loss"].backward()
+    finally:
+        ops.set_precision("fp32")
+    worst16 = 0.0
+    for k in ("loss_trust_region", "loss_entropy", "kl"):
+        err = abs(float(out16[k]) - float(ref16[k])) / (abs(float(ref16[k])) + 1e-6)
+        worst16 = max(worst16, err)
+        assert err < 1e-2, f"smoke (16-bit): {k} {float(out16[k])} vs oracle {float(ref16[k])}"
+    for k, g in ga16.items():
+        if k not in pol or g is None or float(g.abs().max()) == 0.0:
+            continue
+        err = float((pol[k].grad.cpu() - g).abs().max()) / float(g.abs().max())
+        worst16 = max(worst16, err)
+        assert err < 1e-2, f"smoke (16-bit): grad {k} rel err {err}"
+    assert worst16 > 1e-7, "smoke (16-bit): identical to fp32, the tensor-core kernels did not run"
+
     # GAE on a tiny rollout: batched-over-time critic + warp-scan kernel vs the per-step loop + reverse loop
     roll = synthetic_rollout(cfg, gen, num_envs=6, rollout_len=9)
     oracle2 = OracleAgent(cfg, actor.state_dict(), critic.state_dict())
@@ -55,4 +81,4 @@ def run_smoke(cfg_name: str = "rigid_insertion_multi_hepi_trpl_cfg", B: int = 32
     assert err < 1e-4, f"smoke: GAE rel err {err}"
     torch.cuda.synchronize()
     if verbose:
-        print(f"smoke ok: {cfg_name} B={B} worst rel err {max(worst, err):.2e}")
+        print(f"smoke ok: {cfg_name} B={B} worst rel err fp32 path {max(worst, err):.2e}, 16-bit path {worst16:.2e}")

@@ -111,15 +111,21 @@ def _worker(rank, world, port, out_path):
         dist.all_reduce(loss_g)
         # per-sample metrics
         agg = dp.aggregate_metrics({"kl": lw[sl].abs()})
-        # staged reduction of the fused TRPL loss (grl_trpl_loss_fwd stages 1-3 with ops.TrplLossFn's four all-reduces)
+        # staged reduction of the fused TRPL loss (grl_trpl_loss_fwd stages 1-3 with ops.TrplLossFn's two all-gathers)
         terms = _loss_terms(B, torch.Generator().manual_seed(9))
         stats, sums = torch.zeros(8, dtype=torch.float64), torch.zeros(16, dtype=torch.float64)
+        def make_global(buf, lo, hi, n_sum):  # ONE all-gather per stage + grl_dp_combine's rank-order sum / max (torch mirror)
+            g_ = dp.all_gather_small(buf[lo:hi])
+            assert g_.shape == (world, hi - lo)
+            acc = g_[0].clone()
+            for r in range(1, world):
+                acc[:n_sum] = acc[:n_sum] + g_[r, :n_sum]
+                acc[n_sum:] = torch.maximum(acc[n_sum:], g_[r, n_sum:])
+            buf[lo:hi] = acc
         _stage1(terms[sl], stats)
-        dp.all_reduce_named(stats[0:3], "sum")
-        dp.all_reduce_named(stats[3:4], "max")
+        make_global(stats, 0, 4, 3)
         _stage2(terms[sl], stats, sums)
-        dp.all_reduce_named(sums[3:10], "sum")
-        dp.all_reduce_named(sums[10:12], "max")
+        make_global(sums, 3, 12, 7)
         scal = _stage3(stats, sums, 0.01, 4.0)
         share = scal[:3].clone()
         dist.all_reduce(share)  # the three losses are per-rank shares: their sum is the global loss

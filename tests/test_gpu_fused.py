@@ -96,7 +96,7 @@ def test_fused_edge_kernels_match_torch_fp64(case):
 
     # ---- kernels through the C ABI ------------------------------------------------------------------------------
     x1 = torch.full((es.n_dst, 16, 64), float("nan"), device="cuda")
-    fd = L.GrlFusedEdgeDesc(n_key=es.n_dst, n_edges=es.n_edges, dim=dim, n_partials=0, rowptr=L.ptr(es.rowptr_dst),
+    fd = L.GrlFusedEdgeDesc(n_key=es.n_dst, n_other=es.n_src, n_edges=es.n_edges, dim=dim, n_partials=0, rowptr=L.ptr(es.rowptr_dst),
                             e_src=L.ptr(es.edge_src), e_dst=L.ptr(es.edge_dst), pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst),
                             ori=L.ptr(ori3), w1=L.ptr(p["bw1"]), b1=L.ptr(p["bb1"]), w2=L.ptr(p["bw2"]), b2=L.ptr(p["bb2"]),
                             wk=L.ptr(p["wk"]), x_src=L.ptr(x_src), x1=L.ptr(x1))
@@ -105,7 +105,7 @@ def test_fused_edge_kernels_match_torch_fp64(case):
     n_p = max(1, min(es.n_src, L.sm_count()))
     g_xsrc = torch.full((es.n_src, 16, 64), float("nan"), device="cuda")
     part = torch.full((n_p, L.FUSED_EDGE_GRAD_FLOATS), float("nan"), device="cuda")
-    bd = L.GrlFusedEdgeDesc(n_key=es.n_src, n_edges=es.n_edges, dim=dim, n_partials=n_p, rowptr=L.ptr(es.rowptr_src),
+    bd = L.GrlFusedEdgeDesc(n_key=es.n_src, n_other=es.n_dst, n_edges=es.n_edges, dim=dim, n_partials=n_p, rowptr=L.ptr(es.rowptr_src),
                             e_src=L.ptr(s_src), e_dst=L.ptr(s_dst), pos_src=L.ptr(pos_src), pos_dst=L.ptr(pos_dst),
                             ori=L.ptr(ori3), w1=L.ptr(p["bw1"]), b1=L.ptr(p["bb1"]), w2=L.ptr(p["bw2"]), b2=L.ptr(p["bb2"]),
                             wk=L.ptr(p["wk"]), x_src=L.ptr(x_src), grad_x1=L.ptr(g_x1), grad_x_src=L.ptr(g_xsrc),

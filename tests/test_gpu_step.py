@@ -246,8 +246,8 @@ def test_graph_replay_and_prefetched_inputs_match_eager_updates():
         dev = [to_device(b, G.dev()) for b in (mb, mb2)]
         lrn = learner.Learner(cfg, actor, critic, loss_module)
         if mode == "eager":
-            for i in range(3 + 3):  # capture() below runs 3 real warm-up updates first
-                lrn.update(dev[0] if i < 3 else dev[(i - 3) % 2])
+            for i in range(3):  # capture() undoes its warm-up updates: the first replay is the first update
+                lrn.update(dev[i % 2])
         else:
             lrn.capture(dev[0], warmup=3)
             if mode == "graph":

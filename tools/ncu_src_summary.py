@@ -36,7 +36,7 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[0] != "Address"]
 tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
 print("total samples", tot)
 names = ["stall_long_sb", "stall_short_sb", "stall_mio", "stall_barrier", "stall_wait", "stall_math", "stall_not_selected",
