@@ -1135,6 +1135,7 @@ __device__ __forceinline__ int swz_off(int j, int half, int o, int k) {
   return (((j * 2 + half) * kO + o) << 5) + ((k ^ (o & 7)) << 2);
 }
 
+template <int kVariant>  // bit 0: kern MMA of tile t+1 issued at the end of tile t; bit 1: residual rows two flushes ahead
 __global__ void __launch_bounds__(kWs2Threads, 1)
 edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUtensorMap tm_gx, const __grid_constant__ CUtensorMap tm_xs) {
   extern __shared__ unsigned char smem_dyn[];
@@ -1313,33 +1314,46 @@ edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
     // =========================================== role C ===========================================================
     const int o = rt >> 4, cg = rt & 15;  // mapping of the segmented-sum phase
     int cur = n_lo;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), init = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t toff = (size_t)o * kC + 4 * cg;
-    auto begin_node = [&](int node) {
-      if (d.grad_x_src_init && node < n_hi) init = ldg4(d.grad_x_src_init + (size_t)node * kRow + toff);
+    // Residual rows (grad_x_src_init) of node `cur` and of node `cur + 1`: each is requested TWO flushes before it is
+    // added.  (ncu, first ws2 build: with the row requested at the previous flush, ~3 edges earlier, every flush stalled
+    // ~700 cycles on it: 18 % of role C's tile period.)
+    auto ld_init = [&](int node) {
+      return (d.grad_x_src_init && node < n_hi) ? ldg4(d.grad_x_src_init + (size_t)node * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto flush = [&](int node) {
-      sum.x += init.x; sum.y += init.y; sum.z += init.z; sum.w += init.w;
-      st4(d.grad_x_src + (size_t)node * kRow + toff, sum);
-      sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    };
+    float4 init_cur = ld_init(cur), init_nxt = ld_init(cur + 1);
     auto advance = [&](int to) {
-      flush(cur);
+      sum.x += init_cur.x; sum.y += init_cur.y; sum.z += init_cur.z; sum.w += init_cur.w;
+      st4(d.grad_x_src + (size_t)cur * kRow + toff, sum);
+      sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      ++cur;
+      if (cur == to) {  // the usual case: the next node has edges too
+        if (kVariant & 2) {
+          init_cur = init_nxt;
+          init_nxt = ld_init(cur + 1);
+        } else {
+          init_cur = ld_init(cur);
+        }
+        return;
+      }
+      // a run of edge-less nodes [cur, to): their rows are the residual rows alone
+      if (cur < n_hi) st4(d.grad_x_src + (size_t)cur * kRow + toff, init_nxt);
       ++cur;
       while (cur < to) {
         const int n = min(4, to - cur);
         float4 r[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          r[i] = (d.grad_x_src_init && i < n) ? ldg4(d.grad_x_src_init + (size_t)(cur + i) * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) r[i] = i < n ? ld_init(cur + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (i < n) st4(d.grad_x_src + (size_t)(cur + i) * kRow + toff, r[i]);
         cur += n;
       }
-      begin_node(cur);
+      cur = to;
+      init_cur = ld_init(cur);
+      init_nxt = ld_init(cur + 1);
     };
-    begin_node(cur);
     const int rj = row >> 4, ro = row & 15;
 
     for (int t = 0; t < n_tiles; ++t) {
@@ -1357,7 +1371,7 @@ edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       }
       tc::mbar_wait(&s.full[b], parb);  // role R has finished set b
       tc::tc_fence_after();
-      if (rt == 0) {  // kern = basis Wk^T
+      if (rt == 0 && (t == 0 || !(kVariant & 1))) {  // kern = basis Wk^T  (for t > 0 it was issued at the end of tile t-1)
         tc::issue_mma(tmem + kR2, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
         tc::mma_commit(&s.bar_c[0]);
       }
@@ -1466,6 +1480,14 @@ edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
         // [gW1 | gb1] += gP1^T [F | 1 1]; its completion frees operand set b (role R) and G[b] (tile t+2)
         tc::issue_mma(tmem + kGW1, tc::view_mn(xa, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, acc);
         tc::mma_commit(&s.empty[b]);
+        if ((kVariant & 1) && t + 1 < n_tiles) {
+          // kern of tile t+1 right behind it (kR2 is free: every thread has read gH1), so that its round trip runs
+          // under the start of the next tile instead of in front of the message products
+          tc::mbar_wait(&s.full[b ^ 1], (uint32_t)((t + 1) >> 1) & 1u);
+          tc::tc_fence_after();
+          tc::issue_mma(tmem + kR2, tc::view_k(tc::smem_u32(s.BZ[b ^ 1]), kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+          tc::mma_commit(&s.bar_c[0]);
+        }
       }
     }
     for (int t = max(0, n_tiles - 2); t < n_tiles; ++t) {  // the last MMAs on both operand sets
@@ -1473,6 +1495,444 @@ edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
     }
     tc::tc_fence_after();
     if (cur < n_hi) advance(n_hi);
+  }
+  // partial slot of this CTA: gWk[64][64] | gW1b[64][16] (columns 14, 15 = gb1) | gW2[64][64] | gb2[64]
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  float* P = d.grad_partials + (size_t)blockIdx.x * GRL_FUSED_EDGE_GRAD_FLOATS;
+  if (warp < 16) {
+    const int q4 = warp & 3, cq = warp >> 2, row4 = 32 * q4 + lane, c0 = 16 * cq;  // 16 warps: 16 columns per thread
+    const uint32_t la = tmem + ((uint32_t)(32 * q4) << 16);
+    float v[16];
+    auto read = [&](uint32_t col) {
+      if (n_tiles > 0) {
+        tc::tmem_ld16(la + col, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+      }
+    };
+    read(kGWk + c0);
+    if (row4 >= 64) {
+      float* p = P + (size_t)(row4 - 64) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+    read(kGW2 + c0);
+    if (row4 >= 64) {
+      float* p = P + kWFloats + 64 * 16 + (size_t)(row4 - 64) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+    read(kGW1);
+    if (row4 >= 64 && cq == 0) {
+      float* p = P + kWFloats + (size_t)(row4 - 64) * 16;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+    }
+  }
+  if (tid < kC)
+    P[2 * kWFloats + 64 * 16 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward, third generation: a four-stage pipeline inside one CTA per SM (the product path).
+// ncu on the second generation (profiles/r02_fused_bwd_ws2.md): role R still idles > 50 % of the time; role C's tile period
+// (10.6 k cycles) is a serial chain of FOUR tensor-core round trips (kern -> products -> g_basis -> gP2 -> gH1 -> gP1) that
+// no amount of prefetching shortens.  The chain is therefore cut in two roles that work on consecutive tiles:
+//   producer (warp 20)  index stream + TMA row gathers, one tile ahead                              (as in ws2)
+//   role R  (warps 0..7)   features -> pre1 -> H1, GELU' -> pre2 -> basis, GELU'      into operand set t & 1
+//   role C1 (warps 8..15)  kern MMA, message products (g_x1 * kern in place, g_kern image), issues the g_basis / gWk
+//                          MMAs, src-CSR segmented sum -> grad_x_src
+//   role C2 (warps 16..19) gP2 = g_basis * GELU'(pre2), gb2, issues the gH1 / gW2 MMAs, gP1 = gH1 * GELU'(pre1), issues
+//                          the [gW1 | gb1] MMA whose commit frees the operand set
+// TMEM (464 columns): one 64-column scratch for pre1 / pre2 (role R works on one tile at a time), 64 columns per operand
+// set for the two packed fp16 derivative planes, 64 for kern (C1), 64 for g_basis / gH1 (C2), 144 for the weight gradients.
+// Hand-offs: full[b] (R -> C1, C2), bar_c[1] = the g_basis MMA's commit (C1 -> C2), b2_free (C2 -> C1: the g_basis / gH1
+// columns may be overwritten), empty[b] = the last MMA's commit (C2 -> R, C1: operand set b and gradient image b are free).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWs3Threads = 672;
+
+struct FusedBwdWs3Smem {
+  float GX[kTM * kC];            // [8 entries][2 halves][16 rows][32 floats]: 2 KB boxes at 1024-byte multiples, swizzled by TMA
+  float XS[kTM * kC];
+  __nv_bfloat16 F[2][kTM * 16];
+  __nv_bfloat16 H1[2][kTM * kC];
+  __nv_bfloat16 BZ[2][kTM * kC];
+  __nv_bfloat16 W1b[kC * 16];
+  __nv_bfloat16 Wkb[kC * kC];    // [Wkb | W2b] and G[0] are the ignored X halves of the [X | G] images of G[0] and G[1]
+  __nv_bfloat16 W2b[kC * kC];
+  __nv_bfloat16 G[2][kTM * kC];  // MUST directly follow W2b
+  float b2[kC];
+  float acc_gb2[4][kC];
+  int src[4][kTE], dst[4][kTE], lead[4][kTE];
+  uint64_t bar_r[2], bar_c[3], full[2], empty[2];
+  uint64_t bar_g, xs_free, gx_free, b2_free;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWs3Threads, 1)
+edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUtensorMap tm_gx, const __grid_constant__ CUtensorMap tm_xs) {
+  extern __shared__ unsigned char smem_dyn[];
+  FusedBwdWs3Smem& s = *reinterpret_cast<FusedBwdWs3Smem*>(
+      smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));  // the swizzle atoms want a 1024-byte aligned base
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int role = warp < 8 ? 0 : (warp < 16 ? 1 : (warp < 20 ? 2 : 3));  // R, C1, C2, producer
+  const int rw = role == 2 ? warp - 16 : (warp & 7);                      // warp index inside the role
+  const int rt = rw * 32 + lane;
+  const int q = rw & 3, ch = rw >> 2, row = 32 * q + lane;
+  if (tid == 0) {
+    tc::mbar_init(&s.bar_r[0], 1);
+    tc::mbar_init(&s.bar_r[1], 1);
+    for (int i = 0; i < 3; ++i) tc::mbar_init(&s.bar_c[i], 1);
+    tc::mbar_init(&s.full[0], 256);
+    tc::mbar_init(&s.full[1], 256);
+    tc::mbar_init(&s.empty[0], 1);
+    tc::mbar_init(&s.empty[1], 1);
+    tc::mbar_init(&s.bar_g, 1);
+    tc::mbar_init(&s.xs_free, 256);
+    tc::mbar_init(&s.gx_free, 256);
+    tc::mbar_init(&s.b2_free, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 512);
+  stage_w1_bias(s.W1b, d.w1, d.b1);
+  tc::stage_weight_bf16(s.W2b, d.w2, kC, kC, kC);
+  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
+  if (tid < kC) s.b2[tid] = __ldg(d.b2 + tid);
+  if (tid < 4 * kC) (&s.acc_gb2[0][0])[tid] = 0.f;
+  const long long W = 8ll * d.n_edges + d.n_key;
+  const int n_lo = blockIdx.x == 0 ? 0 : fused_lower_bound(d.rowptr, d.n_key, W * blockIdx.x / gridDim.x);
+  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_key : fused_lower_bound(d.rowptr, d.n_key, W * (blockIdx.x + 1) / gridDim.x);
+  const int p0 = d.rowptr[n_lo], p1 = d.rowptr[n_hi];
+  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b), wk = tc::smem_u32(s.Wkb);
+  // TMEM columns: [0,64) pre1 / pre2 scratch   set b: [64 + 64 b, +32) packed GELU'(pre1), [+32, +64) packed GELU'(pre2)
+  //               [192,256) kern   [256,320) g_basis -> gH1   [320,384) gWk   [384,448) gW2   [448,464) [gW1 | gb1]
+  constexpr uint32_t kScr = 0, kKern = 192, kGB = 256, kGWk = 320, kGW2 = 384, kGW1 = 448;
+
+  if (role == 3) {
+    // =========================================== producer warp =====================================================
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tm_gx);
+      tc::tma_prefetch_desc(&tm_xs);
+    }
+    int es = 0, ed = 0, es_n = 0, ed_n = 0;
+    auto load_idx = [&](int t_, int& a, int& b_) {
+      a = 0; b_ = 0;
+      const int e = p0 + t_ * kTE + lane;
+      if (lane < kTE && t_ < n_tiles && e < p1) { a = __ldg(d.e_src + e); b_ = __ldg(d.e_dst + e); }
+    };
+    load_idx(0, es, ed);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int slot = t & 3;
+      const int cnt = min(kTE, p1 - (p0 + t * kTE));
+      load_idx(t + 1, es_n, ed_n);
+      // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row tile
+      const int prev = __shfl_up_sync(0xffffffffu, es, 1);
+      const bool valid = lane < cnt;
+      const bool starts = lane == 0 || !valid || es != prev;
+      const unsigned heads = __ballot_sync(0xffffffffu, starts);
+      const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
+      const unsigned leaders = __ballot_sync(0xffffffffu, valid && ld == lane);
+      if (lane < kTE) { s.src[slot][lane] = es; s.dst[slot][lane] = ed; s.lead[slot][lane] = ld; }
+      if (lane < kTE && t + 1 < n_tiles && p0 + (t + 1) * kTE + lane < p1) {  // next tile's rows -> L2
+        tc::prefetch_l2(d.grad_x1 + (size_t)ed_n * kRow, kRow * 4u);
+        tc::prefetch_l2(d.x_src + (size_t)es_n * kRow, kRow * 4u);
+        if (d.grad_x_src_init) tc::prefetch_l2(d.grad_x_src_init + (size_t)es_n * kRow, kRow * 4u);
+      }
+      if (t > 0) tc::mbar_wait(&s.xs_free, (uint32_t)(t - 1) & 1u);  // role C1 has multiplied tile t-1's x_src rows
+      if (cnt < kTE) {  // rows past the end of the list: zeros (they meet finite rows in the products)
+        for (int i = lane; i < (kTE - cnt) * kRow / 4; i += 32) {
+          reinterpret_cast<float4*>(s.XS + cnt * kRow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (valid && ld == lane) {
+        tc::tma_load_2d(s.XS + (lane * 2 + 0) * 512, &tm_xs, 0, es * kO, &s.bar_g);
+        tc::tma_load_2d(s.XS + (lane * 2 + 1) * 512, &tm_xs, 32, es * kO, &s.bar_g);
+      }
+      if (t > 0) tc::mbar_wait(&s.gx_free, (uint32_t)(t - 1) & 1u);  // ... and summed its g_x1 * kern rows
+      if (cnt < kTE) {
+        for (int i = lane; i < (kTE - cnt) * kRow / 4; i += 32) {
+          reinterpret_cast<float4*>(s.GX + cnt * kRow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (valid) {
+        tc::tma_load_2d(s.GX + (lane * 2 + 0) * 512, &tm_gx, 0, ed * kO, &s.bar_g);
+        tc::tma_load_2d(s.GX + (lane * 2 + 1) * 512, &tm_gx, 32, ed * kO, &s.bar_g);
+      }
+      __syncwarp();
+      // one arrival + the byte count: completes when every box has landed; release also publishes the ring slot
+      if (lane == 0) tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + __popc(leaders)) * kRow * 4u);
+      es = es_n; ed = ed_n;
+    }
+  } else if (role == 0) {
+    // =========================================== role R ===========================================================
+    RowPos pos;
+    int es_n = 0, ed_n = 0;
+    bool v_n = false;
+    auto load_ids = [&](int t_) {
+      const int e = p0 + t_ * kTE + (rt >> 4);
+      v_n = rt < kTM && t_ < n_tiles && e < p1;
+      if (v_n) { es_n = __ldg(d.e_src + e); ed_n = __ldg(d.e_dst + e); }
+    };
+    pos.valid = false;
+    load_ids(0);
+    pos.load(d, es_n, ed_n, v_n);
+    load_ids(1);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int b = t & 1;
+      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
+      const uint32_t fa = tc::smem_u32(s.F[b]), ha = tc::smem_u32(s.H1[b]);
+      const uint32_t kSet = 64u + 64u * b;
+      tc::mbar_wait(&s.empty[b], parb ^ 1u);  // roles C1 / C2 are done with set b (tile t-2); passes at once for t < 2
+      tc::tc_fence_after();
+      if (rt < kTM) {
+        pos.emit(d, s.F[b], rt);
+        pos.load(d, es_n, ed_n, v_n);
+        load_ids(t + 2);
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      tc::group_sync(1, 256);  // also: every thread has read tile t-1's pre2 from the scratch columns
+      if (rt == 0) {  // pre1 = [F | 1 1] [W1 | b1]^T
+        tc::tc_fence_after();
+        tc::issue_mma(tmem + kScr, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
+        tc::mma_commit(&s.bar_r[0]);
+      }
+      tc::mbar_wait(&s.bar_r[0], par);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int layer = 0; layer < 2; ++layer) {
+        __nv_bfloat16* img = layer == 0 ? s.H1[b] : s.BZ[b];
+        if (layer == 1) {
+          tc::fence_async_smem();
+          tc::tc_fence_before();
+          tc::group_sync(1, 256);  // H1 is complete and every thread has read pre1: the scratch columns may be rewritten
+          if (rt == 0) {  // pre2 = H1 W2^T
+            tc::tc_fence_after();
+            tc::issue_mma(tmem + kScr, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+            tc::mma_commit(&s.bar_r[1]);
+          }
+          tc::mbar_wait(&s.bar_r[1], par);
+          tc::tc_fence_after();
+        }
+        uint32_t dpk[16];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 32 * ch + 16 * i;
+          float v[16];
+          tc::tmem_ld16(lane_addr + kScr + c0, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x0 = v[2 * e], x1 = v[2 * e + 1];
+            if (layer == 1) { x0 += s.b2[c0 + 2 * e]; x1 += s.b2[c0 + 2 * e + 1]; }
+            __half2 y, dy;
+            tc::gelu_h2(__floats2half2_rn(x0, x1), y, dy);
+            const float2 yf = __half22float2(y);
+            v[2 * e] = yf.x; v[2 * e + 1] = yf.y;
+            dpk[8 * i + e] = *reinterpret_cast<const uint32_t*>(&dy);
+          }
+          *reinterpret_cast<uint4*>(img + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+          *reinterpret_cast<uint4*>(img + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+        }
+        // packed GELU' of this thread's 32 columns -> 16 columns of the set's derivative plane `layer`
+        tc::tmem_st16(lane_addr + kSet + 32 * layer + 16 * ch, dpk);
+      }
+      tc::tmem_st_wait();
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s.full[b]);
+    }
+  } else if (role == 1) {
+    // =========================================== role C1 ==========================================================
+    const int o = rt >> 4, cg = rt & 15;  // mapping of the segmented-sum phase
+    int cur = n_lo;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), init = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t toff = (size_t)o * kC + 4 * cg;
+    auto begin_node = [&](int node) {
+      if (d.grad_x_src_init && node < n_hi) init = ldg4(d.grad_x_src_init + (size_t)node * kRow + toff);
+    };
+    auto advance = [&](int to) {
+      sum.x += init.x; sum.y += init.y; sum.z += init.z; sum.w += init.w;
+      st4(d.grad_x_src + (size_t)cur * kRow + toff, sum);
+      sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      ++cur;
+      while (cur < to) {
+        const int n = min(4, to - cur);
+        float4 r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          r[i] = (d.grad_x_src_init && i < n) ? ldg4(d.grad_x_src_init + (size_t)(cur + i) * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < n) st4(d.grad_x_src + (size_t)(cur + i) * kRow + toff, r[i]);
+        cur += n;
+      }
+      begin_node(cur);
+    };
+    begin_node(cur);
+    const int rj = row >> 4, ro = row & 15;
+
+    for (int t = 0; t < n_tiles; ++t) {
+      const int slot = t & 3, b = t & 1;
+      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
+      const int cnt = min(kTE, p1 - (p0 + t * kTE));
+      const bool acc = t > 0;
+      const uint32_t bz = tc::smem_u32(s.BZ[b]);
+      const uint32_t ga = tc::smem_u32(s.G[b]), xa = ga - kTM * kC * 2;  // xa: the 16 KB in front of G[b]
+      __nv_bfloat16* G = s.G[b];
+      if (t >= 2) {  // G[b] was last read by the [gW1 | gb1] MMA of tile t-2
+        tc::mbar_wait(&s.empty[b], parb ^ 1u);
+        tc::tc_fence_after();
+      }
+      tc::mbar_wait(&s.full[b], parb);  // role R has finished set b
+      tc::tc_fence_after();
+      if (rt == 0) {  // kern = basis Wk^T  (the kern columns are free: every C1 thread passed barrier (E) of tile t-1)
+        tc::issue_mma(tmem + kKern, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
+        tc::mma_commit(&s.bar_c[0]);
+      }
+      tc::mbar_wait(&s.bar_g, par);  // the producer's rows have landed; its ring slot is visible
+      tc::mbar_wait(&s.bar_c[0], par);
+      tc::tc_fence_after();
+      {
+        float* gxb = s.GX + (((rj * 2 + ch) * kO + ro) << 5);
+        const float* xsb = s.XS + (((s.lead[slot][rj] * 2 + ch) * kO + ro) << 5);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 32 * ch + 16 * i;
+          float v[16], gkv[16];
+          tc::tmem_ld16(lane_addr + kKern + c0, v);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int off = ((4 * i + e4) ^ (ro & 7)) << 2;
+            const float4 gm = ld4(gxb + off), x = ld4(xsb + off);
+            const int e = 4 * e4;
+            st4(gxb + off, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
+            gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
+          }
+          *reinterpret_cast<uint4*>(G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
+          *reinterpret_cast<uint4*>(G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
+        }
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&s.xs_free);  // this thread is done with the x_src tile
+      tc::tc_fence_before();
+      tc::group_sync(2, 256);  // (E)
+      if (rt == 0) {
+        if (t > 0) tc::mbar_wait(&s.b2_free, (uint32_t)(t - 1) & 1u);  // role C2 has read gH1 of tile t-1
+        tc::tc_fence_after();
+        // g_basis = g_kern Wk (Wk image read MN-major: K = c, N = j)
+        tc::issue_mma(tmem + kGB, tc::view_k(ga, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
+        // lanes 64..127: gWk[c][j] += sum_rows g_kern[row][c] basis[row][j]   ([X | G] as one 128-column image)
+        tc::issue_mma(tmem + kGWk, tc::view_mn(xa, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
+        tc::mma_commit(&s.bar_c[1]);  // role C2 takes over from here
+      }
+      // src-CSR segmented sum of g_x1 * kern
+#pragma unroll
+      for (int j = 0; j < kTE; ++j) {
+        if (j < cnt) {
+          const int sn = s.src[slot][j];
+          if (cur < sn) advance(sn);
+          const float4 m = ld4(s.GX + swz_off(j, cg >> 3, o, cg & 7));
+          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+        }
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&s.gx_free);  // ... and with the g_x1 tile
+    }
+    if (cur < n_hi) advance(n_hi);
+  } else {
+    // =========================================== role C2 (4 warps: 64 accumulator columns per thread) ================
+    for (int t = 0; t < n_tiles; ++t) {
+      const int b = t & 1;
+      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
+      const bool acc = t > 0;
+      const uint32_t fa = tc::smem_u32(s.F[b]), ha = tc::smem_u32(s.H1[b]);
+      const uint32_t ga = tc::smem_u32(s.G[b]), xa = ga - kTM * kC * 2;
+      __nv_bfloat16* G = s.G[b];
+      const uint32_t kSet = 64u + 64u * b;
+      tc::mbar_wait(&s.full[b], parb);      // the derivative planes of set b are in TMEM
+      tc::mbar_wait(&s.bar_c[1], par);      // g_basis is complete (and the MMAs that read g_kern from G[b] are done)
+      tc::tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // 32 columns at a time
+        uint32_t dpk[16];
+        tc::tmem_ld16_raw(lane_addr + kSet + 32 + 16 * h, dpk);  // GELU'(pre2), columns 32 h .. 32 h + 31
+        float gp2[32];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 32 * h + 16 * i;
+          float v[16];
+          tc::tmem_ld16(lane_addr + kGB + c0, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float2 dg = __half22float2(*reinterpret_cast<const __half2*>(&dpk[8 * i + e]));
+            gp2[16 * i + 2 * e] = v[2 * e] * dg.x;
+            gp2[16 * i + 2 * e + 1] = v[2 * e + 1] * dg.y;
+          }
+          *reinterpret_cast<uint4*>(G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i);
+          *reinterpret_cast<uint4*>(G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i + 8);
+        }
+        tc::warp_colsum<32>(gp2, lane);
+        s.acc_gb2[q][32 * h + lane] += gp2[0];
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      tc::group_sync(3, 128);  // (F)
+      if (rt == 0) {
+        tc::tc_fence_after();
+        // gH1 = gP2 W2 (W2 image read MN-major: K = n, N = k) over the g_basis columns
+        tc::issue_mma(tmem + kGB, tc::view_k(ga, kTM), tc::view_mn(w2, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
+        // lanes 64..127: gW2[n][k] += sum_rows gP2[row][n] H1[row][k]
+        tc::issue_mma(tmem + kGW2, tc::view_mn(xa, kTM), tc::view_mn(ha, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
+        tc::mma_commit(&s.bar_c[2]);
+      }
+      tc::mbar_wait(&s.bar_c[2], par);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t dpk[16];
+        tc::tmem_ld16_raw(lane_addr + kSet + 16 * h, dpk);  // GELU'(pre1)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = 32 * h + 16 * i;
+          float v[16];
+          tc::tmem_ld16(lane_addr + kGB + c0, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float2 dg = __half22float2(*reinterpret_cast<const __half2*>(&dpk[8 * i + e]));
+            v[2 * e] *= dg.x;
+            v[2 * e + 1] *= dg.y;
+          }
+          *reinterpret_cast<uint4*>(G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
+          *reinterpret_cast<uint4*>(G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
+        }
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      tc::group_sync(3, 128);  // (G)
+      if (rt == 0) {
+        tc::mbar_arrive(&s.b2_free);  // every C2 thread has read gH1: role C1 may issue the next g_basis MMA
+        tc::tc_fence_after();
+        // [gW1 | gb1] += gP1^T [F | 1 1]; its completion frees operand set b (role R) and G[b] (role C1, tile t+2)
+        tc::issue_mma(tmem + kGW1, tc::view_mn(xa, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, acc);
+        tc::mma_commit(&s.empty[b]);
+      }
+    }
+    for (int t = max(0, n_tiles - 2); t < n_tiles; ++t) {  // the last MMAs on both operand sets
+      tc::mbar_wait(&s.empty[t & 1], (uint32_t)(t >> 1) & 1u);
+    }
+    tc::tc_fence_after();
   }
   // partial slot of this CTA: gWk[64][64] | gW1b[64][16] (columns 14, 15 = gb1) | gW2[64][64] | gb2[64]
   tc::tc_fence_before();
@@ -1549,16 +2009,37 @@ int grl_fbconv_edge_fused_bwd(const GrlFusedEdgeDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d->n_partials > 0 && d->n_partials <= d->n_key, GRL_EINVAL,
               "grl_fbconv_edge_fused_bwd: n_partials=%d must be in [1, n_key]", d->n_partials);
   GRL_REQUIRE(d->n_other > 0, GRL_EINVAL, "grl_fbconv_edge_fused_bwd: n_other=%d (rows of grad_x1) must be set", d->n_other);
-  // GRL_FUSED_BWD=lockstep | ws1 select the earlier generations (kept as parity partners and for the profiles);
-  // default: producer warp + two decoupled roles
-  static const int gen = [] { const char* e = getenv("GRL_FUSED_BWD"); return !e ? 2 : (e[0] == 'l' ? 0 : (e[0] == 'w' ? 1 : 2)); }();
-  if (gen == 2) {
+  // GRL_FUSED_BWD=lockstep | ws1 | ws2 select the earlier generations (kept as parity partners and for the profiles);
+  // default (ws3): producer warp + three decoupled roles
+  static const int gen = [] {
+    const char* e = getenv("GRL_FUSED_BWD");
+    if (!e) return 3;
+    if (e[0] == 'l') return 0;
+    return e[0] == 'w' && e[1] == 's' && e[2] >= '1' && e[2] <= '3' ? e[2] - '0' : 3;
+  }();
+  if (gen == 3) {
+    alignas(64) CUtensorMap tm_gx, tm_xs;
+    if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
+    if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
+    const int smem = (int)sizeof(grl::FusedBwdWs3Smem) + 1024;
+    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws3_kernel, smem) != GRL_OK) return GRL_ECUDA;
+    grl::edge_fused_bwd_ws3_kernel<<<d->n_partials, grl::kWs3Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs);
+  } else if (gen == 2) {
     alignas(64) CUtensorMap tm_gx, tm_xs;
     if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
     if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
     const int smem = (int)sizeof(grl::FusedBwdWs2Smem) + 1024;
-    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws2_kernel, smem) != GRL_OK) return GRL_ECUDA;
-    grl::edge_fused_bwd_ws2_kernel<<<d->n_partials, grl::kWs2Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs);
+    static const int variant = [] { const char* e = getenv("GRL_WS2_VARIANT"); return e ? atoi(e) & 3 : 0; }();
+#define GRL_WS2_LAUNCH(V)                                                                                              \
+  do {                                                                                                                 \
+    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws2_kernel<V>, smem) != GRL_OK) return GRL_ECUDA;    \
+    grl::edge_fused_bwd_ws2_kernel<V><<<d->n_partials, grl::kWs2Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs); \
+  } while (0)
+    if (variant == 0) GRL_WS2_LAUNCH(0);
+    else if (variant == 1) GRL_WS2_LAUNCH(1);
+    else if (variant == 2) GRL_WS2_LAUNCH(2);
+    else GRL_WS2_LAUNCH(3);
+#undef GRL_WS2_LAUNCH
   } else if (gen == 0) {
     const int smem = (int)sizeof(grl::FusedBwdSmem);
     if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
