@@ -54,6 +54,15 @@ class GrlFusedEdgeDesc(C.Structure):
                 ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp), ("grad_partials", _fp), ("n_other", _i32)]
 
 
+class GrlCriticDesc(C.Structure):
+    _fields_ = [("n_graphs", _i32), ("n_tokens", _i32), ("n_feat", _i32), ("n_partials", _i32), ("eps", C.c_float),
+                ("count", C.c_double), ("x", _fp), ("w1", _fp), ("b1", _fp), ("gamma", _fp), ("beta", _fp), ("stats", _fp),
+                ("stat_partials", _fp), ("ysum", _fp), ("grad_ysum", _fp), ("bstats", _fp), ("grad_partials", _fp)]
+
+
+CRITIC_GRAD_FLOATS = 3 * 64 + 64 * 16
+
+
 class GrlProjDesc(C.Structure):
     _fields_ = [("batch", _i32), ("k", _i32), ("proj_type", _i32), ("eps_mean", C.c_float), ("eps_cov", C.c_float),
                 ("mean", _fp), ("v", _fp), ("old_mean", _fp), ("old_v", _fp), ("proj_mean", _fp), ("proj_v", _fp),
@@ -113,6 +122,10 @@ SIGNATURES = {
     "grl_fbconv_node_bwd_tc": (C.c_int, [C.POINTER(GrlConvDesc), _fp]),
     "grl_fbconv_edge_fused_fwd": (C.c_int, [C.POINTER(GrlFusedEdgeDesc), _fp]),
     "grl_fbconv_edge_fused_bwd": (C.c_int, [C.POINTER(GrlFusedEdgeDesc), _fp]),
+    "grl_critic_inner_stats": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
+    "grl_critic_inner_fwd": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
+    "grl_critic_inner_bwd_stats": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
+    "grl_critic_inner_bwd": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
     "grl_readout_fwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_readout_bwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_trpl_loss_fwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),

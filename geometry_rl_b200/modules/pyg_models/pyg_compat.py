@@ -44,6 +44,8 @@ class GraphLayerNorm(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.ones(in_channels))
         self.bias = torch.nn.Parameter(torch.zeros(in_channels))
         self.stats_reduce = None
+        # data parallel, fused critic kernels: (all_reduce(double tensor) -> None, world_size); set by DataParallel.attach
+        self.fused_all_reduce = None
 
     def forward(self, x, groups: int = 1):
         shape = x.shape

@@ -647,6 +647,63 @@ def aggregate_messages(x_src, basis, wk, es: EdgeSet) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# V1: DeepSets critic, inner per-token MLP up to the pooled sum
+# ------------------------------------------------------------------------------------------------
+class CriticInnerFn(torch.autograd.Function):
+    """x [B,N,F] -> ysum [B,64] = sum_n relu(graph_layer_norm(x W1^T + b1) * gamma + beta)  (deepsets.py:34-53 up to the
+    token sum; PyG LayerNorm(mode='graph') statistics over the whole tensor).  Four launches forward + backward, no
+    [B N, 64] activation in HBM.  `all_reduce(double[2])` (data parallel) makes the statistics global."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, gamma, beta, eps, all_reduce=None, world_size=1):
+        x, w1c, b1c = _f32c(x), _f32c(w1.detach()), _f32c(b1.detach())
+        gc, bc = _f32c(gamma.detach()), _f32c(beta.detach())
+        B, N, Fdim = x.shape
+        assert tuple(w1c.shape) == (64, Fdim) and Fdim <= 16, f"critic inner layer {tuple(w1c.shape)} on {Fdim} features"
+        dev = x.device
+        n_p = _n_partials(B, 2)
+        stats = torch.empty(2, dtype=torch.float64, device=dev)
+        sp = torch.empty(n_p, 2, dtype=torch.float64, device=dev)
+        ysum = torch.empty(B, 64, dtype=torch.float32, device=dev)
+        d = L.GrlCriticDesc(n_graphs=B, n_tokens=N, n_feat=Fdim, n_partials=n_p, eps=float(eps),
+                            count=float(B) * N * 64 * world_size, x=L.ptr(x), w1=L.ptr(w1c), b1=L.ptr(b1c), gamma=L.ptr(gc),
+                            beta=L.ptr(bc), stats=L.ptr_any(stats), stat_partials=L.ptr_any(sp), ysum=L.ptr(ysum))
+        L.call("grl_critic_inner_stats", C.byref(d), shape=(B * N, B, 0))
+        if all_reduce is not None:
+            all_reduce(stats)
+        L.call("grl_critic_inner_fwd", C.byref(d), shape=(B * N, B, 0))
+        ctx.save_for_backward(x, w1c, b1c, gc, bc, stats)
+        ctx.meta = (float(eps), all_reduce, world_size, n_p)
+        return ysum
+
+    @staticmethod
+    def backward(ctx, g_ysum):
+        x, w1c, b1c, gc, bc, stats = ctx.saved_tensors
+        eps, all_reduce, world_size, n_p = ctx.meta
+        B, N, Fdim = x.shape
+        dev = x.device
+        g_ysum = _f32c(g_ysum)
+        bstats = torch.empty(2, dtype=torch.float64, device=dev)
+        sp = torch.empty(n_p, 2, dtype=torch.float64, device=dev)
+        part = torch.empty(n_p, L.CRITIC_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        d = L.GrlCriticDesc(n_graphs=B, n_tokens=N, n_feat=Fdim, n_partials=n_p, eps=eps, count=float(B) * N * 64 * world_size,
+                            x=L.ptr(x), w1=L.ptr(w1c), b1=L.ptr(b1c), gamma=L.ptr(gc), beta=L.ptr(bc), stats=L.ptr_any(stats),
+                            stat_partials=L.ptr_any(sp), grad_ysum=L.ptr(g_ysum), bstats=L.ptr_any(bstats),
+                            grad_partials=L.ptr(part))
+        L.call("grl_critic_inner_bwd_stats", C.byref(d), shape=(B * N, B, 0))
+        if all_reduce is not None:
+            all_reduce(bstats)
+        L.call("grl_critic_inner_bwd", C.byref(d), shape=(B * N, B, 0))
+        g = _reduce(part)
+        g_w1 = g[192:].view(64, 16)[:, :Fdim].contiguous()
+        return None, g_w1, g[128:192], g[0:64], g[64:128], None, None, None
+
+
+def critic_inner(x, w1, b1, gamma, beta, eps, all_reduce=None, world_size=1):
+    return CriticInnerFn.apply(x, w1, b1, gamma, beta, eps, all_reduce, world_size)
+
+
+# ------------------------------------------------------------------------------------------------
 # K3: GAE
 # ------------------------------------------------------------------------------------------------
 def gae(reward, value_T1, done, terminated, gamma: float, lmbda: float):

@@ -156,4 +156,5 @@ class DataParallel:
         for m in loss_module.critic_network.modules():
             if isinstance(m, GraphLayerNorm):
                 m.stats_reduce = critic_dp.graph_norm_stats
+                m.fused_all_reduce = (critic_dp.all_reduce, critic_dp.world_size)
         return loss_module

@@ -257,6 +257,42 @@ int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats,
                         grl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * V1  DeepSets critic, inner per-token MLP up to the pooled sum: replaces the first Linear, PyG LayerNorm(mode='graph'),
+ * ReLU and the token sum of geometry_rl/modules/pyg_models/deepsets.py:34-53 (mlp_inner.lins.0, mlp_inner.norms.0,
+ * x.sum(dim=1)).  The inner MLP's second Linear commutes with the sum and is applied by the caller on [B][64]:
+ *   ysum[b] = sum_n relu(((x[b][n] W1^T + b1) - mean) / (std + eps) * gamma + beta)
+ * with mean / biased std over the WHOLE [B][N][64] pre-activation tensor (LayerNorm mode 'graph', batch=None) — of all
+ * ranks under data parallelism: `stats` / `bstats` are two doubles the caller all-reduces between the two passes of
+ * each direction, `count` is the GLOBAL element count.  No [B N][64] activation is ever written: every pass recomputes
+ * the pre-activations from x (4 F bytes per token).
+ *   forward : grl_critic_inner_stats (-> stats = (sum h, sum h^2)), [all-reduce], grl_critic_inner_fwd (-> ysum)
+ *   backward: grl_critic_inner_bwd_stats (-> bstats = (sum g_xhat, sum g_xhat xhat), g_gamma, g_beta partials),
+ *             [all-reduce], grl_critic_inner_bwd (-> g_b1, g_W1 partials)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_graphs, n_tokens, n_feat, n_partials; /* n_feat <= 16; n_partials <= n_graphs CTAs, one partial slot each    */
+  float eps;
+  double count;            /* number of elements of the [B][N][64] tensor over ALL ranks                              */
+  const float* x;          /* [B][N][F]                                                                                */
+  const float* w1;         /* [64][F] row-major (mlp_inner.lins.0.weight)                                              */
+  const float* b1;         /* [64]                                                                                     */
+  const float* gamma;      /* [64] mlp_inner.norms.0.weight                                                            */
+  const float* beta;       /* [64] mlp_inner.norms.0.bias                                                              */
+  double* stats;           /* [2] (sum h, sum h^2): written by _stats for this rank's rows, read by the other passes   */
+  double* stat_partials;   /* [n_partials][2] workspace                                                                */
+  float* ysum;             /* [B][64]                                                                                  */
+  const float* grad_ysum;  /* [B][64]                                                                                  */
+  double* bstats;          /* [2] (S1, S2): written by _bwd_stats, read by _bwd                                        */
+  float* grad_partials;    /* [n_partials][GRL_CRITIC_GRAD_FLOATS]                                                     */
+} GrlCriticDesc;
+/* partial layout: g_gamma[64] | g_beta[64] | g_b1[64] | g_W1[64][16] (columns >= F are zero) */
+#define GRL_CRITIC_GRAD_FLOATS (3 * 64 + 64 * 16)
+int grl_critic_inner_stats(const GrlCriticDesc* d, grl_stream_t stream);
+int grl_critic_inner_fwd(const GrlCriticDesc* d, grl_stream_t stream);
+int grl_critic_inner_bwd_stats(const GrlCriticDesc* d, grl_stream_t stream);
+int grl_critic_inner_bwd(const GrlCriticDesc* d, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * M4  Equivariant readout of the output-node latents: replaces hepi.py:173-190 / ponita_gcn.py:132-146 with
  * ponita/utils/to_from_sphere.py:12-17: decoder Linear(64 -> od + odv) per orientation, orientation means,
  * vector readout against the orientation grid, gating by the scalar readout, z = 0 padding in 2-D.

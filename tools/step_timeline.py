@@ -1,7 +1,7 @@
 """Device timeline of ONE graph-replayed update step (torch.profiler / CUPTI kernel records): which kernels sit on
 the critical path between the library's own kernels.  Writes gpurun_out/timeline_<config>.json (compact list of
 [name, stream, start_us, dur_us]) for analysis off the GPU box, and prints the per-stream totals.
-usage: python tools/step_timeline.py [config] [precision]"""
+usage: python tools/step_timeline.py [config] [precision] [minibatch]"""
 import json
 import os
 import sys
@@ -19,11 +19,11 @@ name = sys.argv[1] if len(sys.argv) > 1 else "rigid_pushing_multi_empn_trpl_cfg"
 precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 cfg = CONFIGS[name]
 dev = torch.device("cuda")
-torch.backends.cuda.matmul.allow_tf32 = precision == "bf16"
+torch.backends.cuda.matmul.allow_tf32 = False
 ops.set_precision(precision)
 actor, critic, projection, loss_module, adv = learner.build_agent(cfg, dev, seed=0)
 lrn = learner.Learner(cfg, actor, critic, loss_module)
-B = cfg.mini_batch_size
+B = int(sys.argv[3]) if len(sys.argv) > 3 else cfg.mini_batch_size
 gen = torch.Generator().manual_seed(1)
 obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) % cfg.num_envs)
 with torch.no_grad():
