@@ -1560,6 +1560,7 @@ constexpr int kWs3Threads = 672;
 struct FusedBwdWs3Smem {
   float GX[kTM * kC];            // [8 entries][2 halves][16 rows][32 floats]: 2 KB boxes at 1024-byte multiples, swizzled by TMA
   float XS[kTM * kC];
+  float IN[kTM * kC];            // residual rows (grad_x_src_init) of the nodes whose run STARTS in this tile, same layout
   __nv_bfloat16 F[2][kTM * 16];
   __nv_bfloat16 H1[2][kTM * kC];
   __nv_bfloat16 BZ[2][kTM * kC];
@@ -1570,13 +1571,15 @@ struct FusedBwdWs3Smem {
   float b2[kC];
   float acc_gb2[4][kC];
   int src[4][kTE], dst[4][kTE], lead[4][kTE];
+  int adv[4][kTE];               // key nodes to advance before adding entry j: 0 = same node as the previous entry
   uint64_t bar_r[2], bar_c[3], full[2], empty[2];
   uint64_t bar_g, xs_free, gx_free, b2_free;
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(kWs3Threads, 1)
-edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUtensorMap tm_gx, const __grid_constant__ CUtensorMap tm_xs) {
+edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUtensorMap tm_gx, const __grid_constant__ CUtensorMap tm_xs,
+                          const __grid_constant__ CUtensorMap tm_in) {
   extern __shared__ unsigned char smem_dyn[];
   FusedBwdWs3Smem& s = *reinterpret_cast<FusedBwdWs3Smem*>(
       smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));  // the swizzle atoms want a 1024-byte aligned base
@@ -1626,7 +1629,9 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       tc::tma_prefetch_desc(&tm_gx);
       tc::tma_prefetch_desc(&tm_xs);
     }
+    if (lane == 0) tc::tma_prefetch_desc(&tm_in);
     int es = 0, ed = 0, es_n = 0, ed_n = 0;
+    int last_key = n_lo;  // key node of the previous entry (the segmented sum starts at node n_lo)
     auto load_idx = [&](int t_, int& a, int& b_) {
       a = 0; b_ = 0;
       const int e = p0 + t_ * kTE + lane;
@@ -1638,13 +1643,17 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       const int cnt = min(kTE, p1 - (p0 + t * kTE));
       load_idx(t + 1, es_n, ed_n);
       // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row tile
-      const int prev = __shfl_up_sync(0xffffffffu, es, 1);
+      int prev = __shfl_up_sync(0xffffffffu, es, 1);
       const bool valid = lane < cnt;
       const bool starts = lane == 0 || !valid || es != prev;
       const unsigned heads = __ballot_sync(0xffffffffu, starts);
       const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
       const unsigned leaders = __ballot_sync(0xffffffffu, valid && ld == lane);
-      if (lane < kTE) { s.src[slot][lane] = es; s.dst[slot][lane] = ed; s.lead[slot][lane] = ld; }
+      if (lane == 0) prev = last_key;
+      const int adv = valid ? es - prev : 0;  // > 0: entry j starts the run of a new key node (adv - 1 edge-less nodes skipped)
+      const unsigned run_starts = d.grad_x_src_init ? __ballot_sync(0xffffffffu, adv > 0) : 0u;
+      last_key = __shfl_sync(0xffffffffu, es, cnt - 1);
+      if (lane < kTE) { s.src[slot][lane] = es; s.dst[slot][lane] = ed; s.lead[slot][lane] = ld; s.adv[slot][lane] = adv; }
       if (lane < kTE && t + 1 < n_tiles && p0 + (t + 1) * kTE + lane < p1) {  // next tile's rows -> L2
         tc::prefetch_l2(d.grad_x1 + (size_t)ed_n * kRow, kRow * 4u);
         tc::prefetch_l2(d.x_src + (size_t)es_n * kRow, kRow * 4u);
@@ -1670,9 +1679,13 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
         tc::tma_load_2d(s.GX + (lane * 2 + 0) * 512, &tm_gx, 0, ed * kO, &s.bar_g);
         tc::tma_load_2d(s.GX + (lane * 2 + 1) * 512, &tm_gx, 32, ed * kO, &s.bar_g);
       }
+      if ((run_starts >> lane) & 1u) {  // residual row of a node whose run starts here (read by the segmented sum)
+        tc::tma_load_2d(s.IN + (lane * 2 + 0) * 512, &tm_in, 0, es * kO, &s.bar_g);
+        tc::tma_load_2d(s.IN + (lane * 2 + 1) * 512, &tm_in, 32, es * kO, &s.bar_g);
+      }
       __syncwarp();
       // one arrival + the byte count: completes when every box has landed; release also publishes the ring slot
-      if (lane == 0) tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + __popc(leaders)) * kRow * 4u);
+      if (lane == 0) tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + __popc(leaders) + __popc(run_starts)) * kRow * 4u);
       es = es_n; ed = ed_n;
     }
   } else if (role == 0) {
@@ -1757,30 +1770,18 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
     // =========================================== role C1 ==========================================================
     const int o = rt >> 4, cg = rt & 15;  // mapping of the segmented-sum phase
     int cur = n_lo;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), init = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t toff = (size_t)o * kC + 4 * cg;
-    auto begin_node = [&](int node) {
-      if (d.grad_x_src_init && node < n_hi) init = ldg4(d.grad_x_src_init + (size_t)node * kRow + toff);
+    const bool has_init = d.grad_x_src_init != nullptr;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    // residual row of node `cur`: from global memory for the first node of the range, from the IN tile (TMA, one tile
+    // ahead of its use) for every node whose run starts later
+    float4 init = has_init && cur < n_hi ? ldg4(d.grad_x_src_init + (size_t)cur * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // rows of the edge-less nodes [lo, hi): the residual rows alone (rare: kNN graphs have a few nodes nobody points to)
+    auto fill_gap = [&](int lo, int hi) {
+      for (int n = lo; n < hi; ++n)
+        st4(d.grad_x_src + (size_t)n * kRow + toff,
+            has_init ? ldg4(d.grad_x_src_init + (size_t)n * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f));
     };
-    auto advance = [&](int to) {
-      sum.x += init.x; sum.y += init.y; sum.z += init.z; sum.w += init.w;
-      st4(d.grad_x_src + (size_t)cur * kRow + toff, sum);
-      sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      ++cur;
-      while (cur < to) {
-        const int n = min(4, to - cur);
-        float4 r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          r[i] = (d.grad_x_src_init && i < n) ? ldg4(d.grad_x_src_init + (size_t)(cur + i) * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < n) st4(d.grad_x_src + (size_t)(cur + i) * kRow + toff, r[i]);
-        cur += n;
-      }
-      begin_node(cur);
-    };
-    begin_node(cur);
     const int rj = row >> 4, ro = row & 15;
 
     for (int t = 0; t < n_tiles; ++t) {
@@ -1837,20 +1838,34 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
         tc::issue_mma(tmem + kGWk, tc::view_mn(xa, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
         tc::mma_commit(&s.bar_c[1]);  // role C2 takes over from here
       }
-      // src-CSR segmented sum of g_x1 * kern
+      // src-CSR segmented sum of g_x1 * kern.  Everything a step needs is in registers before the chain starts: the run
+      // flags (producer), the messages and the residual rows of the runs that start in this tile (IN tile, shared memory)
+      {
+        const int4 a_lo = *reinterpret_cast<const int4*>(&s.adv[slot][0]), a_hi = *reinterpret_cast<const int4*>(&s.adv[slot][4]);
+        const int adv[kTE] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+        float4 m[kTE];
 #pragma unroll
-      for (int j = 0; j < kTE; ++j) {
-        if (j < cnt) {
-          const int sn = s.src[slot][j];
-          if (cur < sn) advance(sn);
-          const float4 m = ld4(s.GX + swz_off(j, cg >> 3, o, cg & 7));
-          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
+        for (int j = 0; j < kTE; ++j) m[j] = ld4(s.GX + swz_off(j, cg >> 3, o, cg & 7));
+#pragma unroll
+        for (int j = 0; j < kTE; ++j) {
+          if (adv[j] > 0) {  // warp-uniform: node `cur` is complete (adv is 0 past the end of the list)
+            st4(d.grad_x_src + (size_t)cur * kRow + toff,
+                make_float4(sum.x + init.x, sum.y + init.y, sum.z + init.z, sum.w + init.w));
+            if (adv[j] > 1) fill_gap(cur + 1, cur + adv[j]);
+            cur += adv[j];
+            sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            init = has_init ? ld4(s.IN + swz_off(j, cg >> 3, o, cg & 7)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          sum.x += m[j].x; sum.y += m[j].y; sum.z += m[j].z; sum.w += m[j].w;
         }
       }
       tc::fence_async_smem();
-      tc::mbar_arrive(&s.gx_free);  // ... and with the g_x1 tile
+      tc::mbar_arrive(&s.gx_free);  // ... and with the g_x1 / residual tiles
     }
-    if (cur < n_hi) advance(n_hi);
+    if (cur < n_hi) {  // the last node of the range and the edge-less nodes behind it
+      st4(d.grad_x_src + (size_t)cur * kRow + toff, make_float4(sum.x + init.x, sum.y + init.y, sum.z + init.z, sum.w + init.w));
+      fill_gap(cur + 1, n_hi);
+    }
   } else {
     // =========================================== role C2 (4 warps: 64 accumulator columns per thread) ================
     for (int t = 0; t < n_tiles; ++t) {
@@ -2018,12 +2033,14 @@ int grl_fbconv_edge_fused_bwd(const GrlFusedEdgeDesc* d, grl_stream_t stream) {
     return e[0] == 'w' && e[1] == 's' && e[2] >= '1' && e[2] <= '3' ? e[2] - '0' : 3;
   }();
   if (gen == 3) {
-    alignas(64) CUtensorMap tm_gx, tm_xs;
+    alignas(64) CUtensorMap tm_gx, tm_xs, tm_in;
     if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
     if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
+    // residual rows (optional): an unused map over x_src keeps the kernel signature fixed when there are none
+    if (grl::make_row_tensor_map(&tm_in, d->grad_x_src_init ? d->grad_x_src_init : d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
     const int smem = (int)sizeof(grl::FusedBwdWs3Smem) + 1024;
     if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws3_kernel, smem) != GRL_OK) return GRL_ECUDA;
-    grl::edge_fused_bwd_ws3_kernel<<<d->n_partials, grl::kWs3Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs);
+    grl::edge_fused_bwd_ws3_kernel<<<d->n_partials, grl::kWs3Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs, tm_in);
   } else if (gen == 2) {
     alignas(64) CUtensorMap tm_gx, tm_xs;
     if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
