@@ -544,11 +544,14 @@ def run_ours(args):
 
 def main():
     args = parse()
-    # the contract is ONE JSON line on stdout: library chatter goes to stderr
-    real_stdout = sys.stdout
+    # the contract is ONE JSON line on stdout: library chatter goes to stderr — at the file-descriptor level too, because
+    # NCCL prints its version banner with C stdio ("NCCL version 2.28.9+cuda12.9")
+    sys.stdout.flush()
+    real_fd = os.dup(1)
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     global _emit
-    _emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
+    _emit = lambda line: os.write(real_fd, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:

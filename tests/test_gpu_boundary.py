@@ -7,7 +7,7 @@ The fixtures were produced by the UNMODIFIED reference wrappers driving the unmo
   * `GNNVFNet(gnn=DeepSets, hyper_data=*TasksData)(*obs)` for 2-D and 3-D observations — what ValueOperator / GAE call
     (value/gnn_vf_net.py:50-102, utils_algo_graph.py:200-203).
 Here the repo's wrappers + bodies + data builders load those state dicts with strict=True and must reproduce outputs
-(1e-5) and every parameter gradient (2e-5) from the same flat observation tensors."""
+(1e-5) and every parameter gradient (1e-5) from the same flat observation tensors."""
 import pytest
 import torch
 
@@ -39,7 +39,7 @@ def test_policy_wrapper_matches_the_reference_caller(name):
     for k, g in rec["grads"].items():
         if g is None:
             assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0, k
-        elif G.rel(params[k].grad, g) >= 2e-5:
+        elif G.rel(params[k].grad, g) >= 1e-5:
             bad.append(G.err_report(k, params[k].grad, g))
     assert not bad, "\n".join(bad)
 
@@ -62,5 +62,5 @@ def test_value_wrapper_matches_the_reference_caller():
     (v3 * rec["w"].cuda()).sum().backward()
     params = dict(vf.named_parameters())
     bad = [G.err_report(k, params[k].grad, g) for k, g in rec["grads"].items()
-           if g is not None and G.rel(params[k].grad, g) >= 2e-5]
+           if g is not None and G.rel(params[k].grad, g) >= 1e-5]
     assert not bad, "\n".join(bad)

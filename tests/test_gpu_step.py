@@ -1,9 +1,11 @@
 """GPU parity of the whole update step (`-m gpu`): graph features -> policy -> head -> TRPL projection ->
 TRPLLoss -> critic -> both backward passes, and of the advantage phase (batched-over-time critic + GAE
 kernel), against the CPU oracle (oracle/step.py) on the same seeded synthetic inputs.
-Tolerances: losses 1e-5 relative; gradients 5e-5 relative to each tensor's max (fp32 accumulations over
-B*N*16 rows in a different order than torch's CPU kernels); W2 gradients 1e-4 (the reference's own fp32
-result is that far from an fp64 evaluation, see tests/test_oracle_golden.py::test_w2_grad_noise_floor)."""
+Tolerances: losses and gradients 1e-5 (north_star's fp32 bound), gradients relative to each tensor's max magnitude.
+Measured (tools/fp32_parity_report.py -> profiles/r02_fp32_parity.json): the CUDA path is at most 7.0e-6 from the fp32
+oracle and 5.2e-6 from an fp64 evaluation of it over all five configs — closer to fp64 than the CPU fp32 oracle itself
+(1.1e-5 worst, tests/test_fp32_noise_floor.py).  W2 covariance gradients 1e-4: the reference's own fp32 result is 4e-5 away
+from an fp64 evaluation there (tests/test_oracle_golden.py::test_w2_grad_noise_floor)."""
 import pytest
 import torch
 
@@ -56,7 +58,7 @@ def test_update_step_matches_oracle(cfg_name, proj_type):
         a, b = float(out[k]), float(ref[k])
         if not abs(a - b) <= 1e-5 * abs(b) + 2e-7:
             bad.append(f"{k}: {a} vs {b}")
-    gtol = 1e-4 if proj_type == "w2" else 5e-5
+    gtol = 1e-4 if proj_type == "w2" else 1e-5
     pol = dict(actor.get_submodule("0").module.named_parameters())
     n_checked = 0
     for k, g in ga.items():
@@ -69,7 +71,7 @@ def test_update_step_matches_oracle(cfg_name, proj_type):
         n_checked += 1
     vf = dict(critic.module._network1.named_parameters())
     for k, g in gc.items():
-        if G.rel(vf[k].grad, g) >= 5e-5:
+        if G.rel(vf[k].grad, g) >= 1e-5:
             bad.append(G.err_report("critic " + k, vf[k].grad, g))
         n_checked += 1
     assert n_checked >= 30
@@ -162,7 +164,7 @@ def test_fused_and_unfused_loss_modules_agree():
     assert set(o1) == set(o0)
     bad = [f"{k}: {o1[k]} vs {o0[k]}" for k in o0 if not abs(o1[k] - o0[k]) <= 1e-5 * abs(o0[k]) + 2e-7]
     assert set(g1) == set(g0)
-    bad += [G.err_report(k, g1[k], g0[k]) for k in g0 if G.rel(g1[k], g0[k]) >= 2e-5]
+    bad += [G.err_report(k, g1[k], g0[k]) for k in g0 if G.rel(g1[k], g0[k]) >= 1e-5]
     assert not bad, "\n".join(bad)
 
 
@@ -208,9 +210,9 @@ def test_advantage_phase_matches_oracle(cfg_name):
                        "terminated": roll["terminated"].unsqueeze(-1).cuda()})
     adv_module(td)
     assert td["advantage"].shape == (Benv, T, 1) and td["value_target"].shape == (Benv, T, 1)
-    assert G.rel(td["state_value"][..., 0], v_ref[:, :-1]) < 2e-5, G.err_report("value", td["state_value"][..., 0], v_ref[:, :-1])
-    assert G.rel(td["advantage"][..., 0], a_ref) < 2e-5, G.err_report("adv", td["advantage"][..., 0], a_ref)
-    assert G.rel(td["value_target"][..., 0], vt_ref) < 2e-5
+    assert G.rel(td["state_value"][..., 0], v_ref[:, :-1]) < 1e-5, G.err_report("value", td["state_value"][..., 0], v_ref[:, :-1])
+    assert G.rel(td["advantage"][..., 0], a_ref) < 1e-5, G.err_report("adv", td["advantage"][..., 0], a_ref)
+    assert G.rel(td["value_target"][..., 0], vt_ref) < 1e-5
 
 
 def test_learner_update_changes_parameters_and_is_deterministic():

@@ -3,7 +3,7 @@ edge kernels, tcgen05 node kernels) against the CPU oracle (oracle/step.py, fp32
 
   * all four message-passing configs, eager: the 13 loss / metric scalars and every actor gradient (after the projection
     and the loss backward) within north_star's 16-bit bound, 1e-2 of each tensor's max magnitude; the critic branch is
-    not a 16-bit path (fp32 library GEMMs, TF32 off in tests and in bench.py) and stays at the fp32 bound, 5e-5;
+    not a 16-bit path (fp32 library GEMMs, TF32 off in tests and in bench.py) and stays at the fp32 bound, 1e-5;
   * the headline workload at B = 1024 through `Learner.capture` / `update_graphed` (CUDA-graph replay, critic branch on
     its second stream): gradients read back from the learner's flat bucket;
   * `Learner.fit` over a `DeviceRolloutBuffer` == the same permutation fed by hand (bit-identical parameters).
@@ -66,7 +66,7 @@ def _compare(out, ref, grads_actor, ga, grads_critic, gc, report):
             bad.append(G.err_report(k, grads_actor[k], g))
         n += 1
     for k, g in gc.items():
-        if G.rel(grads_critic[k], g) >= 5e-5:
+        if G.rel(grads_critic[k], g) >= 1e-5:
             bad.append(G.err_report("critic " + k, grads_critic[k], g))
         n += 1
     assert n >= 30
