@@ -1555,7 +1555,7 @@ edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
 // Hand-offs: full[b] (R -> C1, C2), bar_c[1] = the g_basis MMA's commit (C1 -> C2), b2_free (C2 -> C1: the g_basis / gH1
 // columns may be overwritten), empty[b] = the last MMA's commit (C2 -> R, C1: operand set b and gradient image b are free).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kWs3Threads = 672;
+constexpr int kWs3Threads = 800;
 
 struct FusedBwdWs3Smem {
   float GX[kTM * kC];            // [8 entries][2 halves][16 rows][32 floats]: 2 KB boxes at 1024-byte multiples, swizzled by TMA
@@ -1584,8 +1584,8 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
   FusedBwdWs3Smem& s = *reinterpret_cast<FusedBwdWs3Smem*>(
       smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));  // the swizzle atoms want a 1024-byte aligned base
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int role = warp < 8 ? 0 : (warp < 16 ? 1 : (warp < 20 ? 2 : 3));  // R, C1, C2, producer
-  const int rw = role == 2 ? warp - 16 : (warp & 7);                      // warp index inside the role
+  const int role = warp < 8 ? 0 : (warp < 16 ? 1 : (warp < 24 ? 2 : 3));  // R, C1, C2, producer
+  const int rw = warp & 7;                                                // warp index inside the role
   const int rt = rw * 32 + lane;
   const int q = rw & 3, ch = rw >> 2, row = 32 * q + lane;
   if (tid == 0) {
@@ -1867,7 +1867,7 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       fill_gap(cur + 1, n_hi);
     }
   } else {
-    // =========================================== role C2 (4 warps: 64 accumulator columns per thread) ================
+    // =========================================== role C2 ==========================================================
     for (int t = 0; t < n_tiles; ++t) {
       const int b = t & 1;
       const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
@@ -1879,8 +1879,8 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       tc::mbar_wait(&s.full[b], parb);      // the derivative planes of set b are in TMEM
       tc::mbar_wait(&s.bar_c[1], par);      // g_basis is complete (and the MMAs that read g_kern from G[b] are done)
       tc::tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {  // 32 columns at a time
+      {
+        const int h = ch;  // this warp's 32 columns
         uint32_t dpk[16];
         tc::tmem_ld16_raw(lane_addr + kSet + 32 + 16 * h, dpk);  // GELU'(pre2), columns 32 h .. 32 h + 31
         float gp2[32];
@@ -1903,7 +1903,7 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       }
       tc::fence_async_smem();
       tc::tc_fence_before();
-      tc::group_sync(3, 128);  // (F)
+      tc::group_sync(3, 256);  // (F)
       if (rt == 0) {
         tc::tc_fence_after();
         // gH1 = gP2 W2 (W2 image read MN-major: K = n, N = k) over the g_basis columns
@@ -1914,8 +1914,8 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       }
       tc::mbar_wait(&s.bar_c[2], par);
       tc::tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      {
+        const int h = ch;
         uint32_t dpk[16];
         tc::tmem_ld16_raw(lane_addr + kSet + 16 * h, dpk);  // GELU'(pre1)
 #pragma unroll
@@ -1935,7 +1935,7 @@ edge_fused_bwd_ws3_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUte
       }
       tc::fence_async_smem();
       tc::tc_fence_before();
-      tc::group_sync(3, 128);  // (G)
+      tc::group_sync(3, 256);  // (G)
       if (rt == 0) {
         tc::mbar_arrive(&s.b2_free);  // every C2 thread has read gH1: role C1 may issue the next g_basis MMA
         tc::tc_fence_after();
