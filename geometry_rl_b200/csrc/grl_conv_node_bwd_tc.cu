@@ -15,6 +15,8 @@
 // Reference: autograd of ponita/conv.py:88-114 (FiberBundleConv.forward node part).
 // Operand images are [chunk][row][8] 16-bit (grl_tc.cuh); the SAME image is read K-major (activation x weight)
 // and MN-major (weight gradients X^T Y, products with W instead of W^T) so nothing is ever transposed.
+#include <stdlib.h>
+
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
 
@@ -404,6 +406,831 @@ __global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(con
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Kernel (1b): warp-specialised, quarter-pipelined version of kernel (1)  (the default).
+//   * 16 epilogue warps (512 threads, thread = tile row x 16-column group) + ONE MMA-issue warp (one elected lane).
+//     The roles meet only through mbarriers: `full[b]` (tcgen05.commit -> epilogue, accumulator buffer b holds a fresh
+//     result), `edone[b]` (16 warp arrivals -> MMA warp: buffer b has been read and the operand quarter derived from it
+//     is in shared memory), `lnready` (y / grad_out operands of the tile are staged), `gyfull` (every MMA of the tile
+//     has retired).  No CTA-wide barrier inside the hidden-layer phase.
+//   * the hidden layer is walked in four 64-column quarters over TWO 64-column accumulator buffers: while the epilogue
+//     warps turn quarter q into h / GELU' (E1) or gPre (E2), the tensor pipe already computes the next quarter into
+//     the other buffer, and the weight-gradient / gY MMAs of a finished half run underneath the following epilogues
+//     (the tensor pipe retires MMAs in issue order, so a later `full` wait covers them).
+//     issue order per tile:  pre0 pre1 | gH0 | gH1 dW2(h0) | pre2 | pre3 gY(h0) dW1(h0) | gH2 | gH3 dW2(h1) | - |
+//                            gY(h1) dW1(h1) -> gyfull
+//     epilogue order:        E1(0) E1(1) E2(0) E2(1) E1(2) E1(3) E2(2) E2(3), LayerNorm backward, LayerNorm forward
+//                            of the next tile.
+// TMEM columns: D0 0..63 | D1 64..127 | gY 128..191 | dW1 192..351 (2 x 80) | dW2^T 352..479 (2 x 64).
+// Shared memory, operand images, fp16 formats, gradient scale: as kernel (1).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kNB3Epi = 512;
+constexpr int kNB3Threads = kNB3Epi + 32;
+constexpr uint32_t kCol3D0 = 0, kCol3D1 = 64, kCol3GY = 128, kCol3DW1 = 192, kCol3DW2 = 352;
+
+struct NodeBwd3Smem {
+  __half W1h[kH * kKb];
+  __half W2h[kC * kH];
+  __half A1[kTM * kKb];
+  __half GZh[kTM * kC];
+  union {
+    struct {
+      float X2[kTM * kLDX2];
+      float GZf[kTM * kLDX2];
+    } in;
+    struct {
+      __half A2h[kTM * 128];
+      __half AP[kTM * 128];
+    } h;
+  } u;
+  float bias[kC], lng[kC], lnb[kC];
+  float rs[2][4][kTM];
+  float acc_gb2[4][kC], acc_glng[4][kC], acc_glnb[4][kC];
+  uint64_t full[2], edone[2], lnready, gyfull;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(const GrlConvDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NodeBwd3Smem& s = *reinterpret_cast<NodeBwd3Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_epi = warp < 16;
+  const int q = warp & 3, cg = (warp >> 2) & 3;  // TMEM lane quarter / 16-column group of an epilogue warp
+  const int row = 32 * q + lane;
+
+  if (tid == 0) {
+    tc::mbar_init(&s.full[0], 1);
+    tc::mbar_init(&s.full[1], 1);
+    tc::mbar_init(&s.edone[0], 16);
+    tc::mbar_init(&s.edone[1], 16);
+    tc::mbar_init(&s.lnready, 16);
+    tc::mbar_init(&s.gyfull, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 16) tc::tmem_alloc(&s.tmem_base, 512);
+  tc::stage_weight_f16(s.W1h, d.w1, kH, kC, kC);
+  tc::stage_weight_f16(s.W2h, d.w2, kC, kH, kH);
+  for (int n = tid; n < kH; n += kNB3Threads) {
+    const float b = d.b1[n];
+    const __half hi = __float2half_rn(b);
+    const __half lo = __float2half_rn(b - __half2float(hi));
+    const __half2 p0 = __halves2half2(hi, lo);
+    *reinterpret_cast<uint4*>(s.W1h + ((size_t)8 * kH + n) * 8) = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s.W1h + ((size_t)9 * kH + n) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < kTM) {
+    *reinterpret_cast<uint4*>(s.A1 + ((size_t)8 * kTM + tid) * 8) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s.A1 + ((size_t)9 * kTM + tid) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < kC) { s.bias[tid] = d.bias[tid]; s.lng[tid] = d.ln_g[tid]; s.lnb[tid] = d.ln_b[tid]; }
+  for (int i = tid; i < 4 * kC; i += kNB3Threads) {
+    (&s.acc_gb2[0][0])[i] = 0.f; (&s.acc_glng[0][0])[i] = 0.f; (&s.acc_glnb[0][0])[i] = 0.f;
+  }
+  const float gscale = d.grad_amax ? tc::grad_scale_from_amax(__ldg(d.grad_amax)) : 1.0f;
+  const float inv_gscale = 1.0f / gscale;
+  const int n_tiles = (d.n_dst + kTE - 1) / kTE;
+  int tile = blockIdx.x;
+  auto stage_x2 = [&](int t) {  // epilogue threads only
+    const int cnt = min(kTE, d.n_dst - t * kTE);
+    const float* src = d.x2 + (size_t)t * kTE * kRow;
+    const float* gsrc = d.grad_out + (size_t)t * kTE * kRow;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + kNB3Epi * i;
+      const int so = (f >> 4) * kLDX2 + 4 * (f & 15);
+      if ((f >> 8) < cnt) {
+        cp_async16(s.u.in.X2 + so, src + 4 * f);
+        cp_async16(s.u.in.GZf + so, gsrc + 4 * f);
+      } else {
+        *reinterpret_cast<float4*>(s.u.in.X2 + so) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s.u.in.GZf + so) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  if (is_epi && tile < n_tiles) {
+    stage_x2(tile);
+    cp_async_commit();
+  }
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const uint32_t a1 = tc::smem_u32(s.A1), gz = tc::smem_u32(s.GZh), a2 = tc::smem_u32(s.u.h.A2h), ap = tc::smem_u32(s.u.h.AP);
+  const uint32_t w1 = tc::smem_u32(s.W1h), w2 = tc::smem_u32(s.W2h);
+  bool first_tile = true;
+
+  if (!is_epi) {
+    // ================= MMA-issue warp: warp-uniform loop, one elected lane issues =================
+    uint32_t p_ln = 0, p_e0 = 0, p_e1 = 0;
+    constexpr uint32_t id_pre = tc::idesc_f16_ex(128, 64, 0, 0, 0, 0);
+    constexpr uint32_t id_gh = tc::idesc_f16_ex(128, 64, 0, 1, 0, 0);
+    constexpr uint32_t id_dw2 = tc::idesc_f16_ex(128, 64, 1, 1, 0, 0);
+    constexpr uint32_t id_dw1 = tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0);
+    const tc::Op a1_k = tc::op_k(a1, kTM), a1_mn = tc::op_mn(a1, kTM);
+    const tc::Op gz_k = tc::op_k(gz, kTM), gz_mn = tc::op_mn(gz, kTM);
+    const tc::Op a2_mn = tc::op_mn(a2, kTM), ap_k = tc::op_k(ap, kTM), ap_mn = tc::op_mn(ap, kTM);
+    const tc::Op w1_k = tc::op_k(w1, kH), w1_mn = tc::op_mn(w1, kH), w2_mn = tc::op_mn(w2, kC);
+    auto shifted = [](tc::Op o, uint32_t bytes) { o.lo += bytes >> 4; return o; };
+    // pre(qq) = [y | 1 1 0..] [W1 | b1]^T, rows 64 qq .. of W1;  gH'(qq) = gZ' W2[:, quarter]  (W2h MN-major: N = k', K = n)
+    auto pre = [&](int qq, uint32_t col) { tc::issue_mma_fast<kKb / 16>(tmem + col, a1_k, shifted(w1_k, 64u * qq * 16u), id_pre, false); };
+    auto gh = [&](int qq, uint32_t col) { tc::issue_mma_fast<kC / 16>(tmem + col, gz_k, shifted(w2_mn, 8u * qq * (kC * 16u)), id_gh, false); };
+    for (; tile < n_tiles; tile += gridDim.x) {
+      tc::mbar_wait(&s.lnready, p_ln);
+      p_ln ^= 1u;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        pre(0, kCol3D0);
+        tc::mma_commit(&s.full[0]);
+        pre(1, kCol3D1);
+        tc::mma_commit(&s.full[1]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        tc::mbar_wait(&s.edone[0], p_e0);  // E1(2 hh): h quarter staged, D0 read
+        p_e0 ^= 1u;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          gh(2 * hh, kCol3D0);
+          tc::mma_commit(&s.full[0]);
+        }
+        __syncwarp();
+        tc::mbar_wait(&s.edone[1], p_e1);  // E1(2 hh + 1)
+        p_e1 ^= 1u;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          gh(2 * hh + 1, kCol3D1);
+          tc::mma_commit(&s.full[1]);
+          // dW2'^T[k'][n] += h^T gZ'  (both MN-major, K = tile rows); retires under the next epilogues
+          tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW2 + 64 * hh, a2_mn, gz_mn, id_dw2, !first_tile);
+        }
+        __syncwarp();
+        tc::mbar_wait(&s.edone[0], p_e0);  // E2(2 hh): gPre quarter staged, D0 read
+        p_e0 ^= 1u;
+        tc::tc_fence_after();
+        if (hh == 0) {
+          if (tc::elect_one()) {
+            pre(2, kCol3D0);
+            tc::mma_commit(&s.full[0]);
+          }
+          __syncwarp();
+        }
+        tc::mbar_wait(&s.edone[1], p_e1);  // E2(2 hh + 1)
+        p_e1 ^= 1u;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          if (hh == 0) {
+            pre(3, kCol3D1);
+            tc::mma_commit(&s.full[1]);
+          }
+          // gY' (+)= gPre' W1[half]  (W1h read MN-major: N = c, K = k');  [dW1' | gb1'] += gPre'^T [y | 1 1 0..]
+          tc::issue_mma_fast<128 / 16>(tmem + kCol3GY, ap_k, shifted(w1_mn, 128u * hh * 16u), id_gh, hh > 0);
+          tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW1 + kKb * hh, ap_mn, a1_mn, id_dw1, !first_tile);
+          if (hh == 1) tc::mma_commit(&s.gyfull);
+        }
+        __syncwarp();
+      }
+      first_tile = false;
+    }
+  } else {
+    // ================= epilogue warps =================
+    uint32_t pf0 = 0, pf1 = 0, pgy = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+      const int n0 = tile * kTE;
+      const int node = n0 + (row >> 4);
+      const bool live = node < d.n_dst;
+      const size_t roff = (size_t)(live ? node : 0) * kRow + (row & 15) * kC + 16 * cg;
+      if (tid == 0) {
+        const int nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          const uint32_t bytes = (uint32_t)min(kTE, d.n_dst - nt * kTE) * kRow * 4u;
+          tc::prefetch_l2(d.x2 + (size_t)nt * kTE * kRow, bytes);
+          tc::prefetch_l2(d.grad_out + (size_t)nt * kTE * kRow, bytes);
+        }
+      }
+      cp_async_wait_all();
+      tc::group_sync(1, kNB3Epi);
+
+      // ---- LayerNorm forward + scaled grad_out -> fp16 operands ------------------------------------------
+      float xh[16];
+      float rstd;
+      {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = ld4(s.u.in.X2 + row * kLDX2 + 16 * cg + 4 * i);
+          xh[4 * i] = v.x; xh[4 * i + 1] = v.y; xh[4 * i + 2] = v.z; xh[4 * i + 3] = v.w;
+          sum += (v.x + v.y) + (v.z + v.w);
+        }
+        float g16[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 gv = ld4(s.u.in.GZf + row * kLDX2 + 16 * cg + 4 * i);
+          g16[4 * i] = gv.x; g16[4 * i + 1] = gv.y; g16[4 * i + 2] = gv.z; g16[4 * i + 3] = gv.w;
+        }
+        s.rs[0][cg][row] = sum;
+        tc::group_sync(1, kNB3Epi);
+        const float mean = ((s.rs[0][0][row] + s.rs[0][1][row]) + (s.rs[0][2][row] + s.rs[0][3][row])) * (1.0f / 64.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { xh[i] -= mean; sq = fmaf(xh[i], xh[i], sq); }
+        s.rs[1][cg][row] = sq;
+        {
+          float gs[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gs[i] = g16[i] * gscale;
+          *reinterpret_cast<uint4*>(s.GZh + ((size_t)(2 * cg) * kTM + row) * 8) = tc::pack8_h(gs);
+          *reinterpret_cast<uint4*>(s.GZh + ((size_t)(2 * cg + 1) * kTM + row) * 8) = tc::pack8_h(gs + 8);
+        }
+        warp_colsum16(g16, lane);
+        if ((lane & 1) == 0) s.acc_gb2[q][16 * cg + (lane >> 1)] += g16[0];
+        tc::group_sync(1, kNB3Epi);
+        rstd = rsqrtf(((s.rs[1][0][row] + s.rs[1][1][row]) + (s.rs[1][2][row] + s.rs[1][3][row])) * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = 16 * cg + 8 * i + e;
+            xh[8 * i + e] *= rstd;
+            y[e] = xh[8 * i + e] * s.lng[c] + s.lnb[c];
+          }
+          *reinterpret_cast<uint4*>(s.A1 + ((size_t)(2 * cg + i) * kTM + row) * 8) = tc::pack8_h(y);
+        }
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.lnready);
+
+      // ---- hidden layer: four quarters over two accumulator buffers ----------------------------------------
+      __half2 dG0[8], dG1[8];
+      auto e1 = [&](uint32_t col, uint64_t* fullb, uint32_t& pf, uint64_t* doneb, __half2 (&dG)[8], int chunk) {
+        tc::mbar_wait(fullb, pf);
+        pf ^= 1u;
+        tc::tc_fence_after();
+        float v[16];
+        tc::tmem_ld16(lane_addr + col + 16 * cg, v);
+        __half2 h0[4], h1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), h0[e], dG[e]);
+          tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), h1[e], dG[4 + e]);
+        }
+        *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)chunk * kTM + row) * 8) = tc::pack_h8(h0);
+        *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)(chunk + 1) * kTM + row) * 8) = tc::pack_h8(h1);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(doneb);
+      };
+      auto e2 = [&](uint32_t col, uint64_t* fullb, uint32_t& pf, uint64_t* doneb, const __half2 (&dG)[8], int chunk) {
+        tc::mbar_wait(fullb, pf);
+        pf ^= 1u;
+        tc::tc_fence_after();
+        float v[16];
+        tc::tmem_ld16(lane_addr + col + 16 * cg, v);
+        __half2 p0[4], p1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p0[e] = __hmul2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), dG[e]);
+          p1[e] = __hmul2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), dG[4 + e]);
+        }
+        *reinterpret_cast<uint4*>(s.u.h.AP + ((size_t)chunk * kTM + row) * 8) = tc::pack_h8(p0);
+        *reinterpret_cast<uint4*>(s.u.h.AP + ((size_t)(chunk + 1) * kTM + row) * 8) = tc::pack_h8(p1);
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(doneb);
+      };
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        e1(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 2 * cg);
+        e1(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 2 * cg);
+        e2(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 2 * cg);
+        e2(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 2 * cg);
+      }
+      tc::mbar_wait(&s.gyfull, pgy);  // every MMA of this tile has retired: gY is final, the operand buffers are free
+      pgy ^= 1u;
+      tc::tc_fence_after();
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          stage_x2(nt);
+          cp_async_commit();
+        }
+      }
+
+      // ---- LayerNorm backward: gY (TMEM) -> g_x2 (HBM), g_ln_g, g_ln_b -----------------------------------
+      {
+        float gy[32];
+        {
+          float v[16];
+          tc::tmem_ld16(lane_addr + kCol3GY + 16 * cg, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) gy[e] = v[e] * inv_gscale;
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float hx = gy[i] * s.lng[16 * cg + i];
+          s1 += hx;
+          s2 = fmaf(hx, xh[i], s2);
+        }
+        s.rs[0][cg][row] = s1;
+        s.rs[1][cg][row] = s2;
+        tc::group_sync(1, kNB3Epi);
+        const float m1 = ((s.rs[0][0][row] + s.rs[0][1][row]) + (s.rs[0][2][row] + s.rs[0][3][row])) * (1.0f / 64.0f);
+        const float m2 = ((s.rs[1][0][row] + s.rs[1][1][row]) + (s.rs[1][2][row] + s.rs[1][3][row])) * (1.0f / 64.0f);
+        float* gdst = d.grad_x2 + roff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * i + e;
+            const float hx = gy[c] * s.lng[16 * cg + c];
+            o[e] = rstd * (hx - m1 - xh[c] * m2);
+          }
+          if (live) st4(gdst + 4 * i, make_float4(o[0], o[1], o[2], o[3]));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gy[16 + i] = gy[i] * xh[i];
+        tc::warp_colsum<32>(gy, lane);
+        if (lane < 16) s.acc_glnb[q][16 * cg + lane] += gy[0];
+        else s.acc_glng[q][16 * cg + lane - 16] += gy[0];
+      }
+      tc::tc_fence_before();
+      first_tile = false;
+    }
+    cp_async_wait_all();
+  }
+
+  // ---- write this CTA's partial slot ---------------------------------------------------------------------------
+  __syncthreads();
+  tc::tc_fence_after();
+  float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
+  if (is_epi) {
+#pragma unroll 1
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int c0 = 16 * cg;
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = 0.f;
+      if (!first_tile) tc::tmem_ld16(lane_addr + kCol3DW1 + kKb * h2 + c0, v);
+      float* p1 = P + kPGW1 + (size_t)(128 * h2 + row) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        st4(p1 + e, make_float4(v[e] * inv_gscale, v[e + 1] * inv_gscale, v[e + 2] * inv_gscale, v[e + 3] * inv_gscale));
+      if (cg == 0) {
+        float b[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) b[e] = 0.f;
+        if (!first_tile) tc::tmem_ld16(lane_addr + kCol3DW1 + kKb * h2 + 64, b);
+        P[kPGB1 + 128 * h2 + row] = b[0] * inv_gscale;
+      }
+      if (!first_tile) tc::tmem_ld16(lane_addr + kCol3DW2 + 64 * h2 + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) P[kPGW2 + (size_t)(c0 + e) * kH + 128 * h2 + row] = v[e] * inv_gscale;
+    }
+  }
+  if (tid < kC) {
+    P[kPGB2 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
+    P[kPGLNG + tid] = ((s.acc_glng[0][tid] + s.acc_glng[1][tid]) + s.acc_glng[2][tid]) + s.acc_glng[3][tid];
+    P[kPGLNB + tid] = ((s.acc_glnb[0][tid] + s.acc_glnb[1][tid]) + s.acc_glnb[2][tid]) + s.acc_glnb[3][tid];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Kernel (1c): three roles, tiles overlapped (the default).
+//   * 8 ROW warps     (thread = tile row x 32-channel half): LayerNorm forward of tile i+1 (x2 / grad_out rows read
+//                      straight from global memory, one 128-byte line per thread, L2-prefetched two tiles ahead) into the
+//                      double-buffered fp16 operand images A1 / GZh, and LayerNorm backward of tile i (gY out of TMEM,
+//                      x-hat recomputed from the re-read x2 row and the saved row statistics) -> g_x2;
+//   * 8 EPILOGUE warps (thread = tile row x 32 columns of a hidden quarter): GELU / GELU' (E1) and gPre (E2) of the four
+//                      hidden quarters, nothing else - they never touch global memory and never meet a CTA barrier;
+//   * 1 MMA warp:      the issue order of kernel (1b) with the next tile's first two `pre` quarters issued as soon as
+//                      their accumulator buffers drain.
+//   mbarriers: full[b] (commit -> epilogue), edone[b] (8 epilogue warps -> MMA), lnready[buf] (8 row warps -> MMA),
+//   gyfull (commit -> row warps: every MMA of the tile retired, gY final, operand buffers of the tile free),
+//   gyfree (8 row warps -> MMA: gY has been read out of TMEM).
+// TMEM columns as kernel (1b).  Shared memory: W1h 40 K | W2h 32 K | A1 2 x 20 K | GZh 2 x 16 K | A2h 32 K | AP 32 K.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kNB4Threads = 17 * 32;
+struct NodeBwd4Smem {
+  __half W1h[kH * kKb];
+  __half W2h[kC * kH];
+  __half A1[2][kTM * kKb];
+  __half GZh[2][kTM * kC];
+  __half A2h[kTM * 128];
+  __half AP[kTM * 128];
+  float lng[kC], lnb[kC];
+  float rs[2][2][kTM];        // row partial sums exchanged between the two channel halves (LayerNorm forward)
+  float rsb[2][2][kTM];       // the same for the LayerNorm backward
+  float stat[2][2][kTM];      // [buffer][mean | rstd][row] saved by the LayerNorm forward for its backward
+  float acc_gb2[4][kC], acc_glng[4][kC], acc_glnb[4][kC];
+  uint64_t full[2], edone[2], lnready[2], gyfull, gyfree;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kNB4Threads, 1) fbconv_node_bwd_tc4_kernel(const GrlConvDesc d) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NodeBwd4Smem& s = *reinterpret_cast<NodeBwd4Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3;            // TMEM lane quarter of this warp
+  const int row = 32 * q + lane;     // tile row owned by a row / epilogue thread
+  const int j = (warp >> 2) & 1;     // 32-channel half (row warps) / 32-column half of a quarter (epilogue warps)
+
+  if (tid == 0) {
+    tc::mbar_init(&s.full[0], 1);
+    tc::mbar_init(&s.full[1], 1);
+    tc::mbar_init(&s.edone[0], 8);
+    tc::mbar_init(&s.edone[1], 8);
+    tc::mbar_init(&s.lnready[0], 8);
+    tc::mbar_init(&s.lnready[1], 8);
+    tc::mbar_init(&s.gyfull, 1);
+    tc::mbar_init(&s.gyfree, 8);
+    tc::fence_mbar_init();
+  }
+  if (warp == 16) tc::tmem_alloc(&s.tmem_base, 512);
+  tc::stage_weight_f16(s.W1h, d.w1, kH, kC, kC);
+  tc::stage_weight_f16(s.W2h, d.w2, kC, kH, kH);
+  for (int n = tid; n < kH; n += kNB4Threads) {
+    const float b = d.b1[n];
+    const __half hi = __float2half_rn(b);
+    const __half lo = __float2half_rn(b - __half2float(hi));
+    const __half2 p0 = __halves2half2(hi, lo);
+    *reinterpret_cast<uint4*>(s.W1h + ((size_t)8 * kH + n) * 8) = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(s.W1h + ((size_t)9 * kH + n) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < 2 * kTM) {  // ones columns of both y images
+    __half* a = s.A1[tid >> 7];
+    const int r = tid & 127;
+    *reinterpret_cast<uint4*>(a + ((size_t)8 * kTM + r) * 8) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(a + ((size_t)9 * kTM + r) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid < kC) { s.lng[tid] = d.ln_g[tid]; s.lnb[tid] = d.ln_b[tid]; }
+  for (int i = tid; i < 4 * kC; i += kNB4Threads) {
+    (&s.acc_gb2[0][0])[i] = 0.f; (&s.acc_glng[0][0])[i] = 0.f; (&s.acc_glnb[0][0])[i] = 0.f;
+  }
+  const float gscale = d.grad_amax ? tc::grad_scale_from_amax(__ldg(d.grad_amax)) : 1.0f;
+  const float inv_gscale = 1.0f / gscale;
+  const int n_tiles = (d.n_dst + kTE - 1) / kTE;
+  const int tile0 = blockIdx.x, stride = gridDim.x;
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
+  const bool any_tile = tile0 < n_tiles;
+
+  if (warp == 16) {
+    // ================= MMA-issue warp =================
+    constexpr uint32_t id_pre = tc::idesc_f16_ex(128, 64, 0, 0, 0, 0);
+    constexpr uint32_t id_gh = tc::idesc_f16_ex(128, 64, 0, 1, 0, 0);
+    constexpr uint32_t id_dw2 = tc::idesc_f16_ex(128, 64, 1, 1, 0, 0);
+    constexpr uint32_t id_dw1 = tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0);
+    const uint32_t a1b = tc::smem_u32(s.A1[0]), gzb = tc::smem_u32(s.GZh[0]);
+    const uint32_t a2 = tc::smem_u32(s.A2h), ap = tc::smem_u32(s.AP), w1 = tc::smem_u32(s.W1h), w2 = tc::smem_u32(s.W2h);
+    constexpr uint32_t kA1Bytes = kTM * kKb * 2, kGZBytes = kTM * kC * 2;
+    const tc::Op a2_mn = tc::op_mn(a2, kTM), ap_k = tc::op_k(ap, kTM), ap_mn = tc::op_mn(ap, kTM);
+    const tc::Op w1_k = tc::op_k(w1, kH), w1_mn = tc::op_mn(w1, kH), w2_mn = tc::op_mn(w2, kC);
+    auto shifted = [](tc::Op o, uint32_t bytes) { o.lo += bytes >> 4; return o; };
+    uint32_t p_ln0 = 0, p_ln1 = 0, p_e0 = 0, p_e1 = 0, p_gf = 0;
+    bool first_tile = true;
+    int it = 0;
+    if (any_tile) {  // first tile: its two leading quarters
+      tc::mbar_wait(&s.lnready[0], p_ln0);
+      p_ln0 ^= 1u;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
+        const tc::Op a1_k = tc::op_k(a1b, kTM);
+        tc::issue_mma_fast<kKb / 16>(tmem + kCol3D0, a1_k, w1_k, id_pre, false);
+        tc::mma_commit(&s.full[0]);
+        tc::issue_mma_fast<kKb / 16>(tmem + kCol3D1, a1_k, shifted(w1_k, 64u * 16u), id_pre, false);
+        tc::mma_commit(&s.full[1]);
+      }
+      __syncwarp();
+    }
+    for (int tile = tile0; tile < n_tiles; tile += stride, ++it) {
+      const int buf = it & 1;
+      const bool has_next = tile + stride < n_tiles;
+      const tc::Op a1_k = tc::op_k(a1b + buf * kA1Bytes, kTM), a1_mn = tc::op_mn(a1b + buf * kA1Bytes, kTM);
+      const tc::Op gz_k = tc::op_k(gzb + buf * kGZBytes, kTM), gz_mn = tc::op_mn(gzb + buf * kGZBytes, kTM);
+      const tc::Op a1n_k = tc::op_k(a1b + (buf ^ 1) * kA1Bytes, kTM);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        tc::mbar_wait(&s.edone[0], p_e0);  // E1(2 hh): h quarter staged, D0 read
+        p_e0 ^= 1u;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          // gH'(quarter) = gZ' W2[:, quarter]  (W2h MN-major: N = k', K = n)
+          tc::issue_mma_fast<kC / 16>(tmem + kCol3D0, gz_k, shifted(w2_mn, 8u * (2 * hh) * (kC * 16u)), id_gh, false);
+          tc::mma_commit(&s.full[0]);
+        }
+        __syncwarp();
+        tc::mbar_wait(&s.edone[1], p_e1);  // E1(2 hh + 1)
+        p_e1 ^= 1u;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          tc::issue_mma_fast<kC / 16>(tmem + kCol3D1, gz_k, shifted(w2_mn, 8u * (2 * hh + 1) * (kC * 16u)), id_gh, false);
+          tc::mma_commit(&s.full[1]);
+          // dW2'^T[k'][n] += h^T gZ'  (both MN-major, K = tile rows); retires under the next epilogues
+          tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW2 + 64 * hh, a2_mn, gz_mn, id_dw2, !first_tile);
+        }
+        __syncwarp();
+        tc::mbar_wait(&s.edone[0], p_e0);  // E2(2 hh): gPre quarter staged, D0 drained
+        p_e0 ^= 1u;
+        tc::tc_fence_after();
+        if (hh == 0) {
+          if (tc::elect_one()) {
+            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D0, a1_k, shifted(w1_k, 64u * 2u * 16u), id_pre, false);
+            tc::mma_commit(&s.full[0]);
+          }
+          __syncwarp();
+        } else if (has_next) {  // D0 is free for the rest of this tile: first quarter of the next one
+          if (buf) {
+            tc::mbar_wait(&s.lnready[0], p_ln0);
+            p_ln0 ^= 1u;
+          } else {
+            tc::mbar_wait(&s.lnready[1], p_ln1);
+            p_ln1 ^= 1u;
+          }
+          tc::tc_fence_after();
+          if (tc::elect_one()) {
+            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D0, a1n_k, w1_k, id_pre, false);
+            tc::mma_commit(&s.full[0]);
+          }
+          __syncwarp();
+        }
+        tc::mbar_wait(&s.edone[1], p_e1);  // E2(2 hh + 1)
+        p_e1 ^= 1u;
+        tc::tc_fence_after();
+        if (hh == 0 && it > 0) {  // gY of the previous tile must have been read out before it is overwritten
+          tc::mbar_wait(&s.gyfree, p_gf);
+          p_gf ^= 1u;
+          tc::tc_fence_after();
+        }
+        if (tc::elect_one()) {
+          if (hh == 0) {
+            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D1, a1_k, shifted(w1_k, 64u * 3u * 16u), id_pre, false);
+            tc::mma_commit(&s.full[1]);
+          } else if (has_next) {
+            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D1, a1n_k, shifted(w1_k, 64u * 16u), id_pre, false);
+            tc::mma_commit(&s.full[1]);
+          }
+          // gY' (+)= gPre' W1[half]  (W1h MN-major: N = c, K = k');  [dW1' | gb1'] += gPre'^T [y | 1 1 0..]
+          tc::issue_mma_fast<128 / 16>(tmem + kCol3GY, ap_k, shifted(w1_mn, 128u * hh * 16u), id_gh, hh > 0);
+          tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW1 + kKb * hh, ap_mn, a1_mn, id_dw1, !first_tile);
+          if (hh == 1) tc::mma_commit(&s.gyfull);
+        }
+        __syncwarp();
+      }
+      first_tile = false;
+    }
+  } else if (warp >= 8) {
+    // ================= epilogue warps: thread = (row, 32 columns 32 j .. of the quarter) =================
+    uint32_t pf0 = 0, pf1 = 0;
+    __half2 dG0[16], dG1[16];
+    auto e1 = [&](uint32_t col, uint64_t* fullb, uint32_t& pf, uint64_t* doneb, __half2 (&dG)[16], int chunk) {
+      tc::mbar_wait(fullb, pf);
+      pf ^= 1u;
+      tc::tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float v[16];
+        tc::tmem_ld16(lane_addr + col + 32 * j + 16 * i, v);
+        __half2 h0[4], h1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), h0[e], dG[8 * i + e]);
+          tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), h1[e], dG[8 * i + 4 + e]);
+        }
+        *reinterpret_cast<uint4*>(s.A2h + ((size_t)(chunk + 2 * i) * kTM + row) * 8) = tc::pack_h8(h0);
+        *reinterpret_cast<uint4*>(s.A2h + ((size_t)(chunk + 2 * i + 1) * kTM + row) * 8) = tc::pack_h8(h1);
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(doneb);
+    };
+    auto e2 = [&](uint32_t col, uint64_t* fullb, uint32_t& pf, uint64_t* doneb, const __half2 (&dG)[16], int chunk) {
+      tc::mbar_wait(fullb, pf);
+      pf ^= 1u;
+      tc::tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float v[16];
+        tc::tmem_ld16(lane_addr + col + 32 * j + 16 * i, v);
+        __half2 p0[4], p1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p0[e] = __hmul2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), dG[8 * i + e]);
+          p1[e] = __hmul2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), dG[8 * i + 4 + e]);
+        }
+        *reinterpret_cast<uint4*>(s.AP + ((size_t)(chunk + 2 * i) * kTM + row) * 8) = tc::pack_h8(p0);
+        *reinterpret_cast<uint4*>(s.AP + ((size_t)(chunk + 2 * i + 1) * kTM + row) * 8) = tc::pack_h8(p1);
+      }
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(doneb);
+    };
+    for (int tile = tile0; tile < n_tiles; tile += stride) {
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        e1(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 4 * j);
+        e1(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 4 * j);
+        e2(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 4 * j);
+        e2(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 4 * j);
+      }
+    }
+  } else {
+    // ================= row warps: thread = (row, channels 32 j .. 32 j + 31) =================
+    uint32_t pgy = 0;
+    auto row_ptr = [&](const float* base, int t) -> const float4* {  // nullptr for the padding rows of the last tile
+      const int node = t * kTE + (row >> 4);
+      return node < d.n_dst ? reinterpret_cast<const float4*>(base + (size_t)node * kRow + (row & 15) * kC + 32 * j) : nullptr;
+    };
+    auto ln_fwd = [&](int t, int buf) {
+      const float4* px = row_ptr(d.x2, t);
+      const float4* pg = row_ptr(d.grad_out, t);
+      float x[32], g[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = px ? __ldg(px + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = pg ? __ldg(pg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) sum += (x[i] + x[i + 1]) + (x[i + 2] + x[i + 3]);
+      s.rs[0][j][row] = sum;
+      tc::group_sync(2, 256);
+      const float mean = (s.rs[0][0][row] + s.rs[0][1][row]) * (1.0f / 64.0f);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { x[i] -= mean; sq = fmaf(x[i], x[i], sq); }
+      s.rs[1][j][row] = sq;
+      {  // scaled grad_out -> fp16 operand image (chunks 4 j .. 4 j + 3), gb2 column sums of the raw values
+        __half* gzh = s.GZh[buf];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float gs[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gs[e] = g[8 * c + e] * gscale;
+          *reinterpret_cast<uint4*>(gzh + ((size_t)(4 * j + c) * kTM + row) * 8) = tc::pack8_h(gs);
+        }
+        tc::warp_colsum<32>(g, lane);
+        s.acc_gb2[q][32 * j + lane] += g[0];
+      }
+      tc::group_sync(2, 256);
+      const float rstd = rsqrtf((s.rs[1][0][row] + s.rs[1][1][row]) * (1.0f / 64.0f) + 1e-5f);
+      if (j == 0) { s.stat[buf][0][row] = mean; s.stat[buf][1][row] = rstd; }
+      __half* a1 = s.A1[buf];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = 32 * j + 8 * c + e;
+          y[e] = x[8 * c + e] * rstd * s.lng[ch] + s.lnb[ch];
+        }
+        *reinterpret_cast<uint4*>(a1 + ((size_t)(4 * j + c) * kTM + row) * 8) = tc::pack8_h(y);
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.lnready[buf]);
+    };
+    auto ln_bwd = [&](int t, int buf) {
+      const float4* px = row_ptr(d.x2, t);
+      float xh[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // issued before the wait: the reload (an L2 hit) overlaps the tail of the tile's MMAs
+        const float4 v = px ? __ldg(px + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xh[4 * i] = v.x; xh[4 * i + 1] = v.y; xh[4 * i + 2] = v.z; xh[4 * i + 3] = v.w;
+      }
+      tc::mbar_wait(&s.gyfull, pgy);
+      pgy ^= 1u;
+      tc::tc_fence_after();
+      float gy[32];
+      {
+        float v[16];
+        tc::tmem_ld16(lane_addr + kCol3GY + 32 * j, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) gy[e] = v[e] * inv_gscale;
+        tc::tmem_ld16(lane_addr + kCol3GY + 32 * j + 16, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) gy[16 + e] = v[e] * inv_gscale;
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.gyfree);
+      const float mean = s.stat[buf][0][row], rstd = s.stat[buf][1][row];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        xh[i] = (xh[i] - mean) * rstd;
+        const float hx = gy[i] * s.lng[32 * j + i];
+        s1 += hx;
+        s2 = fmaf(hx, xh[i], s2);
+      }
+      s.rsb[0][j][row] = s1;
+      s.rsb[1][j][row] = s2;
+      tc::group_sync(2, 256);
+      const float m1 = (s.rsb[0][0][row] + s.rsb[0][1][row]) * (1.0f / 64.0f);
+      const float m2 = (s.rsb[1][0][row] + s.rsb[1][1][row]) * (1.0f / 64.0f);
+      const int node = t * kTE + (row >> 4);
+      if (node < d.n_dst) {
+        float4* gdst = reinterpret_cast<float4*>(d.grad_x2 + (size_t)node * kRow + (row & 15) * kC + 32 * j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * i + e;
+            o[e] = rstd * (gy[c] * s.lng[32 * j + c] - m1 - xh[c] * m2);
+          }
+          gdst[i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      // column sums over this warp's 32 rows: g_ln_g = sum gy * xhat, g_ln_b = sum gy
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xh[i] *= gy[i];
+      tc::warp_colsum<32>(xh, lane);
+      tc::warp_colsum<32>(gy, lane);
+      s.acc_glng[q][32 * j + lane] += xh[0];
+      s.acc_glnb[q][32 * j + lane] += gy[0];
+    };
+    auto prefetch = [&](int t) {
+      if (tid == 0 && t < n_tiles) {
+        const uint32_t bytes = (uint32_t)min(kTE, d.n_dst - t * kTE) * kRow * 4u;
+        tc::prefetch_l2(d.x2 + (size_t)t * kTE * kRow, bytes);
+        tc::prefetch_l2(d.grad_out + (size_t)t * kTE * kRow, bytes);
+      }
+    };
+    if (any_tile) {
+      prefetch(tile0 + stride);
+      ln_fwd(tile0, 0);
+    }
+    int it = 0;
+    for (int tile = tile0; tile < n_tiles; tile += stride, ++it) {
+      prefetch(tile + 2 * stride);
+      if (tile + stride < n_tiles) ln_fwd(tile + stride, (it + 1) & 1);
+      ln_bwd(tile, it & 1);
+    }
+  }
+
+  // ---- write this CTA's partial slot ---------------------------------------------------------------------------
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
+  if (warp < 16) {
+    const int cg = warp >> 2;  // 16-column group
+#pragma unroll 1
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int c0 = 16 * cg;
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = 0.f;
+      if (any_tile) tc::tmem_ld16(lane_addr + kCol3DW1 + kKb * h2 + c0, v);
+      float* p1 = P + kPGW1 + (size_t)(128 * h2 + row) * kC + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        st4(p1 + e, make_float4(v[e] * inv_gscale, v[e + 1] * inv_gscale, v[e + 2] * inv_gscale, v[e + 3] * inv_gscale));
+      if (cg == 0) {
+        float b[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) b[e] = 0.f;
+        if (any_tile) tc::tmem_ld16(lane_addr + kCol3DW1 + kKb * h2 + 64, b);
+        P[kPGB1 + 128 * h2 + row] = b[0] * inv_gscale;
+      }
+      if (any_tile) tc::tmem_ld16(lane_addr + kCol3DW2 + 64 * h2 + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) P[kPGW2 + (size_t)(c0 + e) * kH + 128 * h2 + row] = v[e] * inv_gscale;
+    }
+  }
+  if (tid < kC) {
+    P[kPGB2 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
+    P[kPGLNG + tid] = ((s.acc_glng[0][tid] + s.acc_glng[1][tid]) + s.acc_glng[2][tid]) + s.acc_glng[3][tid];
+    P[kPGLNB + tid] = ((s.acc_glnb[0][tid] + s.acc_glnb[1][tid]) + s.acc_glnb[2][tid]) + s.acc_glnb[3][tid];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tc::tmem_dealloc(tmem, 512);
+}
+
 // (2) fibre convolution backward, fp32: a pure streaming pass (reads g_x2 and x1, writes g_x1: 12 KB per node).
 // 512 threads; thread (channel c, orientation pair op) keeps fk[2 o][16 p] and its g_fk accumulators in registers.
 // Tiles of 4 nodes are staged with 16-byte cp.async into a double-buffered shared-memory ring (64 KB in flight per
@@ -493,9 +1320,20 @@ extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream)
               "grl_fbconv_node_bwd_tc: null pointer");
   {
     GRL_REQUIRE(d->x2, GRL_EINVAL, "grl_fbconv_node_bwd_tc: x2 (saved by grl_fbconv_node_fwd_tc) is required");
-    const int smem = (int)sizeof(grl::NodeBwd2Smem);
-    if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc2_kernel, smem) != GRL_OK) return GRL_ECUDA;
-    grl::fbconv_node_bwd_tc2_kernel<<<d->n_partials_node, grl::kNB2Threads, smem, (cudaStream_t)stream>>>(*d);
+    const char* v = getenv("GRL_NODE_BWD");  // "tc2": the bulk-synchronous kernel (kept for A/B measurements)
+    if (v && v[0] == 't' && v[1] == 'c' && v[2] == '2') {
+      const int smem = (int)sizeof(grl::NodeBwd2Smem);
+      if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc2_kernel, smem) != GRL_OK) return GRL_ECUDA;
+      grl::fbconv_node_bwd_tc2_kernel<<<d->n_partials_node, grl::kNB2Threads, smem, (cudaStream_t)stream>>>(*d);
+    } else if (v && v[0] == 't' && v[1] == 'c' && v[2] == '4') {
+      const int smem = (int)sizeof(grl::NodeBwd4Smem);
+      if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc4_kernel, smem) != GRL_OK) return GRL_ECUDA;
+      grl::fbconv_node_bwd_tc4_kernel<<<d->n_partials_node, grl::kNB4Threads, smem, (cudaStream_t)stream>>>(*d);
+    } else {
+      const int smem = (int)sizeof(grl::NodeBwd3Smem);
+      if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc3_kernel, smem) != GRL_OK) return GRL_ECUDA;
+      grl::fbconv_node_bwd_tc3_kernel<<<d->n_partials_node, grl::kNB3Threads, smem, (cudaStream_t)stream>>>(*d);
+    }
   }
   int rc = grl::check_launch("grl_fbconv_node_bwd_tc (mlp)");
   if (rc != GRL_OK) return rc;

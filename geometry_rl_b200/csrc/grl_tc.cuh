@@ -142,13 +142,61 @@ __device__ __forceinline__ OpView view_mn(uint32_t addr, int rows) { return OpVi
 __host__ __device__ constexpr uint32_t idesc_bf16_ex(int M, int N, int a_mn, int b_mn) {
   return idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
+// ---- cheap MMA issue: descriptor halves precomputed once, K steps fully unrolled -----------------------------------
+// The generic loop above rebuilds both 64-bit descriptors for every K = 16 step (~30 uniform-datapath instructions per
+// UTCHMMA, all dependent): at 80+ MMAs per 128-row tile the ISSUING THREAD, not the tensor pipe, bounds the kernel.
+// Only the 14-bit start-address field changes between the K steps of one operand view, so a view is kept as the two
+// descriptor words of its first step plus the per-step increment (in 16-byte units) and each further step costs one add.
+struct Op {
+  uint32_t lo, hi, step;
+};
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ Op op_k(uint32_t addr, int rows) { return Op{desc_lo(addr, (uint32_t)rows * 16u), desc_hi(128u), (uint32_t)rows * 2u}; }
+__device__ __forceinline__ Op op_mn(uint32_t addr, int rows) { return Op{desc_lo(addr, 128u), desc_hi((uint32_t)rows * 16u), 16u}; }
+__device__ __forceinline__ void mma_f16_words(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int KSTEPS>
+__device__ __forceinline__ void issue_mma_fast(uint32_t tmem_d, const Op& a, const Op& b, uint32_t idesc, bool accumulate_first) {
+  mma_f16_words(tmem_d, a.lo, a.hi, b.lo, b.hi, idesc, accumulate_first ? 1u : 0u);
+#pragma unroll
+  for (int k = 1; k < KSTEPS; ++k) mma_f16_words(tmem_d, a.lo + k * a.step, a.hi, b.lo + k * b.step, b.hi, idesc, 1u);
+}
+// generic entry used by every kernel: the operand views' descriptor words are formed once, each K step adds a constant;
+// ksteps is a compile-time constant at every call site, so the loop unrolls into back-to-back UTCHMMA.
 __device__ __forceinline__ void issue_mma(uint32_t tmem_d, const OpView& a, const OpView& b, uint32_t idesc, int ksteps,
                                           bool accumulate_first) {
-#pragma unroll 1
-  for (int k = 0; k < ksteps; ++k) {
-    mma_bf16(tmem_d, smem_desc(a.addr + k * a.adv, a.lbo, a.sbo), smem_desc(b.addr + k * b.adv, b.lbo, b.sbo), idesc,
-             (k > 0 || accumulate_first) ? 1u : 0u);
-  }
+  const uint32_t alo = desc_lo(a.addr, a.lbo), ahi = desc_hi(a.sbo), blo = desc_lo(b.addr, b.lbo), bhi = desc_hi(b.sbo);
+  const uint32_t as = a.adv >> 4, bs = b.adv >> 4;
+#pragma unroll
+  for (int k = 0; k < ksteps; ++k)
+    mma_f16_words(tmem_d, alo + k * as, ahi, blo + k * bs, bhi, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+}
+// one elected lane of a converged warp (the MMA-issue warp runs its loop warp-uniformly and issues under this predicate)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // Sum over the 32 lanes of a warp of NV per-lane values by recursive halving: NV - 2 + ... shuffles instead of
