@@ -1,6 +1,6 @@
 // Backward of the node half of the fibre-bundle convolution, tensor-core path.  Two kernels:
 //
-//  (1) fbconv_node_bwd_tc2_kernel — reads the pre-LayerNorm tensor x2 saved by the forward kernel, recomputes
+//  (1) fbconv_node_bwd_tc3_kernel — reads the pre-LayerNorm tensor x2 saved by the forward kernel, recomputes
 //      LayerNorm + GEMM1, then on the tensor cores
 //        pre  = y W1^T + b1                 (recompute)      h = GELU(pre), dG = GELU'(pre)
 //        gH   = gZ W2                       gPre = gH * dG
@@ -15,8 +15,6 @@
 // Reference: autograd of ponita/conv.py:88-114 (FiberBundleConv.forward node part).
 // Operand images are [chunk][row][8] 16-bit (grl_tc.cuh); the SAME image is read K-major (activation x weight)
 // and MN-major (weight gradients X^T Y, products with W instead of W^T) so nothing is ever transposed.
-#include <stdlib.h>
-
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
 
@@ -34,7 +32,7 @@ constexpr int kPGFK = kPGBIAS + kC;
 static_assert(kPGFK + kO * kO * kC == GRL_NODE_GRAD_FLOATS, "partial layout");
 
 // ---------------------------------------------------------------------------------------------------
-// Kernel (1): 512 threads (16 warps) on one 128-row tile, fp16 operands.
+// Kernel (1): one 128-row tile at a time, fp16 operands, 16 epilogue warps + one MMA-issue warp.
 //   * Every operand is fp16 (11-bit mantissa instead of bf16's 8): activations y, h and the weights are O(1); the
 //     gradients (grad_out, gPre) are multiplied by a power of two derived from grl_absmax(grad_out) so that
 //     max |g| lies in [32, 64) (grl_tc.cuh grad_scale_from_amax) and the factor is removed exactly in the epilogues.
@@ -43,41 +41,11 @@ static_assert(kPGFK + kO * kO * kC == GRL_NODE_GRAD_FLOATS, "partial layout");
 //   * b1 rides in the contraction (K = 80: y[:, 64:66] = 1, W1[:, 64:66] = fp16 (hi, lo) split of b1) and the same
 //     ones-columns turn the dW1 MMA (N = 80) into the b1 gradient: no bias adds, no 64-value column butterfly.
 //   * GELU and GELU' are evaluated two elements per instruction in packed fp16 (gelu_h2); h and dG stay packed.
-//   * the x2 and grad_out tiles of the NEXT tile are fetched with cp.async as soon as this tile's last MMA has
-//     retired, and pulled into L2 one tile earlier still.
 //   * no fibre recompute: the forward kernel saves the pre-LayerNorm tensor x2 (GrlConvDesc.x2) and this kernel
-//     streams it back with cp.async (the fibre phase was 20 % of the stall samples of the recomputing version);
-//   * half 0 never waits on its gY / dW MMAs: they are issued behind pre(1) and retire under the next epilogue (the
-//     tensor pipe completes MMAs in issue order, so a later wait covers them).
-// TMEM columns: D 0..127 | gY 128..191 | dW1 192..351 (2 x 80) | dW2^T 352..479 (2 x 64).
+//     streams it back with cp.async, pulled into L2 one tile earlier still.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kNB2Threads = 512;
 constexpr int kKb = 80;     // GEMM1 contraction / dW1 width: 64 channels + 2 ones columns + 14 zero columns
 constexpr int kLDX2 = 68;   // X2 row stride (floats): conflict-free for the row-per-lane LayerNorm reads
-
-struct NodeBwd2Smem {
-  __half W1h[kH * kKb];     // [10 chunks][256 rows k'][8]; chunk 8 = (b1 hi, b1 lo, 0 ...), chunk 9 = 0
-  __half W2h[kC * kH];      // [32 chunks k'][64 rows n][8]
-  __half A1[kTM * kKb];     // y: [10 chunks][128 rows][8]; chunk 8 = (1, 1, 0 ...), chunk 9 = 0 (written once)
-  __half GZh[kTM * kC];     // scaled grad_out [8 chunks][128 rows][8]
-  union {
-    struct {
-      float X2[kTM * kLDX2];    // pre-LayerNorm x2 tile (saved by the forward kernel), phase B only
-      float GZf[kTM * kLDX2];   // grad_out tile (fp32), phase B only
-    } in;
-    struct {
-      __half A2h[kTM * 128];    // h           half: [16 chunks][128 rows][8]
-      __half AP[kTM * 128];     // scaled gPre half: [16 chunks][128 rows][8]
-    } h;
-  } u;
-  float bias[kC], lng[kC], lnb[kC];
-  float rs[2][4][kTM];          // row partial sums exchanged between the four column groups
-  float acc_gb2[4][kC], acc_glng[4][kC], acc_glnb[4][kC];  // per lane-quarter column sums
-  uint64_t bar[3];
-  uint32_t tmem_base;
-};
-
-constexpr uint32_t kCol2D = 0, kCol2GY = 128, kCol2DW1 = 192, kCol2DW2 = 352;
 
 // column sums over the 32 lanes of 16 per-lane values: on return every lane l holds the total of index l >> 1 in v[0]
 __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
@@ -96,318 +64,8 @@ __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-__global__ void __launch_bounds__(kNB2Threads, 1) fbconv_node_bwd_tc2_kernel(const GrlConvDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  NodeBwd2Smem& s = *reinterpret_cast<NodeBwd2Smem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, cg = warp >> 2;   // TMEM lane quarter / column group (0..3) of this warp
-  const int row = 32 * q + lane;            // tile row owned in the LayerNorm and epilogue phases
-
-  if (tid == 0) {
-    tc::mbar_init(&s.bar[0], 1);
-    tc::mbar_init(&s.bar[1], 1);
-    tc::mbar_init(&s.bar[2], 1);
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 512);
-  tc::stage_weight_f16(s.W1h, d.w1, kH, kC, kC);   // chunks 0..7
-  tc::stage_weight_f16(s.W2h, d.w2, kC, kH, kH);
-  for (int n = tid; n < kH; n += kNB2Threads) {     // chunk 8: fp16 (hi, lo) split of b1; chunk 9: zero
-    const float b = d.b1[n];
-    const __half hi = __float2half_rn(b);
-    const __half lo = __float2half_rn(b - __half2float(hi));
-    const __half2 p0 = __halves2half2(hi, lo);
-    *reinterpret_cast<uint4*>(s.W1h + ((size_t)8 * kH + n) * 8) = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(s.W1h + ((size_t)9 * kH + n) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (tid < kTM) {  // ones columns of y (fp16 1.0 = 0x3C00), persistent
-    *reinterpret_cast<uint4*>(s.A1 + ((size_t)8 * kTM + tid) * 8) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(s.A1 + ((size_t)9 * kTM + tid) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (tid < kC) { s.bias[tid] = d.bias[tid]; s.lng[tid] = d.ln_g[tid]; s.lnb[tid] = d.ln_b[tid]; }
-  for (int i = tid; i < 4 * kC; i += kNB2Threads) {
-    (&s.acc_gb2[0][0])[i] = 0.f; (&s.acc_glng[0][0])[i] = 0.f; (&s.acc_glnb[0][0])[i] = 0.f;
-  }
-  const float gscale = d.grad_amax ? tc::grad_scale_from_amax(__ldg(d.grad_amax)) : 1.0f;
-  const float inv_gscale = 1.0f / gscale;  // exact: gscale is a power of two
-  const int n_tiles = (d.n_dst + kTE - 1) / kTE;
-  int tile = blockIdx.x;
-  auto stage_x2 = [&](int t) {  // x2 and grad_out rows of tile t -> X2 / GZf (row stride kLDX2), 16-byte cp.async pieces
-    const int cnt = min(kTE, d.n_dst - t * kTE);
-    const float* src = d.x2 + (size_t)t * kTE * kRow;
-    const float* gsrc = d.grad_out + (size_t)t * kTE * kRow;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = tid + kNB2Threads * i;  // float4 index 0..2047 of the [128][64] tile
-      const int so = (f >> 4) * kLDX2 + 4 * (f & 15);
-      if ((f >> 8) < cnt) {
-        cp_async16(s.u.in.X2 + so, src + 4 * f);
-        cp_async16(s.u.in.GZf + so, gsrc + 4 * f);
-      } else {
-        *reinterpret_cast<float4*>(s.u.in.X2 + so) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(s.u.in.GZf + so) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  };
-  if (tile < n_tiles) {
-    stage_x2(tile);
-    cp_async_commit();
-  }
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base;
-  const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t a1 = tc::smem_u32(s.A1), gz = tc::smem_u32(s.GZh), a2 = tc::smem_u32(s.u.h.A2h), ap = tc::smem_u32(s.u.h.AP);
-  const uint32_t w1 = tc::smem_u32(s.W1h), w2 = tc::smem_u32(s.W2h);
-  uint32_t par0 = 0, par1 = 0, par2 = 0;
-  bool first_tile = true;
-
-  for (; tile < n_tiles; tile += gridDim.x) {
-    const int n0 = tile * kTE;
-    const int node = n0 + (row >> 4);
-    const bool live = node < d.n_dst;
-    const size_t roff = (size_t)(live ? node : 0) * kRow + (row & 15) * kC + 16 * cg;  // this thread's 16 channels
-    if (tid == 0) {  // next tile's x1 / grad_out -> L2
-      const int nt = tile + gridDim.x;
-      if (nt < n_tiles) {
-        const uint32_t bytes = (uint32_t)min(kTE, d.n_dst - nt * kTE) * kRow * 4u;
-        tc::prefetch_l2(d.x2 + (size_t)nt * kTE * kRow, bytes);
-        tc::prefetch_l2(d.grad_out + (size_t)nt * kTE * kRow, bytes);
-      }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    // ---- B: LayerNorm forward (thread = row x 16-channel group cg) + scaled grad_out -> fp16 operand -------
-    float xh[16];  // x-hat of this thread's 16 channels, kept for the LayerNorm backward
-    float rstd;
-    {
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = ld4(s.u.in.X2 + row * kLDX2 + 16 * cg + 4 * i);
-        xh[4 * i] = v.x; xh[4 * i + 1] = v.y; xh[4 * i + 2] = v.z; xh[4 * i + 3] = v.w;
-        sum += (v.x + v.y) + (v.z + v.w);
-      }
-      s.rs[0][cg][row] = sum;
-      __syncthreads();
-      const float mean = ((s.rs[0][0][row] + s.rs[0][1][row]) + (s.rs[0][2][row] + s.rs[0][3][row])) * (1.0f / 64.0f);
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { xh[i] -= mean; sq = fmaf(xh[i], xh[i], sq); }
-      s.rs[1][cg][row] = sq;
-      __syncthreads();
-      rstd = rsqrtf(((s.rs[1][0][row] + s.rs[1][1][row]) + (s.rs[1][2][row] + s.rs[1][3][row])) * (1.0f / 64.0f) + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float y[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = 16 * cg + 8 * i + e;
-          xh[8 * i + e] *= rstd;
-          y[e] = xh[8 * i + e] * s.lng[c] + s.lnb[c];
-        }
-        *reinterpret_cast<uint4*>(s.A1 + ((size_t)(2 * cg + i) * kTM + row) * 8) = tc::pack8_h(y);
-      }
-      // grad_out row piece: column sums (gb2) of the raw values, then scaled -> GZh
-      float g16[16], gs[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 gv = ld4(s.u.in.GZf + row * kLDX2 + 16 * cg + 4 * i);
-        g16[4 * i] = gv.x; g16[4 * i + 1] = gv.y; g16[4 * i + 2] = gv.z; g16[4 * i + 3] = gv.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) gs[i] = g16[i] * gscale;
-      *reinterpret_cast<uint4*>(s.GZh + ((size_t)(2 * cg) * kTM + row) * 8) = tc::pack8_h(gs);
-      *reinterpret_cast<uint4*>(s.GZh + ((size_t)(2 * cg + 1) * kTM + row) * 8) = tc::pack8_h(gs + 8);
-      warp_colsum16(g16, lane);
-      if ((lane & 1) == 0) s.acc_gb2[q][16 * cg + (lane >> 1)] += g16[0];
-    }
-
-    // ---- C: the two hidden halves -------------------------------------------------------------------------
-#pragma unroll 1
-    for (int h2 = 0; h2 < 2; ++h2) {
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {  // pre = [y | 1 1 0..] [W1 | b1]^T (rows 128 h2 .. of W1)
-        tc::tc_fence_after();
-        tc::issue_mma(tmem + kCol2D, tc::view_k(a1, kTM), tc::view_k(w1 + 128 * h2 * 16, kH),
-                      tc::idesc_f16_ex(128, 128, 0, 0, 0, 0), kKb / 16, false);
-        tc::mma_commit(&s.bar[0]);
-        if (h2 == 1) {
-          // half 0's gY / dW1 are issued BEHIND pre(1): the GELU epilogue below only waits for pre(1), and these two
-          // (576 tensor-pipe cycles) run underneath it.  They read AP(0) / A1, which nobody writes before the wait on
-          // gH(1) (bar[1]) that, by in-order completion, also covers them.
-          tc::issue_mma(tmem + kCol2GY, tc::view_k(ap, kTM), tc::view_mn(w1, kH), tc::idesc_f16_ex(128, 64, 0, 1, 0, 0),
-                        128 / 16, false);
-          tc::issue_mma(tmem + kCol2DW1, tc::view_mn(ap, kTM), tc::view_mn(a1, kTM), tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0),
-                        kTM / 16, !first_tile);
-        }
-      }
-      tc::mbar_wait(&s.bar[0], par0);
-      par0 ^= 1u;
-      tc::tc_fence_after();
-      __half2 dG[16];  // GELU'(pre) of this thread's 32 columns of the half, packed
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 32 * cg + 16 * i;  // column inside the half
-        float v[16];
-        tc::tmem_ld16(lane_addr + kCol2D + c0, v);
-        __half2 h0[4], h1[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), h0[e], dG[8 * i + e]);
-          tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), h1[e], dG[8 * i + 4 + e]);
-        }
-        *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack_h8(h0);
-        *reinterpret_cast<uint4*>(s.u.h.A2h + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack_h8(h1);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        // gH' = gZ' W2[:, half]   (W2h read MN-major: N = k', K = n)
-        tc::issue_mma(tmem + kCol2D, tc::view_k(gz, kTM), tc::view_mn(w2 + (16 * h2) * (kC * 16), kC),
-                      tc::idesc_f16_ex(128, 128, 0, 1, 0, 0), kC / 16, false);
-        tc::mma_commit(&s.bar[1]);  // the epilogue below only needs gH': dW2 runs underneath it
-        // dW2'^T[k'][n] += h^T gZ'   (both MN-major, K = tile rows)
-        tc::issue_mma(tmem + kCol2DW2 + 64 * h2, tc::view_mn(a2, kTM), tc::view_mn(gz, kTM),
-                      tc::idesc_f16_ex(128, 64, 1, 1, 0, 0), kTM / 16, !first_tile);
-      }
-      tc::mbar_wait(&s.bar[1], par1);
-      par1 ^= 1u;
-      tc::tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 32 * cg + 16 * i;
-        float v[16];
-        tc::tmem_ld16(lane_addr + kCol2D + c0, v);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 da = __half22float2(dG[8 * i + e]), db = __half22float2(dG[8 * i + 4 + e]);
-          v[2 * e] *= da.x;
-          v[2 * e + 1] *= da.y;
-          v[8 + 2 * e] *= db.x;
-          v[8 + 2 * e + 1] *= db.y;
-        }
-        *reinterpret_cast<uint4*>(s.u.h.AP + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8_h(v);
-        *reinterpret_cast<uint4*>(s.u.h.AP + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8_h(v + 8);
-      }
-      if (h2 == 0) continue;  // half 0's gY / dW1 are issued at the top of the next iteration, behind pre(1)
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        // gY' += gPre' W1[half]   (W1h read MN-major: N = c, K = k')
-        tc::issue_mma(tmem + kCol2GY, tc::view_k(ap, kTM), tc::view_mn(w1 + 128 * 16, kH),
-                      tc::idesc_f16_ex(128, 64, 0, 1, 0, 0), 128 / 16, true);
-        // [dW1' | gb1'][k'][c] += gPre'^T [y | 1 1 0..]
-        tc::issue_mma(tmem + kCol2DW1 + kKb, tc::view_mn(ap, kTM), tc::view_mn(a1, kTM),
-                      tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0), kTM / 16, !first_tile);
-        tc::mma_commit(&s.bar[2]);
-      }
-    }
-    tc::mbar_wait(&s.bar[2], par2);  // everything of this tile is complete: gY is final, the operand buffers are free
-    par2 ^= 1u;
-    tc::tc_fence_after();
-
-    // A2h / AP (= X2) are free: prefetch the next tile's x2
-    {
-      const int nt = tile + gridDim.x;
-      if (nt < n_tiles) {
-        stage_x2(nt);
-        cp_async_commit();
-      }
-    }
-
-    // ---- D: LayerNorm backward: gY (TMEM) -> g_x2 (HBM), g_ln_g, g_ln_b --------------------------------------
-    {
-      float gy[32];  // [0..15] = gY, [16..31] = gY * x-hat (second half filled below for the column sums)
-      {
-        float v[16];
-        tc::tmem_ld16(lane_addr + kCol2GY + 16 * cg, v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) gy[e] = v[e] * inv_gscale;
-      }
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float hx = gy[i] * s.lng[16 * cg + i];
-        s1 += hx;
-        s2 = fmaf(hx, xh[i], s2);
-      }
-      s.rs[0][cg][row] = s1;
-      s.rs[1][cg][row] = s2;
-      __syncthreads();
-      const float m1 = ((s.rs[0][0][row] + s.rs[0][1][row]) + (s.rs[0][2][row] + s.rs[0][3][row])) * (1.0f / 64.0f);
-      const float m2 = ((s.rs[1][0][row] + s.rs[1][1][row]) + (s.rs[1][2][row] + s.rs[1][3][row])) * (1.0f / 64.0f);
-      float* gdst = d.grad_x2 + roff;  // consumed by kernel (2)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 4 * i + e;
-          const float hx = gy[c] * s.lng[16 * cg + c];
-          o[e] = rstd * (hx - m1 - xh[c] * m2);
-        }
-        if (live) st4(gdst + 4 * i, make_float4(o[0], o[1], o[2], o[3]));
-      }
-      // column sums over this warp's 32 rows: g_ln_b = sum gy (lanes 0..15), g_ln_g = sum gy * xhat (lanes 16..31)
-#pragma unroll
-      for (int i = 0; i < 16; ++i) gy[16 + i] = gy[i] * xh[i];
-      tc::warp_colsum<32>(gy, lane);
-      if (lane < 16) s.acc_glnb[q][16 * cg + lane] += gy[0];
-      else s.acc_glng[q][16 * cg + lane - 16] += gy[0];
-    }
-    tc::tc_fence_before();
-    first_tile = false;
-  }
-
-  // ---- write this CTA's partial slot (weight gradients unscaled here) ------------------------------------------
-  cp_async_wait_all();
-  __syncthreads();
-  tc::tc_fence_after();
-  float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
-#pragma unroll 1
-  for (int h2 = 0; h2 < 2; ++h2) {
-    const int c0 = 16 * cg;  // warp (q, cg): rows 128 h2 + row, columns c0 .. c0 + 15
-    float v[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = 0.f;  // CTA without work: TMEM was never written
-    if (!first_tile) tc::tmem_ld16(lane_addr + kCol2DW1 + kKb * h2 + c0, v);
-    float* p1 = P + kPGW1 + (size_t)(128 * h2 + row) * kC + c0;
-#pragma unroll
-    for (int e = 0; e < 16; e += 4)
-      st4(p1 + e, make_float4(v[e] * inv_gscale, v[e + 1] * inv_gscale, v[e + 2] * inv_gscale, v[e + 3] * inv_gscale));
-    if (cg == 0) {  // gb1 = the first ones column of the dW1 accumulator
-      float b[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) b[e] = 0.f;
-      if (!first_tile) tc::tmem_ld16(lane_addr + kCol2DW1 + kKb * h2 + 64, b);
-      P[kPGB1 + 128 * h2 + row] = b[0] * inv_gscale;
-    }
-    if (!first_tile) tc::tmem_ld16(lane_addr + kCol2DW2 + 64 * h2 + c0, v);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) P[kPGW2 + (size_t)(c0 + e) * kH + 128 * h2 + row] = v[e] * inv_gscale;
-  }
-  if (tid < kC) {
-    P[kPGB2 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
-    P[kPGLNG + tid] = ((s.acc_glng[0][tid] + s.acc_glng[1][tid]) + s.acc_glng[2][tid]) + s.acc_glng[3][tid];
-    P[kPGLNB + tid] = ((s.acc_glnb[0][tid] + s.acc_glnb[1][tid]) + s.acc_glnb[2][tid]) + s.acc_glnb[3][tid];
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
 // ---------------------------------------------------------------------------------------------------
-// Kernel (1b): warp-specialised, quarter-pipelined version of kernel (1)  (the default).
+// Structure: warp-specialised, quarter-pipelined.
 //   * 16 epilogue warps (512 threads, thread = tile row x 16-column group) + ONE MMA-issue warp (one elected lane).
 //     The roles meet only through mbarriers: `full[b]` (tcgen05.commit -> epilogue, accumulator buffer b holds a fresh
 //     result), `edone[b]` (16 warp arrivals -> MMA warp: buffer b has been read and the operand quarter derived from it
@@ -446,7 +104,7 @@ struct NodeBwd3Smem {
   float bias[kC], lng[kC], lnb[kC];
   float rs[2][4][kTM];
   float acc_gb2[4][kC], acc_glng[4][kC], acc_glnb[4][kC];
-  uint64_t full[2], edone[2], lnready, gyfull;
+  uint64_t full[2], edone[2], lnready, gyfull, dwdone;
   uint32_t tmem_base;
 };
 
@@ -465,6 +123,7 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
     tc::mbar_init(&s.edone[1], 16);
     tc::mbar_init(&s.lnready, 16);
     tc::mbar_init(&s.gyfull, 1);
+    tc::mbar_init(&s.dwdone, 1);
     tc::fence_mbar_init();
   }
   if (warp == 16) tc::tmem_alloc(&s.tmem_base, 512);
@@ -587,8 +246,9 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
           }
           // gY' (+)= gPre' W1[half]  (W1h read MN-major: N = c, K = k');  [dW1' | gb1'] += gPre'^T [y | 1 1 0..]
           tc::issue_mma_fast<128 / 16>(tmem + kCol3GY, ap_k, shifted(w1_mn, 128u * hh * 16u), id_gh, hh > 0);
+          if (hh == 1) tc::mma_commit(&s.gyfull);  // gY is final: the LayerNorm backward starts under the last dW1 MMAs
           tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW1 + kKb * hh, ap_mn, a1_mn, id_dw1, !first_tile);
-          if (hh == 1) tc::mma_commit(&s.gyfull);
+          if (hh == 1) tc::mma_commit(&s.dwdone);  // every operand buffer of the tile is free
         }
         __syncwarp();
       }
@@ -611,7 +271,7 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
         }
       }
       cp_async_wait_all();
-      tc::group_sync(1, kNB3Epi);
+      tc::group_sync(5, kNB3Epi);
 
       // ---- LayerNorm forward + scaled grad_out -> fp16 operands ------------------------------------------
       float xh[16];
@@ -631,7 +291,7 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
           g16[4 * i] = gv.x; g16[4 * i + 1] = gv.y; g16[4 * i + 2] = gv.z; g16[4 * i + 3] = gv.w;
         }
         s.rs[0][cg][row] = sum;
-        tc::group_sync(1, kNB3Epi);
+        tc::group_sync(1 + q, 128);
         const float mean = ((s.rs[0][0][row] + s.rs[0][1][row]) + (s.rs[0][2][row] + s.rs[0][3][row])) * (1.0f / 64.0f);
         float sq = 0.f;
 #pragma unroll
@@ -646,7 +306,7 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
         }
         warp_colsum16(g16, lane);
         if ((lane & 1) == 0) s.acc_gb2[q][16 * cg + (lane >> 1)] += g16[0];
-        tc::group_sync(1, kNB3Epi);
+        tc::group_sync(1 + q, 128);
         rstd = rsqrtf(((s.rs[1][0][row] + s.rs[1][1][row]) + (s.rs[1][2][row] + s.rs[1][3][row])) * (1.0f / 64.0f) + 1e-5f);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -712,16 +372,8 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
         e2(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 2 * cg);
         e2(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 2 * cg);
       }
-      tc::mbar_wait(&s.gyfull, pgy);  // every MMA of this tile has retired: gY is final, the operand buffers are free
-      pgy ^= 1u;
+      tc::mbar_wait(&s.gyfull, pgy);  // gY is final
       tc::tc_fence_after();
-      {
-        const int nt = tile + gridDim.x;
-        if (nt < n_tiles) {
-          stage_x2(nt);
-          cp_async_commit();
-        }
-      }
 
       // ---- LayerNorm backward: gY (TMEM) -> g_x2 (HBM), g_ln_g, g_ln_b -----------------------------------
       {
@@ -732,6 +384,15 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
 #pragma unroll
           for (int e = 0; e < 16; ++e) gy[e] = v[e] * inv_gscale;
         }
+        tc::mbar_wait(&s.dwdone, pgy);  // the last dW1 MMAs have retired: A2h / AP (= the staging buffers) and A1 are free
+        pgy ^= 1u;
+        {
+          const int nt = tile + gridDim.x;
+          if (nt < n_tiles) {
+            stage_x2(nt);
+            cp_async_commit();
+          }
+        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -741,7 +402,7 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
         }
         s.rs[0][cg][row] = s1;
         s.rs[1][cg][row] = s2;
-        tc::group_sync(1, kNB3Epi);
+        tc::group_sync(1 + q, 128);
         const float m1 = ((s.rs[0][0][row] + s.rs[0][1][row]) + (s.rs[0][2][row] + s.rs[0][3][row])) * (1.0f / 64.0f);
         const float m2 = ((s.rs[1][0][row] + s.rs[1][1][row]) + (s.rs[1][2][row] + s.rs[1][3][row])) * (1.0f / 64.0f);
         float* gdst = d.grad_x2 + roff;
@@ -806,431 +467,6 @@ __global__ void __launch_bounds__(kNB3Threads, 1) fbconv_node_bwd_tc3_kernel(con
   if (warp == 16) tc::tmem_dealloc(tmem, 512);
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Kernel (1c): three roles, tiles overlapped (the default).
-//   * 8 ROW warps     (thread = tile row x 32-channel half): LayerNorm forward of tile i+1 (x2 / grad_out rows read
-//                      straight from global memory, one 128-byte line per thread, L2-prefetched two tiles ahead) into the
-//                      double-buffered fp16 operand images A1 / GZh, and LayerNorm backward of tile i (gY out of TMEM,
-//                      x-hat recomputed from the re-read x2 row and the saved row statistics) -> g_x2;
-//   * 8 EPILOGUE warps (thread = tile row x 32 columns of a hidden quarter): GELU / GELU' (E1) and gPre (E2) of the four
-//                      hidden quarters, nothing else - they never touch global memory and never meet a CTA barrier;
-//   * 1 MMA warp:      the issue order of kernel (1b) with the next tile's first two `pre` quarters issued as soon as
-//                      their accumulator buffers drain.
-//   mbarriers: full[b] (commit -> epilogue), edone[b] (8 epilogue warps -> MMA), lnready[buf] (8 row warps -> MMA),
-//   gyfull (commit -> row warps: every MMA of the tile retired, gY final, operand buffers of the tile free),
-//   gyfree (8 row warps -> MMA: gY has been read out of TMEM).
-// TMEM columns as kernel (1b).  Shared memory: W1h 40 K | W2h 32 K | A1 2 x 20 K | GZh 2 x 16 K | A2h 32 K | AP 32 K.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kNB4Threads = 17 * 32;
-struct NodeBwd4Smem {
-  __half W1h[kH * kKb];
-  __half W2h[kC * kH];
-  __half A1[2][kTM * kKb];
-  __half GZh[2][kTM * kC];
-  __half A2h[kTM * 128];
-  __half AP[kTM * 128];
-  float lng[kC], lnb[kC];
-  float rs[2][2][kTM];        // row partial sums exchanged between the two channel halves (LayerNorm forward)
-  float rsb[2][2][kTM];       // the same for the LayerNorm backward
-  float stat[2][2][kTM];      // [buffer][mean | rstd][row] saved by the LayerNorm forward for its backward
-  float acc_gb2[4][kC], acc_glng[4][kC], acc_glnb[4][kC];
-  uint64_t full[2], edone[2], lnready[2], gyfull, gyfree;
-  uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(kNB4Threads, 1) fbconv_node_bwd_tc4_kernel(const GrlConvDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  NodeBwd4Smem& s = *reinterpret_cast<NodeBwd4Smem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3;            // TMEM lane quarter of this warp
-  const int row = 32 * q + lane;     // tile row owned by a row / epilogue thread
-  const int j = (warp >> 2) & 1;     // 32-channel half (row warps) / 32-column half of a quarter (epilogue warps)
-
-  if (tid == 0) {
-    tc::mbar_init(&s.full[0], 1);
-    tc::mbar_init(&s.full[1], 1);
-    tc::mbar_init(&s.edone[0], 8);
-    tc::mbar_init(&s.edone[1], 8);
-    tc::mbar_init(&s.lnready[0], 8);
-    tc::mbar_init(&s.lnready[1], 8);
-    tc::mbar_init(&s.gyfull, 1);
-    tc::mbar_init(&s.gyfree, 8);
-    tc::fence_mbar_init();
-  }
-  if (warp == 16) tc::tmem_alloc(&s.tmem_base, 512);
-  tc::stage_weight_f16(s.W1h, d.w1, kH, kC, kC);
-  tc::stage_weight_f16(s.W2h, d.w2, kC, kH, kH);
-  for (int n = tid; n < kH; n += kNB4Threads) {
-    const float b = d.b1[n];
-    const __half hi = __float2half_rn(b);
-    const __half lo = __float2half_rn(b - __half2float(hi));
-    const __half2 p0 = __halves2half2(hi, lo);
-    *reinterpret_cast<uint4*>(s.W1h + ((size_t)8 * kH + n) * 8) = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(s.W1h + ((size_t)9 * kH + n) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (tid < 2 * kTM) {  // ones columns of both y images
-    __half* a = s.A1[tid >> 7];
-    const int r = tid & 127;
-    *reinterpret_cast<uint4*>(a + ((size_t)8 * kTM + r) * 8) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(a + ((size_t)9 * kTM + r) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (tid < kC) { s.lng[tid] = d.ln_g[tid]; s.lnb[tid] = d.ln_b[tid]; }
-  for (int i = tid; i < 4 * kC; i += kNB4Threads) {
-    (&s.acc_gb2[0][0])[i] = 0.f; (&s.acc_glng[0][0])[i] = 0.f; (&s.acc_glnb[0][0])[i] = 0.f;
-  }
-  const float gscale = d.grad_amax ? tc::grad_scale_from_amax(__ldg(d.grad_amax)) : 1.0f;
-  const float inv_gscale = 1.0f / gscale;
-  const int n_tiles = (d.n_dst + kTE - 1) / kTE;
-  const int tile0 = blockIdx.x, stride = gridDim.x;
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base;
-  const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const bool any_tile = tile0 < n_tiles;
-
-  if (warp == 16) {
-    // ================= MMA-issue warp =================
-    constexpr uint32_t id_pre = tc::idesc_f16_ex(128, 64, 0, 0, 0, 0);
-    constexpr uint32_t id_gh = tc::idesc_f16_ex(128, 64, 0, 1, 0, 0);
-    constexpr uint32_t id_dw2 = tc::idesc_f16_ex(128, 64, 1, 1, 0, 0);
-    constexpr uint32_t id_dw1 = tc::idesc_f16_ex(128, kKb, 1, 1, 0, 0);
-    const uint32_t a1b = tc::smem_u32(s.A1[0]), gzb = tc::smem_u32(s.GZh[0]);
-    const uint32_t a2 = tc::smem_u32(s.A2h), ap = tc::smem_u32(s.AP), w1 = tc::smem_u32(s.W1h), w2 = tc::smem_u32(s.W2h);
-    constexpr uint32_t kA1Bytes = kTM * kKb * 2, kGZBytes = kTM * kC * 2;
-    const tc::Op a2_mn = tc::op_mn(a2, kTM), ap_k = tc::op_k(ap, kTM), ap_mn = tc::op_mn(ap, kTM);
-    const tc::Op w1_k = tc::op_k(w1, kH), w1_mn = tc::op_mn(w1, kH), w2_mn = tc::op_mn(w2, kC);
-    auto shifted = [](tc::Op o, uint32_t bytes) { o.lo += bytes >> 4; return o; };
-    uint32_t p_ln0 = 0, p_ln1 = 0, p_e0 = 0, p_e1 = 0, p_gf = 0;
-    bool first_tile = true;
-    int it = 0;
-    if (any_tile) {  // first tile: its two leading quarters
-      tc::mbar_wait(&s.lnready[0], p_ln0);
-      p_ln0 ^= 1u;
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        const tc::Op a1_k = tc::op_k(a1b, kTM);
-        tc::issue_mma_fast<kKb / 16>(tmem + kCol3D0, a1_k, w1_k, id_pre, false);
-        tc::mma_commit(&s.full[0]);
-        tc::issue_mma_fast<kKb / 16>(tmem + kCol3D1, a1_k, shifted(w1_k, 64u * 16u), id_pre, false);
-        tc::mma_commit(&s.full[1]);
-      }
-      __syncwarp();
-    }
-    for (int tile = tile0; tile < n_tiles; tile += stride, ++it) {
-      const int buf = it & 1;
-      const bool has_next = tile + stride < n_tiles;
-      const tc::Op a1_k = tc::op_k(a1b + buf * kA1Bytes, kTM), a1_mn = tc::op_mn(a1b + buf * kA1Bytes, kTM);
-      const tc::Op gz_k = tc::op_k(gzb + buf * kGZBytes, kTM), gz_mn = tc::op_mn(gzb + buf * kGZBytes, kTM);
-      const tc::Op a1n_k = tc::op_k(a1b + (buf ^ 1) * kA1Bytes, kTM);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        tc::mbar_wait(&s.edone[0], p_e0);  // E1(2 hh): h quarter staged, D0 read
-        p_e0 ^= 1u;
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          // gH'(quarter) = gZ' W2[:, quarter]  (W2h MN-major: N = k', K = n)
-          tc::issue_mma_fast<kC / 16>(tmem + kCol3D0, gz_k, shifted(w2_mn, 8u * (2 * hh) * (kC * 16u)), id_gh, false);
-          tc::mma_commit(&s.full[0]);
-        }
-        __syncwarp();
-        tc::mbar_wait(&s.edone[1], p_e1);  // E1(2 hh + 1)
-        p_e1 ^= 1u;
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          tc::issue_mma_fast<kC / 16>(tmem + kCol3D1, gz_k, shifted(w2_mn, 8u * (2 * hh + 1) * (kC * 16u)), id_gh, false);
-          tc::mma_commit(&s.full[1]);
-          // dW2'^T[k'][n] += h^T gZ'  (both MN-major, K = tile rows); retires under the next epilogues
-          tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW2 + 64 * hh, a2_mn, gz_mn, id_dw2, !first_tile);
-        }
-        __syncwarp();
-        tc::mbar_wait(&s.edone[0], p_e0);  // E2(2 hh): gPre quarter staged, D0 drained
-        p_e0 ^= 1u;
-        tc::tc_fence_after();
-        if (hh == 0) {
-          if (tc::elect_one()) {
-            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D0, a1_k, shifted(w1_k, 64u * 2u * 16u), id_pre, false);
-            tc::mma_commit(&s.full[0]);
-          }
-          __syncwarp();
-        } else if (has_next) {  // D0 is free for the rest of this tile: first quarter of the next one
-          if (buf) {
-            tc::mbar_wait(&s.lnready[0], p_ln0);
-            p_ln0 ^= 1u;
-          } else {
-            tc::mbar_wait(&s.lnready[1], p_ln1);
-            p_ln1 ^= 1u;
-          }
-          tc::tc_fence_after();
-          if (tc::elect_one()) {
-            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D0, a1n_k, w1_k, id_pre, false);
-            tc::mma_commit(&s.full[0]);
-          }
-          __syncwarp();
-        }
-        tc::mbar_wait(&s.edone[1], p_e1);  // E2(2 hh + 1)
-        p_e1 ^= 1u;
-        tc::tc_fence_after();
-        if (hh == 0 && it > 0) {  // gY of the previous tile must have been read out before it is overwritten
-          tc::mbar_wait(&s.gyfree, p_gf);
-          p_gf ^= 1u;
-          tc::tc_fence_after();
-        }
-        if (tc::elect_one()) {
-          if (hh == 0) {
-            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D1, a1_k, shifted(w1_k, 64u * 3u * 16u), id_pre, false);
-            tc::mma_commit(&s.full[1]);
-          } else if (has_next) {
-            tc::issue_mma_fast<kKb / 16>(tmem + kCol3D1, a1n_k, shifted(w1_k, 64u * 16u), id_pre, false);
-            tc::mma_commit(&s.full[1]);
-          }
-          // gY' (+)= gPre' W1[half]  (W1h MN-major: N = c, K = k');  [dW1' | gb1'] += gPre'^T [y | 1 1 0..]
-          tc::issue_mma_fast<128 / 16>(tmem + kCol3GY, ap_k, shifted(w1_mn, 128u * hh * 16u), id_gh, hh > 0);
-          tc::issue_mma_fast<kTM / 16>(tmem + kCol3DW1 + kKb * hh, ap_mn, a1_mn, id_dw1, !first_tile);
-          if (hh == 1) tc::mma_commit(&s.gyfull);
-        }
-        __syncwarp();
-      }
-      first_tile = false;
-    }
-  } else if (warp >= 8) {
-    // ================= epilogue warps: thread = (row, 32 columns 32 j .. of the quarter) =================
-    uint32_t pf0 = 0, pf1 = 0;
-    __half2 dG0[16], dG1[16];
-    auto e1 = [&](uint32_t col, uint64_t* fullb, uint32_t& pf, uint64_t* doneb, __half2 (&dG)[16], int chunk) {
-      tc::mbar_wait(fullb, pf);
-      pf ^= 1u;
-      tc::tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float v[16];
-        tc::tmem_ld16(lane_addr + col + 32 * j + 16 * i, v);
-        __half2 h0[4], h1[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), h0[e], dG[8 * i + e]);
-          tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), h1[e], dG[8 * i + 4 + e]);
-        }
-        *reinterpret_cast<uint4*>(s.A2h + ((size_t)(chunk + 2 * i) * kTM + row) * 8) = tc::pack_h8(h0);
-        *reinterpret_cast<uint4*>(s.A2h + ((size_t)(chunk + 2 * i + 1) * kTM + row) * 8) = tc::pack_h8(h1);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(doneb);
-    };
-    auto e2 = [&](uint32_t col, uint64_t* fullb, uint32_t& pf, uint64_t* doneb, const __half2 (&dG)[16], int chunk) {
-      tc::mbar_wait(fullb, pf);
-      pf ^= 1u;
-      tc::tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float v[16];
-        tc::tmem_ld16(lane_addr + col + 32 * j + 16 * i, v);
-        __half2 p0[4], p1[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          p0[e] = __hmul2(__floats2half2_rn(v[2 * e], v[2 * e + 1]), dG[8 * i + e]);
-          p1[e] = __hmul2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]), dG[8 * i + 4 + e]);
-        }
-        *reinterpret_cast<uint4*>(s.AP + ((size_t)(chunk + 2 * i) * kTM + row) * 8) = tc::pack_h8(p0);
-        *reinterpret_cast<uint4*>(s.AP + ((size_t)(chunk + 2 * i + 1) * kTM + row) * 8) = tc::pack_h8(p1);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(doneb);
-    };
-    for (int tile = tile0; tile < n_tiles; tile += stride) {
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        e1(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 4 * j);
-        e1(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 4 * j);
-        e2(kCol3D0, &s.full[0], pf0, &s.edone[0], dG0, 4 * j);
-        e2(kCol3D1, &s.full[1], pf1, &s.edone[1], dG1, 8 + 4 * j);
-      }
-    }
-  } else {
-    // ================= row warps: thread = (row, channels 32 j .. 32 j + 31) =================
-    uint32_t pgy = 0;
-    auto row_ptr = [&](const float* base, int t) -> const float4* {  // nullptr for the padding rows of the last tile
-      const int node = t * kTE + (row >> 4);
-      return node < d.n_dst ? reinterpret_cast<const float4*>(base + (size_t)node * kRow + (row & 15) * kC + 32 * j) : nullptr;
-    };
-    auto ln_fwd = [&](int t, int buf) {
-      const float4* px = row_ptr(d.x2, t);
-      const float4* pg = row_ptr(d.grad_out, t);
-      float x[32], g[32];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 v = px ? __ldg(px + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 v = pg ? __ldg(pg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) sum += (x[i] + x[i + 1]) + (x[i + 2] + x[i + 3]);
-      s.rs[0][j][row] = sum;
-      tc::group_sync(2, 256);
-      const float mean = (s.rs[0][0][row] + s.rs[0][1][row]) * (1.0f / 64.0f);
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { x[i] -= mean; sq = fmaf(x[i], x[i], sq); }
-      s.rs[1][j][row] = sq;
-      {  // scaled grad_out -> fp16 operand image (chunks 4 j .. 4 j + 3), gb2 column sums of the raw values
-        __half* gzh = s.GZh[buf];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float gs[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) gs[e] = g[8 * c + e] * gscale;
-          *reinterpret_cast<uint4*>(gzh + ((size_t)(4 * j + c) * kTM + row) * 8) = tc::pack8_h(gs);
-        }
-        tc::warp_colsum<32>(g, lane);
-        s.acc_gb2[q][32 * j + lane] += g[0];
-      }
-      tc::group_sync(2, 256);
-      const float rstd = rsqrtf((s.rs[1][0][row] + s.rs[1][1][row]) * (1.0f / 64.0f) + 1e-5f);
-      if (j == 0) { s.stat[buf][0][row] = mean; s.stat[buf][1][row] = rstd; }
-      __half* a1 = s.A1[buf];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float y[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int ch = 32 * j + 8 * c + e;
-          y[e] = x[8 * c + e] * rstd * s.lng[ch] + s.lnb[ch];
-        }
-        *reinterpret_cast<uint4*>(a1 + ((size_t)(4 * j + c) * kTM + row) * 8) = tc::pack8_h(y);
-      }
-      tc::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s.lnready[buf]);
-    };
-    auto ln_bwd = [&](int t, int buf) {
-      const float4* px = row_ptr(d.x2, t);
-      float xh[32];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {  // issued before the wait: the reload (an L2 hit) overlaps the tail of the tile's MMAs
-        const float4 v = px ? __ldg(px + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xh[4 * i] = v.x; xh[4 * i + 1] = v.y; xh[4 * i + 2] = v.z; xh[4 * i + 3] = v.w;
-      }
-      tc::mbar_wait(&s.gyfull, pgy);
-      pgy ^= 1u;
-      tc::tc_fence_after();
-      float gy[32];
-      {
-        float v[16];
-        tc::tmem_ld16(lane_addr + kCol3GY + 32 * j, v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) gy[e] = v[e] * inv_gscale;
-        tc::tmem_ld16(lane_addr + kCol3GY + 32 * j + 16, v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) gy[16 + e] = v[e] * inv_gscale;
-      }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s.gyfree);
-      const float mean = s.stat[buf][0][row], rstd = s.stat[buf][1][row];
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        xh[i] = (xh[i] - mean) * rstd;
-        const float hx = gy[i] * s.lng[32 * j + i];
-        s1 += hx;
-        s2 = fmaf(hx, xh[i], s2);
-      }
-      s.rsb[0][j][row] = s1;
-      s.rsb[1][j][row] = s2;
-      tc::group_sync(2, 256);
-      const float m1 = (s.rsb[0][0][row] + s.rsb[0][1][row]) * (1.0f / 64.0f);
-      const float m2 = (s.rsb[1][0][row] + s.rsb[1][1][row]) * (1.0f / 64.0f);
-      const int node = t * kTE + (row >> 4);
-      if (node < d.n_dst) {
-        float4* gdst = reinterpret_cast<float4*>(d.grad_x2 + (size_t)node * kRow + (row & 15) * kC + 32 * j);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 4 * i + e;
-            o[e] = rstd * (gy[c] * s.lng[32 * j + c] - m1 - xh[c] * m2);
-          }
-          gdst[i] = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      }
-      // column sums over this warp's 32 rows: g_ln_g = sum gy * xhat, g_ln_b = sum gy
-#pragma unroll
-      for (int i = 0; i < 32; ++i) xh[i] *= gy[i];
-      tc::warp_colsum<32>(xh, lane);
-      tc::warp_colsum<32>(gy, lane);
-      s.acc_glng[q][32 * j + lane] += xh[0];
-      s.acc_glnb[q][32 * j + lane] += gy[0];
-    };
-    auto prefetch = [&](int t) {
-      if (tid == 0 && t < n_tiles) {
-        const uint32_t bytes = (uint32_t)min(kTE, d.n_dst - t * kTE) * kRow * 4u;
-        tc::prefetch_l2(d.x2 + (size_t)t * kTE * kRow, bytes);
-        tc::prefetch_l2(d.grad_out + (size_t)t * kTE * kRow, bytes);
-      }
-    };
-    if (any_tile) {
-      prefetch(tile0 + stride);
-      ln_fwd(tile0, 0);
-    }
-    int it = 0;
-    for (int tile = tile0; tile < n_tiles; tile += stride, ++it) {
-      prefetch(tile + 2 * stride);
-      if (tile + stride < n_tiles) ln_fwd(tile + stride, (it + 1) & 1);
-      ln_bwd(tile, it & 1);
-    }
-  }
-
-  // ---- write this CTA's partial slot ---------------------------------------------------------------------------
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
-  if (warp < 16) {
-    const int cg = warp >> 2;  // 16-column group
-#pragma unroll 1
-    for (int h2 = 0; h2 < 2; ++h2) {
-      const int c0 = 16 * cg;
-      float v[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = 0.f;
-      if (any_tile) tc::tmem_ld16(lane_addr + kCol3DW1 + kKb * h2 + c0, v);
-      float* p1 = P + kPGW1 + (size_t)(128 * h2 + row) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4)
-        st4(p1 + e, make_float4(v[e] * inv_gscale, v[e + 1] * inv_gscale, v[e + 2] * inv_gscale, v[e + 3] * inv_gscale));
-      if (cg == 0) {
-        float b[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) b[e] = 0.f;
-        if (any_tile) tc::tmem_ld16(lane_addr + kCol3DW1 + kKb * h2 + 64, b);
-        P[kPGB1 + 128 * h2 + row] = b[0] * inv_gscale;
-      }
-      if (any_tile) tc::tmem_ld16(lane_addr + kCol3DW2 + 64 * h2 + c0, v);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) P[kPGW2 + (size_t)(c0 + e) * kH + 128 * h2 + row] = v[e] * inv_gscale;
-    }
-  }
-  if (tid < kC) {
-    P[kPGB2 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
-    P[kPGLNG + tid] = ((s.acc_glng[0][tid] + s.acc_glng[1][tid]) + s.acc_glng[2][tid]) + s.acc_glng[3][tid];
-    P[kPGLNB + tid] = ((s.acc_glnb[0][tid] + s.acc_glnb[1][tid]) + s.acc_glnb[2][tid]) + s.acc_glnb[3][tid];
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 16) tc::tmem_dealloc(tmem, 512);
-}
-
 // (2) fibre convolution backward, fp32: a pure streaming pass (reads g_x2 and x1, writes g_x1: 12 KB per node).
 // 512 threads; thread (channel c, orientation pair op) keeps fk[2 o][16 p] and its g_fk accumulators in registers.
 // Tiles of 4 nodes are staged with 16-byte cp.async into a double-buffered shared-memory ring (64 KB in flight per
@@ -1258,14 +494,14 @@ __global__ void __launch_bounds__(kFiberThreads, 1) fbconv_fiber_bwd_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FiberBwdSmem& s = *reinterpret_cast<FiberBwdSmem*>(smem_raw);
   const int tid = threadIdx.x, c = tid & 63, op = tid >> 6;
-  float fk[2][kO], gfk[2][kO];
+  // both orientations of the thread ride in one packed register pair: (fk[2 op][p], fk[2 op + 1][p]) etc.
+  unsigned long long fk2[kO], gfk2[kO];
 #pragma unroll
-  for (int oi = 0; oi < 2; ++oi)
-#pragma unroll
-    for (int p = 0; p < kO; ++p) {
-      fk[oi][p] = __ldg(d.fiber_kernel + ((size_t)((2 * op + oi) * kO + p)) * kC + c) * 0.0625f;
-      gfk[oi][p] = 0.f;
-    }
+  for (int p = 0; p < kO; ++p) {
+    fk2[p] = pack2(__ldg(d.fiber_kernel + ((size_t)((2 * op) * kO + p)) * kC + c) * 0.0625f,
+                   __ldg(d.fiber_kernel + ((size_t)((2 * op + 1) * kO + p)) * kC + c) * 0.0625f);
+    gfk2[p] = pack2(0.f, 0.f);
+  }
   float gbias = 0.f;
   const int n_tiles = (d.n_dst + kFibTile - 1) / kFibTile;
   int tile = blockIdx.x, buf = 0;
@@ -1282,32 +518,35 @@ __global__ void __launch_bounds__(kFiberThreads, 1) fbconv_fiber_bwd_kernel(cons
       const int node = tile * kFibTile + j;
       const float* G = s.G[buf] + j * kRow + c;
       const float* X = s.X[buf] + j * kRow + c;
-      float g2[kO];
+      const unsigned long long xv = pack2(X[(2 * op) * kC], X[(2 * op + 1) * kC]);
+      unsigned long long a2 = pack2(0.f, 0.f);
+      float gsum = 0.f;
 #pragma unroll
-      for (int p = 0; p < kO; ++p) g2[p] = G[p * kC];
-#pragma unroll
-      for (int oi = 0; oi < 2; ++oi) {
-        const float x1v = X[(2 * op + oi) * kC];
-        float a = 0.f;
-#pragma unroll
-        for (int p = 0; p < kO; ++p) {
-          a = fmaf(g2[p], fk[oi][p], a);
-          gfk[oi][p] = fmaf(x1v, g2[p], gfk[oi][p]);
-        }
-        if (node < d.n_dst) d.grad_x1[(size_t)node * kRow + (2 * op + oi) * kC + c] = a;
+      for (int p = 0; p < kO; ++p) {
+        const float g = G[p * kC];
+        const unsigned long long gg = pack2(g, g);
+        a2 = ffma2(gg, fk2[p], a2);          // g_x1[2 op + oi] += g_x2[p] fk[2 op + oi][p]
+        gfk2[p] = ffma2(xv, gg, gfk2[p]);    // g_fk[2 op + oi][p] += x1[2 op + oi] g_x2[p]
+        gsum += g;
       }
-      if (op == 0) {
-#pragma unroll
-        for (int p = 0; p < kO; ++p) gbias += g2[p];
+      if (node < d.n_dst) {
+        float a0, a1;
+        unpack2(a2, a0, a1);
+        d.grad_x1[(size_t)node * kRow + (2 * op) * kC + c] = a0;
+        d.grad_x1[(size_t)node * kRow + (2 * op + 1) * kC + c] = a1;
       }
+      if (op == 0) gbias += gsum;
     }
     __syncthreads();  // everyone done with `buf` before the next iteration's prefetch overwrites it
   }
   float* P = d.node_grad_partials + (size_t)blockIdx.x * GRL_NODE_GRAD_FLOATS;
 #pragma unroll
-  for (int oi = 0; oi < 2; ++oi)
-#pragma unroll
-    for (int p = 0; p < kO; ++p) P[kPGFK + ((size_t)((2 * op + oi) * kO + p)) * kC + c] = gfk[oi][p] * 0.0625f;
+  for (int p = 0; p < kO; ++p) {
+    float g0, g1;
+    unpack2(gfk2[p], g0, g1);
+    P[kPGFK + ((size_t)((2 * op) * kO + p)) * kC + c] = g0 * 0.0625f;
+    P[kPGFK + ((size_t)((2 * op + 1) * kO + p)) * kC + c] = g1 * 0.0625f;
+  }
   if (op == 0) P[kPGBIAS + c] = gbias;
 }
 
@@ -1320,20 +559,9 @@ extern "C" int grl_fbconv_node_bwd_tc(const GrlConvDesc* d, grl_stream_t stream)
               "grl_fbconv_node_bwd_tc: null pointer");
   {
     GRL_REQUIRE(d->x2, GRL_EINVAL, "grl_fbconv_node_bwd_tc: x2 (saved by grl_fbconv_node_fwd_tc) is required");
-    const char* v = getenv("GRL_NODE_BWD");  // "tc2": the bulk-synchronous kernel (kept for A/B measurements)
-    if (v && v[0] == 't' && v[1] == 'c' && v[2] == '2') {
-      const int smem = (int)sizeof(grl::NodeBwd2Smem);
-      if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc2_kernel, smem) != GRL_OK) return GRL_ECUDA;
-      grl::fbconv_node_bwd_tc2_kernel<<<d->n_partials_node, grl::kNB2Threads, smem, (cudaStream_t)stream>>>(*d);
-    } else if (v && v[0] == 't' && v[1] == 'c' && v[2] == '4') {
-      const int smem = (int)sizeof(grl::NodeBwd4Smem);
-      if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc4_kernel, smem) != GRL_OK) return GRL_ECUDA;
-      grl::fbconv_node_bwd_tc4_kernel<<<d->n_partials_node, grl::kNB4Threads, smem, (cudaStream_t)stream>>>(*d);
-    } else {
-      const int smem = (int)sizeof(grl::NodeBwd3Smem);
-      if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc3_kernel, smem) != GRL_OK) return GRL_ECUDA;
-      grl::fbconv_node_bwd_tc3_kernel<<<d->n_partials_node, grl::kNB3Threads, smem, (cudaStream_t)stream>>>(*d);
-    }
+    const int smem = (int)sizeof(grl::NodeBwd3Smem);
+    if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_bwd_tc3_kernel, smem) != GRL_OK) return GRL_ECUDA;
+    grl::fbconv_node_bwd_tc3_kernel<<<d->n_partials_node, grl::kNB3Threads, smem, (cudaStream_t)stream>>>(*d);
   }
   int rc = grl::check_launch("grl_fbconv_node_bwd_tc (mlp)");
   if (rc != GRL_OK) return rc;

@@ -96,11 +96,14 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
   if (tid < kC) { s.b2[tid] = d.b2[tid]; s.bias[tid] = d.bias[tid]; s.lng[tid] = d.ln_g[tid]; s.lnb[tid] = d.ln_b[tid]; }
   // fibre kernel slice of this thread: channel fc, output orientations p = 4 pq .. 4 pq + 3, all 16 inputs o
   const int fc = gt & 63, pq = gt >> 6;
-  float fk[kO][4];
+  // packed pairs of output orientations (FFMA2: two fused multiply-adds per fma-pipe issue slot)
+  unsigned long long fk2[kO][2];
 #pragma unroll
   for (int o = 0; o < kO; ++o)
 #pragma unroll
-    for (int pi = 0; pi < 4; ++pi) fk[o][pi] = __ldg(d.fiber_kernel + ((size_t)(o * kO + 4 * pq + pi)) * kC + fc) * 0.0625f;
+    for (int pi = 0; pi < 2; ++pi)
+      fk2[o][pi] = pack2(__ldg(d.fiber_kernel + ((size_t)(o * kO + 4 * pq + 2 * pi)) * kC + fc) * 0.0625f,
+                         __ldg(d.fiber_kernel + ((size_t)(o * kO + 4 * pq + 2 * pi + 1)) * kC + fc) * 0.0625f);
 
   const int n_tiles = (d.n_dst + kTE - 1) / kTE;
   const int tile_stride = 2 * gridDim.x;
@@ -134,15 +137,17 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
       const float bias_c = s.bias[fc];
 #pragma unroll 2
       for (int j = 0; j < kTE; ++j) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        unsigned long long a01 = pack2(0.f, 0.f), a23 = a01;
 #pragma unroll
         for (int o = 0; o < kO; ++o) {
           const float x = G.u.x.X1[(16 * j + o) * kC + fc];
-          a0 = fmaf(x, fk[o][0], a0);
-          a1 = fmaf(x, fk[o][1], a1);
-          a2 = fmaf(x, fk[o][2], a2);
-          a3 = fmaf(x, fk[o][3], a3);
+          const unsigned long long xx = pack2(x, x);
+          a01 = ffma2(xx, fk2[o][0], a01);
+          a23 = ffma2(xx, fk2[o][1], a23);
         }
+        float a0, a1, a2, a3;
+        unpack2(a01, a0, a1);
+        unpack2(a23, a2, a3);
         float* o2 = G.u.x.X2 + (16 * j + 4 * pq) * kLDX + fc;
         o2[0 * kLDX] = a0 + bias_c;
         o2[1 * kLDX] = a1 + bias_c;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
     tc::group_sync(bar_id, 256);
     if (gt == 0) {
       tc::tc_fence_after();
-      tc::issue_mma(tmem, tc::view_k(a1_addr, kTM), tc::view_k(w1_addr, kH), tc::idesc_f16_ex(128, kH, 0, 0, 0, 0), kK1 / 16, false);
+      tc::issue_mma_rolled(tmem, tc::view_k(a1_addr, kTM), tc::view_k(w1_addr, kH), tc::idesc_f16_ex(128, kH, 0, 0, 0, 0), kK1 / 16, false);
       tc::mma_commit(&s.bar[grp][0]);
     }
     // ---- D: hidden = GELU(D1) -> A2 (aliases X1 / X2 / A1, which nobody reads any more) ----------------
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
     tc::group_sync(bar_id, 256);
     if (gt == 0) {
       tc::tc_fence_after();
-      tc::issue_mma(tmem, tc::view_k(a2_addr, kTM), tc::view_k(w2_addr, kC), tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), kH / 16, false);
+      tc::issue_mma_rolled(tmem, tc::view_k(a2_addr, kTM), tc::view_k(w2_addr, kC), tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), kH / 16, false);
       tc::mma_commit(&s.bar[grp][1]);
     }
     // x_dst of this thread's two 16-column pieces: issued BEFORE the wait so the DRAM round trip hides behind GEMM2

@@ -186,6 +186,19 @@ __device__ __forceinline__ void issue_mma(uint32_t tmem_d, const OpView& a, cons
   for (int k = 0; k < ksteps; ++k)
     mma_f16_words(tmem_d, alo + k * as, ahi, blo + k * bs, bhi, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
 }
+// the same with the K loop kept rolled (two adds + one UTCHMMA per step): for kernels whose issuing thread is short of registers
+__device__ __forceinline__ void issue_mma_rolled(uint32_t tmem_d, const OpView& a, const OpView& b, uint32_t idesc, int ksteps,
+                                                 bool accumulate_first) {
+  uint32_t alo = desc_lo(a.addr, a.lbo), blo = desc_lo(b.addr, b.lbo);
+  const uint32_t ahi = desc_hi(a.sbo), bhi = desc_hi(b.sbo), as = a.adv >> 4, bs = b.adv >> 4;
+  mma_f16_words(tmem_d, alo, ahi, blo, bhi, idesc, accumulate_first ? 1u : 0u);
+#pragma unroll 1
+  for (int k = 1; k < ksteps; ++k) {
+    alo += as;
+    blo += bs;
+    mma_f16_words(tmem_d, alo, ahi, blo, bhi, idesc, 1u);
+  }
+}
 // one elected lane of a converged warp (the MMA-issue warp runs its loop warp-uniformly and issues under this predicate)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -423,6 +423,10 @@ int grl_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K,
 int grl_tc_debug_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, float* D, int N, int n_ksteps,
                      uint32_t lbo_a, uint32_t sbo_a, uint32_t adv_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t adv_b,
                      uint32_t idesc, uint32_t desc_hi_bits, grl_stream_t stream);
+/* Hand-off latency probe (SM clock cycles): out64[2 i], out64[2 i + 1] = min, mean of measurement i, 9 measurements
+ * (MMA + commit -> wait for 1/4/8/16 MMAs, fence.proxy.async, mbarrier arrive -> wait, tcgen05.ld, epilogue <-> MMA-warp
+ * round trips); out64 must hold 64 entries.  Measurement hook only (tools/tc_latency_probe.py). */
+int grl_tc_latency_probe(long long* out64, grl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,9 @@ def full(src, dst):
 
 # C-ABI entry point -> the kernels one call launches
 ABI_KERNELS = {
-    "grl_fbconv_node_bwd_tc": ["fbconv_node_bwd_tc2_kernel", "fbconv_fiber_bwd_kernel"],
+    "grl_fbconv_node_bwd_tc": ["fbconv_node_bwd_tc3_kernel", "fbconv_fiber_bwd_kernel"],
+    "grl_fbconv_edge_fused_fwd": ["edge_fused_fwd_kernel"],
+    "grl_fbconv_edge_fused_bwd": ["edge_fused_bwd_ws3_kernel"],
     "grl_fbconv_node_fwd_tc": ["fbconv_node_fwd_tc2_kernel"],
     "grl_fbconv_edge_fwd_tc": ["fbconv_edge_fwd_tc_kernel"],
     "grl_fbconv_edge_bwd_tc": ["fbconv_edge_bwd_tc2_kernel"],
