@@ -272,6 +272,65 @@ def run_reference(args):
     _emit(json.dumps(line))
 
 
+def topology_rebuild_cost(dev, precision, name="rope_shaping_hepi_trpl_cfg", B=2048, steps=10):
+    """BASELINE configs[3] extension: the rope policy graph's kNN topology rebuilt from the current link positions at
+    every update (`hyper_data.rebuild_every_call`) against the reference's build-once rule, both launched eagerly (the
+    rebuilt topology has host-visible sizes, so that mode cannot be replayed from a CUDA graph), plus the graph
+    construction alone (kNN + dense task edges + dst/src CSR + live-row sets).  Single process; reporting only."""
+    from geometry_rl_b200 import learner, ops
+    from geometry_rl_b200.synthetic import CONFIGS, synthetic_minibatch, synthetic_obs
+    from geometry_rl_b200.tensors import to_device
+    ops.set_precision(precision)
+    cfg = CONFIGS[name]
+    actor, critic, _, loss_module, _ = learner.build_agent(cfg, dev, seed=0)
+    lrn = learner.Learner(cfg, actor, critic, loss_module)
+    gen = torch.Generator().manual_seed(4321)
+    obs = synthetic_obs(cfg, B, gen, env_ids=torch.arange(B) % cfg.num_envs)
+    lrn.calibrate(to_device(obs, dev))
+    with torch.no_grad():
+        d_ = actor.get_dist(to_device(obs, dev))
+        v = critic.module(*[obs[k].to(dev) for k in critic.in_keys])
+    mb = to_device(synthetic_minibatch(obs, d_.mean, d_.var_diag, v, gen), dev)
+    hd = actor.module.hyper_data if hasattr(actor, "module") and hasattr(actor.module, "hyper_data") else None
+    if hd is None:
+        for m in actor.modules():
+            if hasattr(m, "hyper_data"):
+                hd = m.hyper_data
+                break
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {"workload": f"{name}@{B}", "launch": "eager (no CUDA graph)", "steps": steps}
+    hd.rebuild_every_call = False
+    out["build_once_ms_per_step"] = timed(lambda: lrn.update(mb), steps)
+    hd.rebuild_every_call = True
+    out["rebuild_every_step_ms_per_step"] = timed(lambda: lrn.update(mb), steps)
+    pol_obs = [mb[k] for k in actor.in_keys] if hasattr(actor, "in_keys") else None
+
+    def build_only():
+        hd.invalidate()
+        g, _ = hd.build_data(*pol_obs, train=True)
+        if g.output_mask_key is not None:
+            g.hetero_pruned()
+
+    if pol_obs is not None:
+        out["graph_construction_only_ms"] = timed(build_only, steps)
+    hd.rebuild_every_call = False
+    out["samples_per_s_rebuild"] = B / (out["rebuild_every_step_ms_per_step"] * 1e-3)
+    out["samples_per_s_build_once"] = B / (out["build_once_ms_per_step"] * 1e-3)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -367,6 +426,28 @@ def measure(args, cfg_name, B, precision, dev, dp, rank, world, local, steps, fu
         del lrn, actor, critic, loss_module, dev_batches, host_batches
         torch.cuda.empty_cache()
         return res
+
+    # ---- optional device timeline of ONE step on rank 0 (GRL_TIMELINE=<path>; every rank runs the step: it holds
+    # collectives).  Compact list of [name, stream, start_us, dur_us]; read with tools/timeline_summary.py. -----------
+    tl_path = os.environ.get("GRL_TIMELINE")
+    if tl_path:
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        if rank == 0:
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step(dev_batches[0])
+                torch.cuda.synchronize()
+            trace = tl_path + ".trace.json"
+            prof.export_chrome_trace(trace)
+            ev = json.load(open(trace)).get("traceEvents", [])
+            rows = sorted(([e["name"], e.get("args", {}).get("stream"), e["ts"], e["dur"]] for e in ev
+                           if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e), key=lambda r: r[2])
+            t0 = rows[0][2] if rows else 0
+            json.dump([[r[0], r[1], round(r[2] - t0, 3), r[3]] for r in rows], open(tl_path, "w"))
+            os.remove(trace)
+        else:
+            step(dev_batches[0])
+        barrier()
 
     # ---- end to end: pinned host minibatch -> H2D -> step -> loss scalar D2H, every step ----------------
     e2e_regions = []
@@ -528,6 +609,11 @@ def run_ours(args):
             "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
             "roofline": main_res["roofline"], "cpu_baseline": cpu, "configs": side,
         }
+        if not args.no_side_workloads and dp is None:
+            try:
+                line["topology_rebuild"] = topology_rebuild_cost(dev, args.precision)
+            except Exception as exc:  # reporting only
+                line["topology_rebuild"] = {"error": f"{type(exc).__name__}: {exc}"}
         try:
             line["gae"] = gae_rate(dev, 65536, 128)
         except Exception as exc:  # reporting only

@@ -61,6 +61,11 @@ class BaseData:
         # every rollout -> update boundary restores the reference's refresh points).  A captured CUDA graph
         # (Learner.capture) holds the topology tensors it was recorded with: re-capture after an invalidation.
         self.cache_all_sizes = False
+        # Extension (BASELINE configs[3]): rebuild the kNN / task topology from the CURRENT positions on every
+        # `build_data` call instead of re-using the placeholder of the first batch (rope_tasks_data.py:224-225,251 builds
+        # once).  Off by default - parity runs use the reference's build-once rule; never on inside a CUDA-graph capture
+        # (the pruned row sets are derived with host-visible sizes).
+        self.rebuild_every_call = False
         self._placeholders: Dict[int, GraphBatch] = {}
         self._example_data: Optional[GraphBatch] = None
 
@@ -89,6 +94,9 @@ class BaseData:
         return data, input_vector
 
     def _should_reconstruct_placeholders(self, batch_size, **ignored) -> bool:
+        if self.rebuild_every_call:
+            self._placeholders.clear()
+            return True
         cached = self._placeholders.get(batch_size)
         if cached is not None:
             self._example_data = cached

@@ -51,6 +51,35 @@ def test_topology_bit_exact(cfg_name, B):
         assert torch.equal(graph.homogeneous().coo.cpu(), og_.homogeneous_edge_index())
 
 
+def test_topology_rebuild_every_call_follows_the_positions():
+    """Extension R1 (BASELINE configs[3]): with `rebuild_every_call` the rope kNN topology is that of the positions of
+    THIS call (bit-exact vs the oracle's per-graph kNN); without it the placeholder of the first batch is kept, as the
+    reference does (rope_tasks_data.py:224-225, 251)."""
+    cfg = CONFIGS["rope_shaping_hepi_trpl_cfg"]
+    B = 7
+    gen = torch.Generator().manual_seed(5)
+    env_ids = torch.arange(B) * max(1, cfg.num_envs // B)
+    obs0 = synthetic_obs(cfg, B, gen, env_ids=env_ids)
+    obs1 = synthetic_obs(cfg, B, gen, env_ids=env_ids)  # the rope has moved
+    og0, _ = oracle_graph_from_obs(cfg, obs0, policy=True)
+    og1, _ = oracle_graph_from_obs(cfg, obs1, policy=True)
+    et = ("links", "internal", "links")
+    assert not torch.equal(og0.edge_index_dict[et], og1.edge_index_dict[et]), "test needs two different kNN graphs"
+    data = G.make_data(cfg, policy=True)
+    g0, _ = data.build_data(*G.obs_args(cfg, obs0, policy=True), train=False)
+    g1, _ = data.build_data(*G.obs_args(cfg, obs1, policy=True), train=False)
+    assert torch.equal(g0.edge_index_dict[et].cpu(), og0.edge_index_dict[et])
+    assert torch.equal(g1.edge_index_dict[et].cpu(), og0.edge_index_dict[et]), "build-once: topology of the first batch"
+    data.rebuild_every_call = True
+    g1r, _ = data.build_data(*G.obs_args(cfg, obs1, policy=True), train=False)
+    assert torch.equal(g1r.edge_index_dict[et].cpu(), og1.edge_index_dict[et])
+    pr = g1r.hetero_pruned()  # live-row sets and CSR of the rebuilt graph are consistent
+    es = pr.edge_sets[et]
+    assert int(es.rowptr_dst[-1]) == es.n_edges == og1.edge_index_dict[et].shape[1]
+    g0r, _ = data.build_data(*G.obs_args(cfg, obs0, policy=True), train=False)
+    assert torch.equal(g0r.edge_index_dict[et].cpu(), og0.edge_index_dict[et])
+
+
 def test_knn_ragged_and_tiny():
     """Edge cases: graphs with 0, 1, 2, k and k+1 valid points; P not a multiple of anything."""
     from geometry_rl_b200 import ops
