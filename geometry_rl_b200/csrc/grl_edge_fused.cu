@@ -22,9 +22,8 @@
 // Forward: 256 threads, 74 KB shared memory, 128 TMEM columns -> three CTAs per SM overlap each other's MMA round
 // trips and epilogues.  The x_src rows of a tile are requested through the bulk-copy engine at the START of the tile
 // and land under its two MLP stages.
-// Backward: the live set of a tile (F, H1, basis, one gradient image, the g_x1 and x_src row tiles, three weight images)
-// is 141 KB, so one CTA per SM; it runs 16 warps in lock step, four per TMEM lane quadrant, 16 accumulator columns per
-// thread, which halves every epilogue's critical path.
+// Backward: one 800-thread CTA per SM, a four-stage pipeline (producer warp, recompute role, message-product role,
+// gradient-epilogue role) over double-buffered operand sets; see the banner above edge_fused_bwd_ws3_kernel.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -34,7 +33,6 @@
 
 namespace grl {
 
-constexpr int kFusedBwdThreads = 512;
 
 // first key node n in [0, n_nodes] with cost(n) = 8 * rowptr[n] + n >= target (a tile of 8 edges costs a few
 // microseconds of MLP work, a node's flush one 4 KB row)
@@ -320,25 +318,6 @@ __global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFu
 // ---------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------
-struct FusedBwdSmem {
-  __nv_bfloat16 F[kTM * 16];     // [2 chunks][128][8]
-  __nv_bfloat16 H1[kTM * kC];    // [8 chunks][128][8]
-  __nv_bfloat16 BZ[kTM * kC];    // recomputed basis tile
-  __nv_bfloat16 G[kTM * kC];     // g_kern, then gP2, then gP1.  MUST directly follow BZ: [BZ | G] is read as one
-                                 // 128-column MN-major image, lanes 64..127 of the accumulator then hold G^T Y
-  float GX[kTileFloats];         // g_x1 rows gathered by dst, then g_x1 * kern in place
-  float XS[kTileFloats];         // x_src rows gathered by src (run leaders only)
-  __nv_bfloat16 W1b[kC * 16];
-  __nv_bfloat16 W2b[kC * kC];    // [8 chunks][64 rows n][8 k]
-  __nv_bfloat16 Wkb[kC * kC];    // [8 chunks][64 rows c][8 j]
-  float b2[kC];
-  float acc_gb2[4][kC];
-  int src[4][kTE], dst[4][kTE], lead[4][kTE];
-  uint64_t bar[6];
-  uint64_t bar_g;
-  uint32_t tmem_base;
-};
-
 // sum over the 32 lanes of a warp of 16 per-lane values by recursive halving; on return lane l holds in v[0] the
 // total of original index l >> 1 (lanes l and l ^ 1 hold the same total).  Fixed exchange pattern -> deterministic.
 __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
@@ -357,1198 +336,24 @@ __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-__global__ void __launch_bounds__(kFusedBwdThreads, 1) edge_fused_bwd_kernel(const GrlFusedEdgeDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  FusedBwdSmem& s = *reinterpret_cast<FusedBwdSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, cq = warp >> 2, row = 32 * q + lane, c0 = 16 * cq;
-  const int so = warp, sl = lane;  // segmented-sum mapping: one warp per orientation, 2 channels per lane
-  if (tid == 0) {
-    for (int i = 0; i < 6; ++i) tc::mbar_init(&s.bar[i], 1);
-    tc::mbar_init(&s.bar_g, 1);
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 512);
-  stage_w1_bias(s.W1b, d.w1, d.b1);
-  tc::stage_weight_bf16(s.W2b, d.w2, kC, kC, kC);
-  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
-  if (tid < kC) s.b2[tid] = __ldg(d.b2 + tid);
-  if (tid < 4 * kC) (&s.acc_gb2[0][0])[tid] = 0.f;
-  const long long W = 8ll * d.n_edges + d.n_key;
-  const int n_lo = blockIdx.x == 0 ? 0 : fused_lower_bound(d.rowptr, d.n_key, W * blockIdx.x / gridDim.x);
-  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_key : fused_lower_bound(d.rowptr, d.n_key, W * (blockIdx.x + 1) / gridDim.x);
-  const int p0 = d.rowptr[n_lo], p1 = d.rowptr[n_hi];
-  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
-
-  auto load_idx = [&](int t, int& es, int& ed) {
-    es = 0; ed = 0;
-    const int e = p0 + t * kTE + tid;
-    if (tid < kTE && t < n_tiles && e < p1) { es = __ldg(d.e_src + e); ed = __ldg(d.e_dst + e); }
-  };
-  auto publish = [&](int slot_, int t_, int es, int ed) {
-    if (warp == 0) {  // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row
-      const int prev = __shfl_up_sync(0xffffffffu, es, 1);
-      const bool valid = lane < kTE && p0 + t_ * kTE + lane < p1;
-      const bool starts = lane == 0 || !valid || es != prev;
-      const unsigned heads = __ballot_sync(0xffffffffu, starts);
-      const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
-      if (lane < kTE) { s.src[slot_][lane] = es; s.dst[slot_][lane] = ed; s.lead[slot_][lane] = ld; }
-    }
-  };
-  int es_a, ed_a, es_b, ed_b;
-  load_idx(0, es_a, ed_a);
-  publish(0, 0, es_a, ed_a);
-  load_idx(1, es_a, ed_a);
-  publish(1, 1, es_a, ed_a);
-  load_idx(2, es_a, ed_a);
-  load_idx(3, es_b, ed_b);
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t fa = tc::smem_u32(s.F), ha = tc::smem_u32(s.H1), bz = tc::smem_u32(s.BZ), ga = tc::smem_u32(s.G);
-  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b), wk = tc::smem_u32(s.Wkb);
-  // TMEM columns: [0,64) pre1 -> gH1   [64,128) pre2   [128,192) kern -> g_basis
-  //               [192,256) gWk   [256,320) gW2   [320,336) [gW1 | gb1]   (lanes 64..127 of the last three)
-  constexpr uint32_t kR0 = 0, kR1 = 64, kR2 = 128, kGWk = 192, kGW2 = 256, kGW1 = 320;
-
-  RowPos pos;
-  pos.valid = false;
-  if (tid < kTM && n_tiles > 0) {
-    const int j = tid >> 4;
-    pos.load(d, s.src[0][j], s.dst[0][j], p0 + j < p1);
-  }
-  // rows of tile t -> L2 (threads 0..15: 8 entries x {g_x1, x_src}); slot (t & 3) must be visible
-  auto prefetch_tile = [&](int t_) {
-    if (tid < 2 * kTE && t_ < n_tiles) {
-      const int j = tid & 7;
-      if (p0 + t_ * kTE + j < p1) {
-        if (tid < kTE) tc::prefetch_l2(d.grad_x1 + (size_t)s.dst[t_ & 3][j] * kRow, kRow * 4u);
-        else if (s.lead[t_ & 3][j] == j) tc::prefetch_l2(d.x_src + (size_t)s.src[t_ & 3][j] * kRow, kRow * 4u);
-      }
-    }
-  };
-  prefetch_tile(0);
-
-  int cur = n_lo;
-  float2 sum = make_float2(0.f, 0.f), init = make_float2(0.f, 0.f);
-  const size_t toff = (size_t)so * kC + 2 * sl;
-  auto begin_node = [&](int node) {  // residual row of `node`, added at its flush
-    if (d.grad_x_src_init && node < n_hi) init = __ldg(reinterpret_cast<const float2*>(d.grad_x_src_init + (size_t)node * kRow + toff));
-  };
-  auto flush = [&](int node) {
-    sum.x += init.x; sum.y += init.y;
-    *reinterpret_cast<float2*>(d.grad_x_src + (size_t)node * kRow + toff) = sum;
-    sum = make_float2(0.f, 0.f);
-  };
-  // advance to node `to`: flush the current node, then copy the residual rows of the edge-less nodes in between
-  auto advance = [&](int to) {
-    flush(cur);
-    ++cur;
-    while (cur < to) {
-      const int n = min(4, to - cur);
-      float2 r[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        r[i] = (d.grad_x_src_init && i < n) ? __ldg(reinterpret_cast<const float2*>(d.grad_x_src_init + (size_t)(cur + i) * kRow + toff))
-                                            : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < n) *reinterpret_cast<float2*>(d.grad_x_src + (size_t)(cur + i) * kRow + toff) = r[i];
-      cur += n;
-    }
-    begin_node(cur);
-  };
-  begin_node(cur);
-
-  for (int t = 0; t < n_tiles; ++t) {
-    const int slot = t & 3;
-    const uint32_t par = (uint32_t)t & 1u;
-    const int cnt = min(kTE, p1 - (p0 + t * kTE));
-    const bool acc = t > 0;
-    publish((t + 2) & 3, t + 2, es_a, ed_a);
-    es_a = es_b; ed_a = ed_b;
-    load_idx(t + 4, es_b, ed_b);
-    if (t > 0) {  // the [gW1 | gb1] MMA of tile t-1 still reads F and G
-      tc::mbar_wait(&s.bar[5], par ^ 1u);
-      tc::tc_fence_after();
-    }
-    tc::fence_async_smem();  // generic-proxy accesses to GX / XS (tile t-1) before the bulk engine rewrites them
-    tc::tc_fence_before();
-    __syncthreads();         // (A)
-    prefetch_tile(t + 1);
-    if (tid == 32 && d.grad_x_src_init && cur + 2 < n_hi)  // residual rows of the next few nodes -> L2
-      tc::prefetch_l2(d.grad_x_src_init + (size_t)(cur + 2) * kRow, (uint32_t)min(8, n_hi - cur - 2) * kRow * 4u);
-    if (tid < 2 * kTM) {
-      // thread r < 128 owns row r of GX (g_x1 by dst), thread 128 + r row r of XS (x_src by src, run leaders only)
-      const int rr = tid & 127, j = rr >> 4, oo = rr & 15;
-      const bool is_x = tid >= kTM;
-      float* drow = (is_x ? s.XS : s.GX) + rr * kLDT;
-      if (j < cnt) {
-        if (!is_x) tc::bulk_g2s(drow, d.grad_x1 + (size_t)s.dst[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
-        else if (s.lead[slot][j] == j) tc::bulk_g2s(drow, d.x_src + (size_t)s.src[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
-      } else {  // rows past the end of the list: zeros (they meet finite rows in the products)
-#pragma unroll
-        for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (tid == 0) {
-        int n_lead = 0;
-        for (int jj = 0; jj < cnt; ++jj) n_lead += s.lead[slot][jj] == jj;
-        tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + n_lead) * kO * kC * 4u);
-      }
-      if (!is_x) {
-        pos.emit(d, s.F, tid);
-        const int nb = p0 + (t + 1) * kTE + j;
-        pos.load(d, s.src[(t + 1) & 3][j], s.dst[(t + 1) & 3][j], t + 1 < n_tiles && nb < p1);
-      }
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();  // (B)
-    if (tid == 0) {   // pre1 = [F | 1 1] [W1 | b1]^T
-      tc::tc_fence_after();
-      tc::issue_mma(tmem + kR0, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
-      tc::mma_commit(&s.bar[0]);
-    }
-    tc::mbar_wait(&s.bar[0], par);
-    tc::tc_fence_after();
-    float dG1[16], dG2[16];
-    {
-      float v[16];
-      tc::tmem_ld16(lane_addr + kR0 + c0, v);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) gelu_fast(v[e], v[e], dG1[e]);
-      *reinterpret_cast<uint4*>(s.H1 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-      *reinterpret_cast<uint4*>(s.H1 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();  // (C)
-    if (tid == 0) {   // pre2 = H1 W2^T
-      tc::tc_fence_after();
-      tc::issue_mma(tmem + kR1, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-      tc::mma_commit(&s.bar[1]);
-    }
-    tc::mbar_wait(&s.bar[1], par);
-    tc::tc_fence_after();
-    {
-      float v[16];
-      tc::tmem_ld16(lane_addr + kR1 + c0, v);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) gelu_fast(v[e] + s.b2[c0 + e], v[e], dG2[e]);
-      *reinterpret_cast<uint4*>(s.BZ + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-      *reinterpret_cast<uint4*>(s.BZ + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();  // (D)
-    if (tid == 0) {   // kern = basis Wk^T
-      tc::tc_fence_after();
-      tc::issue_mma(tmem + kR2, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-      tc::mma_commit(&s.bar[2]);
-    }
-    tc::mbar_wait(&s.bar_g, par);  // the g_x1 / x_src rows have landed
-    tc::mbar_wait(&s.bar[2], par);
-    tc::tc_fence_after();
-    {
-      float v[16], gkv[16];
-      tc::tmem_ld16(lane_addr + kR2 + c0, v);
-      float* gx = s.GX + row * kLDT + c0;
-      const float* xs = s.XS + (16 * s.lead[slot][row >> 4] + (row & 15)) * kLDT + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) {
-        const float4 gm = ld4(gx + e), x = ld4(xs + e);
-        st4(gx + e, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
-        gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
-      }
-      *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
-      *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();  // (E)
-    if (tid == 0) {
-      tc::tc_fence_after();
-      // g_basis = g_kern Wk   (Wk image [c rows][j cols] read MN-major: K = c, N = j); kern's columns are free again
-      tc::issue_mma(tmem + kR2, tc::view_k(ga, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-      // lanes 64..127: gWk[c][j] += sum_rows g_kern[row][c] basis[row][j]   ([BZ | G] as one 128-column image)
-      tc::issue_mma(tmem + kGWk, tc::view_mn(bz, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
-      tc::mma_commit(&s.bar[3]);
-    }
-    // src-CSR segmented sum of g_x1 * kern while the tensor core works
-#pragma unroll
-    for (int j = 0; j < kTE; ++j) {
-      if (j < cnt) {
-        const int sn = s.src[slot][j];
-        if (cur < sn) advance(sn);
-        const float2 m = *reinterpret_cast<const float2*>(s.GX + (16 * j + so) * kLDT + 2 * sl);
-        sum.x += m.x; sum.y += m.y;
-      }
-    }
-    tc::mbar_wait(&s.bar[3], par);
-    tc::tc_fence_after();
-    {
-      float v[16];
-      tc::tmem_ld16(lane_addr + kR2 + c0, v);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] *= dG2[e];
-      *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-      *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-      warp_colsum16(v, lane);
-      if ((lane & 1) == 0) s.acc_gb2[q][c0 + (lane >> 1)] += v[0];
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();  // (F)
-    if (tid == 0) {
-      tc::tc_fence_after();
-      // gH1 = gP2 W2   (W2 image [n rows][k cols] read MN-major: K = n, N = k); pre1's columns are free again
-      tc::issue_mma(tmem + kR0, tc::view_k(ga, kTM), tc::view_mn(w2, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-      // lanes 64..127: gW2[n][k] += sum_rows gP2[row][n] H1[row][k]
-      tc::issue_mma(tmem + kGW2, tc::view_mn(bz, kTM), tc::view_mn(ha, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
-      tc::mma_commit(&s.bar[4]);
-    }
-    tc::mbar_wait(&s.bar[4], par);
-    tc::tc_fence_after();
-    {
-      float v[16];
-      tc::tmem_ld16(lane_addr + kR0 + c0, v);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] *= dG1[e];
-      *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-      *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-    }
-    tc::fence_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();  // (G)
-    if (tid == 0) {
-      tc::tc_fence_after();
-      // lanes 64..127: [gW1 | gb1][n][f] += sum_rows gP1[row][n] [F | 1 1][row][f]
-      tc::issue_mma(tmem + kGW1, tc::view_mn(bz, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, acc);
-      tc::mma_commit(&s.bar[5]);
-    }
-  }
-  if (n_tiles > 0) {
-    tc::mbar_wait(&s.bar[5], (uint32_t)(n_tiles - 1) & 1u);
-    tc::tc_fence_after();
-  }
-  if (cur < n_hi) advance(n_hi);
-  // partial slot of this CTA: gWk[64][64] | gW1b[64][16] (columns 14, 15 = gb1) | gW2[64][64] | gb2[64]
-  __syncthreads();
-  float* P = d.grad_partials + (size_t)blockIdx.x * GRL_FUSED_EDGE_GRAD_FLOATS;
-  {
-    float v[16];
-    auto read = [&](uint32_t col) {
-      if (n_tiles > 0) {
-        tc::tmem_ld16(lane_addr + col, v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.f;
-      }
-    };
-    read(kGWk + c0);
-    if (row >= 64) {
-      float* p = P + (size_t)(row - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-    read(kGW2 + c0);
-    if (row >= 64) {
-      float* p = P + kWFloats + 64 * 16 + (size_t)(row - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-    read(kGW1);
-    if (row >= 64 && cq == 0) {
-      float* p = P + kWFloats + (size_t)(row - 64) * 16;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-  }
-  if (tid < kC)
-    P[2 * kWFloats + 64 * 16 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// backward, warp-specialised (the product path): two decoupled 8-warp roles per CTA, one CTA per SM.
-//   role R (warps 0..7)  recomputes the MLP of tile t+1: features -> pre1 -> H1, GELU'(pre1) -> pre2 -> basis, GELU'(pre2)
-//                        into operand set (t+1) & 1 (F, H1, basis in shared memory; the two derivative planes as packed
-//                        fp16 pairs in the TMEM columns their pre-activations occupied, written with tcgen05.st);
-//   role C (warps 8..15) consumes set t & 1: gathers g_x1 / x_src rows, kern, the message products, the src-CSR segmented
-//                        sum, g_basis, gP2, gH1, gP1 and the four weight-gradient MMAs.
-// The roles meet only through two mbarrier pairs: full[b] (256 arrivals of R: set b is complete) and empty[b] (the
-// tcgen05.commit of C's last MMA on set b).  Inside a role the phases are bulk-synchronous on a named barrier, so while
-// one role waits for a tensor-core round trip the other one issues its epilogue: the lock-step kernel above spends
-// 16 k cycles per tile in 7 serial phases (ncu, profiles/r02_*), this one overlaps R's 2 phases with C's 4.
-// ---------------------------------------------------------------------------------------------------
-struct FusedBwdWsSmem {
-  __nv_bfloat16 F[2][kTM * 16];
-  __nv_bfloat16 H1[2][kTM * kC];
-  __nv_bfloat16 BZ[2][kTM * kC];
-  __nv_bfloat16 W1b[kC * 16];
-  __nv_bfloat16 Wkb[kC * kC];    // [Wkb | W2b] = 16 KB of finite values directly in front of G: the ignored X half of the
-  __nv_bfloat16 W2b[kC * kC];    // 128-column [X | G] image of the weight-gradient MMAs
-  __nv_bfloat16 G[kTM * kC];     // g_kern, then gP2, then gP1
-  float GX[kTileFloats];
-  float XS[kTileFloats];
-  float b2[kC];
-  float acc_gb2[4][kC];
-  int src[4][kTE], dst[4][kTE], lead[4][kTE];
-  uint64_t bar_r[2];             // role R's MMA completions (pre1, pre2)
-  uint64_t bar_c[3];             // role C's MMA completions (kern; g_basis + gWk; gH1 + gW2)
-  uint64_t full[2], empty[2];
-  uint64_t bar_g;
-  uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(kFusedBwdThreads, 1) edge_fused_bwd_ws_kernel(const GrlFusedEdgeDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  FusedBwdWsSmem& s = *reinterpret_cast<FusedBwdWsSmem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool role_c = warp >= 8;
-  const int rt = tid & 255, rw = warp & 7;        // thread / warp index inside the role
-  const int q = rw & 3, ch = rw >> 2, row = 32 * q + lane;
-  if (tid == 0) {
-    tc::mbar_init(&s.bar_r[0], 1);
-    tc::mbar_init(&s.bar_r[1], 1);
-    for (int i = 0; i < 3; ++i) tc::mbar_init(&s.bar_c[i], 1);
-    tc::mbar_init(&s.full[0], 256);
-    tc::mbar_init(&s.full[1], 256);
-    tc::mbar_init(&s.empty[0], 1);
-    tc::mbar_init(&s.empty[1], 1);
-    tc::mbar_init(&s.bar_g, 1);
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 512);
-  stage_w1_bias(s.W1b, d.w1, d.b1);
-  tc::stage_weight_bf16(s.W2b, d.w2, kC, kC, kC);
-  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
-  if (tid < kC) s.b2[tid] = __ldg(d.b2 + tid);
-  if (tid < 4 * kC) (&s.acc_gb2[0][0])[tid] = 0.f;
-  const long long W = 8ll * d.n_edges + d.n_key;
-  const int n_lo = blockIdx.x == 0 ? 0 : fused_lower_bound(d.rowptr, d.n_key, W * blockIdx.x / gridDim.x);
-  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_key : fused_lower_bound(d.rowptr, d.n_key, W * (blockIdx.x + 1) / gridDim.x);
-  const int p0 = d.rowptr[n_lo], p1 = d.rowptr[n_hi];
-  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b), wk = tc::smem_u32(s.Wkb), ga = tc::smem_u32(s.G);
-  // TMEM columns: set b: [128 b, +64) pre1 -> packed GELU'(pre1) ; [128 b + 64, +64) pre2 -> packed GELU'(pre2)
-  //               [256,320) kern -> g_basis -> gH1   [320,384) gWk   [384,448) gW2   [448,464) [gW1 | gb1]
-  constexpr uint32_t kR2 = 256, kGWk = 320, kGW2 = 384, kGW1 = 448;
-
-  if (!role_c) {
-    // =========================================== role R ===========================================================
-    RowPos pos;            // positions of tile t's rows
-    int es_n = 0, ed_n = 0;  // endpoints of tile t+1's row
-    bool v_n = false;
-    auto load_ids = [&](int t_) {
-      const int e = p0 + t_ * kTE + (rt >> 4);
-      v_n = rt < kTM && t_ < n_tiles && e < p1;
-      if (v_n) { es_n = __ldg(d.e_src + e); ed_n = __ldg(d.e_dst + e); }
-    };
-    pos.valid = false;
-    load_ids(0);
-    pos.load(d, es_n, ed_n, v_n);
-    load_ids(1);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int b = t & 1;
-      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
-      const uint32_t fa = tc::smem_u32(s.F[b]), ha = tc::smem_u32(s.H1[b]), bz = tc::smem_u32(s.BZ[b]);
-      const uint32_t kA = 128u * b, kB = 128u * b + 64u;
-      tc::mbar_wait(&s.empty[b], parb ^ 1u);  // role C is done with set b (tile t-2); passes at once for t < 2
-      tc::tc_fence_after();
-      if (rt < kTM) {
-        pos.emit(d, s.F[b], rt);
-        pos.load(d, es_n, ed_n, v_n);  // positions of tile t+1 (ids requested one iteration ago)
-        load_ids(t + 2);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(1, 256);
-      if (rt == 0) {  // pre1 = [F | 1 1] [W1 | b1]^T
-        tc::tc_fence_after();
-        tc::issue_mma(tmem + kA, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
-        tc::mma_commit(&s.bar_r[0]);
-      }
-      tc::mbar_wait(&s.bar_r[0], par);
-      tc::tc_fence_after();
-      {
-        uint32_t dpk[16];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16], dg[16];
-          tc::tmem_ld16(lane_addr + kA + c0, v);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) gelu_fast(v[e], v[e], dg[e]);
-          *reinterpret_cast<uint4*>(s.H1[b] + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-          *reinterpret_cast<uint4*>(s.H1[b] + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const __half2 h = __floats2half2_rn(dg[2 * e], dg[2 * e + 1]);
-            dpk[8 * i + e] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-        }
-        tc::tmem_st16(lane_addr + kA + 32 * ch, dpk);  // over this thread's own (already read) pre1 columns
-      }
-      tc::tmem_st_wait();
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(1, 256);
-      if (rt == 0) {  // pre2 = H1 W2^T
-        tc::tc_fence_after();
-        tc::issue_mma(tmem + kB, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-        tc::mma_commit(&s.bar_r[1]);
-      }
-      tc::mbar_wait(&s.bar_r[1], par);
-      tc::tc_fence_after();
-      {
-        uint32_t dpk[16];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16], dg[16];
-          tc::tmem_ld16(lane_addr + kB + c0, v);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) gelu_fast(v[e] + s.b2[c0 + e], v[e], dg[e]);
-          *reinterpret_cast<uint4*>(s.BZ[b] + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-          *reinterpret_cast<uint4*>(s.BZ[b] + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const __half2 h = __floats2half2_rn(dg[2 * e], dg[2 * e + 1]);
-            dpk[8 * i + e] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-        }
-        tc::tmem_st16(lane_addr + kB + 32 * ch, dpk);
-      }
-      tc::tmem_st_wait();
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s.full[b]);  // this thread's share of set b (H1, basis, both derivative planes) is in place
-      (void)bz;
-    }
-  } else {
-    // =========================================== role C ===========================================================
-    const int o = rt >> 4, cg = rt & 15;  // mapping of the segmented-sum phase
-    auto load_idx = [&](int t_, int& es, int& ed) {
-      es = 0; ed = 0;
-      const int e = p0 + t_ * kTE + rt;
-      if (rt < kTE && t_ < n_tiles && e < p1) { es = __ldg(d.e_src + e); ed = __ldg(d.e_dst + e); }
-    };
-    auto publish = [&](int slot_, int t_, int es, int ed) {
-      if (rw == 0) {  // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row
-        const int prev = __shfl_up_sync(0xffffffffu, es, 1);
-        const bool valid = lane < kTE && p0 + t_ * kTE + lane < p1;
-        const bool starts = lane == 0 || !valid || es != prev;
-        const unsigned heads = __ballot_sync(0xffffffffu, starts);
-        const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
-        if (lane < kTE) { s.src[slot_][lane] = es; s.dst[slot_][lane] = ed; s.lead[slot_][lane] = ld; }
-      }
-    };
-    int es_a, ed_a, es_b, ed_b;
-    load_idx(0, es_a, ed_a);
-    publish(0, 0, es_a, ed_a);
-    load_idx(1, es_a, ed_a);
-    publish(1, 1, es_a, ed_a);
-    load_idx(2, es_a, ed_a);
-    load_idx(3, es_b, ed_b);
-    tc::group_sync(2, 256);
-    auto prefetch_tile = [&](int t_) {
-      if (rt < 2 * kTE && t_ < n_tiles) {
-        const int j = rt & 7;
-        if (p0 + t_ * kTE + j < p1) {
-          if (rt < kTE) tc::prefetch_l2(d.grad_x1 + (size_t)s.dst[t_ & 3][j] * kRow, kRow * 4u);
-          else if (s.lead[t_ & 3][j] == j) tc::prefetch_l2(d.x_src + (size_t)s.src[t_ & 3][j] * kRow, kRow * 4u);
-        }
-      }
-    };
-    prefetch_tile(0);
-    int cur = n_lo;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), init = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t toff = (size_t)o * kC + 4 * cg;
-    auto begin_node = [&](int node) {
-      if (d.grad_x_src_init && node < n_hi) init = ldg4(d.grad_x_src_init + (size_t)node * kRow + toff);
-    };
-    auto flush = [&](int node) {
-      sum.x += init.x; sum.y += init.y; sum.z += init.z; sum.w += init.w;
-      st4(d.grad_x_src + (size_t)node * kRow + toff, sum);
-      sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    auto advance = [&](int to) {
-      flush(cur);
-      ++cur;
-      while (cur < to) {
-        const int n = min(4, to - cur);
-        float4 r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          r[i] = (d.grad_x_src_init && i < n) ? ldg4(d.grad_x_src_init + (size_t)(cur + i) * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < n) st4(d.grad_x_src + (size_t)(cur + i) * kRow + toff, r[i]);
-        cur += n;
-      }
-      begin_node(cur);
-    };
-    begin_node(cur);
-
-    for (int t = 0; t < n_tiles; ++t) {
-      const int slot = t & 3, b = t & 1;
-      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
-      const int cnt = min(kTE, p1 - (p0 + t * kTE));
-      const bool acc = t > 0;
-      const uint32_t fa = tc::smem_u32(s.F[b]), ha = tc::smem_u32(s.H1[b]), bz = tc::smem_u32(s.BZ[b]);
-      const uint32_t kA = 128u * b, kB = 128u * b + 64u;
-      publish((t + 2) & 3, t + 2, es_a, ed_a);
-      es_a = es_b; ed_a = ed_b;
-      load_idx(t + 4, es_b, ed_b);
-      if (t > 0) {  // the [gW1 | gb1] MMA of tile t-1 still reads G (its commit is empty[(t-1) & 1])
-        tc::mbar_wait(&s.empty[(t - 1) & 1], (uint32_t)((t - 1) >> 1) & 1u);
-        tc::tc_fence_after();
-      }
-      tc::fence_async_smem();  // generic-proxy accesses to GX / XS (tile t-1) before the bulk engine rewrites them
-      tc::group_sync(2, 256);  // (A)
-      prefetch_tile(t + 1);
-      if (rt == 32 && d.grad_x_src_init && cur + 2 < n_hi)
-        tc::prefetch_l2(d.grad_x_src_init + (size_t)(cur + 2) * kRow, (uint32_t)min(8, n_hi - cur - 2) * kRow * 4u);
-      {
-        // thread r < 128 owns row r of GX (g_x1 by dst), thread 128 + r row r of XS (x_src by src, run leaders only)
-        const int rr = rt & 127, j = rr >> 4, oo = rr & 15;
-        const bool is_x = rt >= kTM;
-        float* drow = (is_x ? s.XS : s.GX) + rr * kLDT;
-        if (j < cnt) {
-          if (!is_x) tc::bulk_g2s(drow, d.grad_x1 + (size_t)s.dst[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
-          else if (s.lead[slot][j] == j) tc::bulk_g2s(drow, d.x_src + (size_t)s.src[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_g);
-        } else {
-#pragma unroll
-          for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (rt == 0) {
-          int n_lead = 0;
-          for (int jj = 0; jj < cnt; ++jj) n_lead += s.lead[slot][jj] == jj;
-          tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + n_lead) * kO * kC * 4u);
-        }
-      }
-      tc::mbar_wait(&s.full[b], parb);  // role R has finished set b
-      tc::tc_fence_after();
-      if (rt == 0) {  // kern = basis Wk^T
-        tc::issue_mma(tmem + kR2, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-        tc::mma_commit(&s.bar_c[0]);
-      }
-      tc::mbar_wait(&s.bar_g, par);  // the g_x1 / x_src rows have landed
-      tc::mbar_wait(&s.bar_c[0], par);
-      tc::tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c0 = 32 * ch + 16 * i;
-        float v[16], gkv[16];
-        tc::tmem_ld16(lane_addr + kR2 + c0, v);
-        float* gx = s.GX + row * kLDT + c0;
-        const float* xs = s.XS + (16 * s.lead[slot][row >> 4] + (row & 15)) * kLDT + c0;
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const float4 gm = ld4(gx + e), x = ld4(xs + e);
-          st4(gx + e, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
-          gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
-        }
-        *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
-        *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(2, 256);  // (E)
-      if (rt == 0) {
-        tc::tc_fence_after();
-        // g_basis = g_kern Wk (Wk image read MN-major: K = c, N = j); kern's columns are free again
-        tc::issue_mma(tmem + kR2, tc::view_k(ga, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-        // lanes 64..127: gWk[c][j] += sum_rows g_kern[row][c] basis[row][j]   ([Wkb W2b | G] as one 128-column image)
-        tc::issue_mma(tmem + kGWk, tc::view_mn(wk, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
-        tc::mma_commit(&s.bar_c[1]);
-      }
-      // src-CSR segmented sum of g_x1 * kern while the tensor core works
-#pragma unroll
-      for (int j = 0; j < kTE; ++j) {
-        if (j < cnt) {
-          const int sn = s.src[slot][j];
-          if (cur < sn) advance(sn);
-          const float4 m = ld4(s.GX + (16 * j + o) * kLDT + 4 * cg);
-          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
-        }
-      }
-      tc::mbar_wait(&s.bar_c[1], par);
-      tc::tc_fence_after();
-      {
-        uint32_t dpk[16];
-        tc::tmem_ld16_raw(lane_addr + kB + 32 * ch, dpk);  // GELU'(pre2) of this thread's 32 columns, packed fp16 pairs
-        float gp2[32];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16];
-          tc::tmem_ld16(lane_addr + kR2 + c0, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 dg = __half22float2(*reinterpret_cast<const __half2*>(&dpk[8 * i + e]));
-            gp2[16 * i + 2 * e] = v[2 * e] * dg.x;
-            gp2[16 * i + 2 * e + 1] = v[2 * e + 1] * dg.y;
-          }
-          *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i);
-          *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i + 8);
-        }
-        tc::warp_colsum<32>(gp2, lane);
-        s.acc_gb2[q][32 * ch + lane] += gp2[0];
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(2, 256);  // (F)
-      if (rt == 0) {
-        tc::tc_fence_after();
-        // gH1 = gP2 W2 (W2 image read MN-major: K = n, N = k)
-        tc::issue_mma(tmem + kR2, tc::view_k(ga, kTM), tc::view_mn(w2, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-        // lanes 64..127: gW2[n][k] += sum_rows gP2[row][n] H1[row][k]
-        tc::issue_mma(tmem + kGW2, tc::view_mn(wk, kTM), tc::view_mn(ha, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
-        tc::mma_commit(&s.bar_c[2]);
-      }
-      tc::mbar_wait(&s.bar_c[2], par);
-      tc::tc_fence_after();
-      {
-        uint32_t dpk[16];
-        tc::tmem_ld16_raw(lane_addr + kA + 32 * ch, dpk);  // GELU'(pre1)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16];
-          tc::tmem_ld16(lane_addr + kR2 + c0, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 dg = __half22float2(*reinterpret_cast<const __half2*>(&dpk[8 * i + e]));
-            v[2 * e] *= dg.x;
-            v[2 * e + 1] *= dg.y;
-          }
-          *reinterpret_cast<uint4*>(s.G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-          *reinterpret_cast<uint4*>(s.G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-        }
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(2, 256);  // (G)
-      if (rt == 0) {
-        tc::tc_fence_after();
-        // lanes 64..127: [gW1 | gb1][n][f] += sum_rows gP1[row][n] [F | 1 1][row][f]; its completion frees set b and G
-        tc::issue_mma(tmem + kGW1, tc::view_mn(wk, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, acc);
-        tc::mma_commit(&s.empty[b]);
-      }
-    }
-    if (n_tiles > 0) {
-      tc::mbar_wait(&s.empty[(n_tiles - 1) & 1], (uint32_t)((n_tiles - 1) >> 1) & 1u);
-      tc::tc_fence_after();
-    }
-    if (cur < n_hi) advance(n_hi);
-  }
-  // partial slot of this CTA: gWk[64][64] | gW1b[64][16] (columns 14, 15 = gb1) | gW2[64][64] | gb2[64]
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  float* P = d.grad_partials + (size_t)blockIdx.x * GRL_FUSED_EDGE_GRAD_FLOATS;
-  {
-    const int q4 = warp & 3, cq = warp >> 2, row4 = 32 * q4 + lane, c0 = 16 * cq;  // all 16 warps: 16 columns per thread
-    const uint32_t la = tmem + ((uint32_t)(32 * q4) << 16);
-    float v[16];
-    auto read = [&](uint32_t col) {
-      if (n_tiles > 0) {
-        tc::tmem_ld16(la + col, v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.f;
-      }
-    };
-    read(kGWk + c0);
-    if (row4 >= 64) {
-      float* p = P + (size_t)(row4 - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-    read(kGW2 + c0);
-    if (row4 >= 64) {
-      float* p = P + kWFloats + 64 * 16 + (size_t)(row4 - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-    read(kGW1);
-    if (row4 >= 64 && cq == 0) {
-      float* p = P + kWFloats + (size_t)(row4 - 64) * 16;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-  }
-  if (tid < kC)
-    P[2 * kWFloats + 64 * 16 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// backward, second generation of the warp-specialised kernel (the product path).  What ncu said about the first one
-// (profiles/r02_fused_bwd_ws1.md): role R idles 57 % of the time waiting for role C, whose tile period (14.5 k cycles) goes
-// to issuing 176 per-row bulk copies through elect-and-broadcast loops (23 %), waiting for them (13 %), and waiting for the
-// previous tile's last MMA before the shared gradient image may be rewritten (14 %).  Hence:
-//   * a PRODUCER warp (warp 16) owns the index stream and the gathers.  Rows arrive through two tensor maps
-//     (cp.async.bulk.tensor.2d, SASS UTMALDG): one 16-row x 32-channel box per (edge, channel half), 128-byte swizzled, so
-//     a tile is 16 + <= 16 copies instead of 176 and the row tiles need no padding.  It runs one tile ahead of role C,
-//     gated by two "free" barriers (x_src tile after the message products, g_x1 tile after the segmented sum), and
-//     publishes (src, dst, leader) of the tile under the same transaction barrier as the data;
-//   * the gradient image G is double buffered, so role C never waits for its own last MMA;
-//   * role R evaluates GELU and its derivative on packed fp16 pairs (the derivative plane is stored as fp16 anyway).
-// Roles R and C are otherwise the ones of edge_fused_bwd_ws_kernel above.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kWs2Threads = 544;
-
-struct FusedBwdWs2Smem {
-  float GX[kTM * kC];            // [8 entries][2 halves][16 rows][32 floats]: 2 KB boxes at 1024-byte multiples, swizzled by TMA
-  float XS[kTM * kC];
-  __nv_bfloat16 F[2][kTM * 16];
-  __nv_bfloat16 H1[2][kTM * kC];
-  __nv_bfloat16 BZ[2][kTM * kC];
-  __nv_bfloat16 W1b[kC * 16];
-  __nv_bfloat16 Wkb[kC * kC];    // [Wkb | W2b] and G[0] are the ignored X halves of the [X | G] images of G[0] and G[1]
-  __nv_bfloat16 W2b[kC * kC];
-  __nv_bfloat16 G[2][kTM * kC];  // MUST directly follow W2b
-  float b2[kC];
-  float acc_gb2[4][kC];
-  int src[4][kTE], dst[4][kTE], lead[4][kTE];
-  uint64_t bar_r[2], bar_c[3], full[2], empty[2];
-  uint64_t bar_g, xs_free, gx_free;
-  uint32_t tmem_base;
-};
-
 // float offset of the 16-byte chunk k (channels 4k..4k+3 of the half) of row (entry j, orientation o) in a swizzled row tile
 __device__ __forceinline__ int swz_off(int j, int half, int o, int k) {
   return (((j * 2 + half) * kO + o) << 5) + ((k ^ (o & 7)) << 2);
 }
 
-template <int kVariant>  // bit 0: kern MMA of tile t+1 issued at the end of tile t; bit 1: residual rows two flushes ahead
-__global__ void __launch_bounds__(kWs2Threads, 1)
-edge_fused_bwd_ws2_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUtensorMap tm_gx, const __grid_constant__ CUtensorMap tm_xs) {
-  extern __shared__ unsigned char smem_dyn[];
-  FusedBwdWs2Smem& s = *reinterpret_cast<FusedBwdWs2Smem*>(
-      smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));  // the swizzle atoms want a 1024-byte aligned base
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int role = warp >> 3;                      // 0 = R, 1 = C, 2 = producer
-  const int rt = tid & 255, rw = warp & 7;
-  const int q = rw & 3, ch = rw >> 2, row = 32 * q + lane;
-  if (tid == 0) {
-    tc::mbar_init(&s.bar_r[0], 1);
-    tc::mbar_init(&s.bar_r[1], 1);
-    for (int i = 0; i < 3; ++i) tc::mbar_init(&s.bar_c[i], 1);
-    tc::mbar_init(&s.full[0], 256);
-    tc::mbar_init(&s.full[1], 256);
-    tc::mbar_init(&s.empty[0], 1);
-    tc::mbar_init(&s.empty[1], 1);
-    tc::mbar_init(&s.bar_g, 1);
-    tc::mbar_init(&s.xs_free, 256);
-    tc::mbar_init(&s.gx_free, 256);
-    tc::fence_mbar_init();
-  }
-  if (warp == 0) tc::tmem_alloc(&s.tmem_base, 512);
-  stage_w1_bias(s.W1b, d.w1, d.b1);
-  tc::stage_weight_bf16(s.W2b, d.w2, kC, kC, kC);
-  tc::stage_weight_bf16(s.Wkb, d.wk, kC, kC, kC);
-  if (tid < kC) s.b2[tid] = __ldg(d.b2 + tid);
-  if (tid < 4 * kC) (&s.acc_gb2[0][0])[tid] = 0.f;
-  const long long W = 8ll * d.n_edges + d.n_key;
-  const int n_lo = blockIdx.x == 0 ? 0 : fused_lower_bound(d.rowptr, d.n_key, W * blockIdx.x / gridDim.x);
-  const int n_hi = blockIdx.x + 1 == gridDim.x ? d.n_key : fused_lower_bound(d.rowptr, d.n_key, W * (blockIdx.x + 1) / gridDim.x);
-  const int p0 = d.rowptr[n_lo], p1 = d.rowptr[n_hi];
-  const int n_tiles = (p1 - p0 + kTE - 1) / kTE;
-  tc::fence_async_smem();
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base, lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-  const uint32_t w1 = tc::smem_u32(s.W1b), w2 = tc::smem_u32(s.W2b), wk = tc::smem_u32(s.Wkb);
-  constexpr uint32_t kR2 = 256, kGWk = 320, kGW2 = 384, kGW1 = 448;
-
-  if (role == 2) {
-    // =========================================== producer warp =====================================================
-    if (lane == 0) {
-      tc::tma_prefetch_desc(&tm_gx);
-      tc::tma_prefetch_desc(&tm_xs);
-    }
-    int es = 0, ed = 0, es_n = 0, ed_n = 0;
-    auto load_idx = [&](int t_, int& a, int& b_) {
-      a = 0; b_ = 0;
-      const int e = p0 + t_ * kTE + lane;
-      if (lane < kTE && t_ < n_tiles && e < p1) { a = __ldg(d.e_src + e); b_ = __ldg(d.e_dst + e); }
-    };
-    load_idx(0, es, ed);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int slot = t & 3;
-      const int cnt = min(kTE, p1 - (p0 + t * kTE));
-      load_idx(t + 1, es_n, ed_n);
-      // src-sorted list: equal sources are adjacent, so a run inside the tile shares one staged x_src row tile
-      const int prev = __shfl_up_sync(0xffffffffu, es, 1);
-      const bool valid = lane < cnt;
-      const bool starts = lane == 0 || !valid || es != prev;
-      const unsigned heads = __ballot_sync(0xffffffffu, starts);
-      const int ld = 31 - __clz(heads & ((2u << lane) - 1u));
-      const unsigned leaders = __ballot_sync(0xffffffffu, valid && ld == lane);
-      if (lane < kTE) { s.src[slot][lane] = es; s.dst[slot][lane] = ed; s.lead[slot][lane] = ld; }
-      if (lane < kTE && t + 1 < n_tiles && p0 + (t + 1) * kTE + lane < p1) {  // next tile's rows -> L2
-        tc::prefetch_l2(d.grad_x1 + (size_t)ed_n * kRow, kRow * 4u);
-        tc::prefetch_l2(d.x_src + (size_t)es_n * kRow, kRow * 4u);
-      }
-      if (t > 0) tc::mbar_wait(&s.xs_free, (uint32_t)(t - 1) & 1u);  // role C has multiplied tile t-1's x_src rows
-      if (cnt < kTE) {  // rows past the end of the list: zeros (they meet finite rows in the products)
-        for (int i = lane; i < (kTE - cnt) * kRow / 4; i += 32) {
-          reinterpret_cast<float4*>(s.XS + cnt * kRow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if (valid && ld == lane) {
-        tc::tma_load_2d(s.XS + (lane * 2 + 0) * 512, &tm_xs, 0, es * kO, &s.bar_g);
-        tc::tma_load_2d(s.XS + (lane * 2 + 1) * 512, &tm_xs, 32, es * kO, &s.bar_g);
-      }
-      if (t > 0) tc::mbar_wait(&s.gx_free, (uint32_t)(t - 1) & 1u);  // ... and summed its g_x1 * kern rows
-      if (cnt < kTE) {
-        for (int i = lane; i < (kTE - cnt) * kRow / 4; i += 32) {
-          reinterpret_cast<float4*>(s.GX + cnt * kRow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if (valid) {
-        tc::tma_load_2d(s.GX + (lane * 2 + 0) * 512, &tm_gx, 0, ed * kO, &s.bar_g);
-        tc::tma_load_2d(s.GX + (lane * 2 + 1) * 512, &tm_gx, 32, ed * kO, &s.bar_g);
-      }
-      __syncwarp();
-      // one arrival + the byte count: completes when every box has landed; release also publishes the ring slot
-      if (lane == 0) tc::mbar_expect_tx(&s.bar_g, (uint32_t)(cnt + __popc(leaders)) * kRow * 4u);
-      es = es_n; ed = ed_n;
-    }
-  } else if (role == 0) {
-    // =========================================== role R ===========================================================
-    RowPos pos;
-    int es_n = 0, ed_n = 0;
-    bool v_n = false;
-    auto load_ids = [&](int t_) {
-      const int e = p0 + t_ * kTE + (rt >> 4);
-      v_n = rt < kTM && t_ < n_tiles && e < p1;
-      if (v_n) { es_n = __ldg(d.e_src + e); ed_n = __ldg(d.e_dst + e); }
-    };
-    pos.valid = false;
-    load_ids(0);
-    pos.load(d, es_n, ed_n, v_n);
-    load_ids(1);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int b = t & 1;
-      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
-      const uint32_t fa = tc::smem_u32(s.F[b]), ha = tc::smem_u32(s.H1[b]);
-      const uint32_t kA = 128u * b, kB = 128u * b + 64u;
-      tc::mbar_wait(&s.empty[b], parb ^ 1u);  // role C is done with set b (tile t-2); passes at once for t < 2
-      tc::tc_fence_after();
-      if (rt < kTM) {
-        pos.emit(d, s.F[b], rt);
-        pos.load(d, es_n, ed_n, v_n);
-        load_ids(t + 2);
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(1, 256);
-      if (rt == 0) {  // pre1 = [F | 1 1] [W1 | b1]^T
-        tc::tc_fence_after();
-        tc::issue_mma(tmem + kA, tc::view_k(fa, kTM), tc::view_k(w1, kC), tc::idesc_bf16(128, kC), 1, false);
-        tc::mma_commit(&s.bar_r[0]);
-      }
-      tc::mbar_wait(&s.bar_r[0], par);
-      tc::tc_fence_after();
-#pragma unroll
-      for (int layer = 0; layer < 2; ++layer) {
-        __nv_bfloat16* img = layer == 0 ? s.H1[b] : s.BZ[b];
-        const uint32_t col = layer == 0 ? kA : kB;
-        if (layer == 1) {
-          tc::tmem_st_wait();
-          tc::fence_async_smem();
-          tc::tc_fence_before();
-          tc::group_sync(1, 256);
-          if (rt == 0) {  // pre2 = H1 W2^T
-            tc::tc_fence_after();
-            tc::issue_mma(tmem + kB, tc::view_k(ha, kTM), tc::view_k(w2, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-            tc::mma_commit(&s.bar_r[1]);
-          }
-          tc::mbar_wait(&s.bar_r[1], par);
-          tc::tc_fence_after();
-        }
-        uint32_t dpk[16];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16];
-          tc::tmem_ld16(lane_addr + col + c0, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float x0 = v[2 * e], x1 = v[2 * e + 1];
-            if (layer == 1) { x0 += s.b2[c0 + 2 * e]; x1 += s.b2[c0 + 2 * e + 1]; }
-            __half2 y, dy;
-            tc::gelu_h2(__floats2half2_rn(x0, x1), y, dy);
-            const float2 yf = __half22float2(y);
-            v[2 * e] = yf.x; v[2 * e + 1] = yf.y;
-            dpk[8 * i + e] = *reinterpret_cast<const uint32_t*>(&dy);
-          }
-          *reinterpret_cast<uint4*>(img + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-          *reinterpret_cast<uint4*>(img + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-        }
-        tc::tmem_st16(lane_addr + col + 32 * ch, dpk);  // packed GELU' over this thread's own (already read) columns
-      }
-      tc::tmem_st_wait();
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s.full[b]);
-    }
-  } else {
-    // =========================================== role C ===========================================================
-    const int o = rt >> 4, cg = rt & 15;  // mapping of the segmented-sum phase
-    int cur = n_lo;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t toff = (size_t)o * kC + 4 * cg;
-    // Residual rows (grad_x_src_init) of node `cur` and of node `cur + 1`: each is requested TWO flushes before it is
-    // added.  (ncu, first ws2 build: with the row requested at the previous flush, ~3 edges earlier, every flush stalled
-    // ~700 cycles on it: 18 % of role C's tile period.)
-    auto ld_init = [&](int node) {
-      return (d.grad_x_src_init && node < n_hi) ? ldg4(d.grad_x_src_init + (size_t)node * kRow + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    float4 init_cur = ld_init(cur), init_nxt = ld_init(cur + 1);
-    auto advance = [&](int to) {
-      sum.x += init_cur.x; sum.y += init_cur.y; sum.z += init_cur.z; sum.w += init_cur.w;
-      st4(d.grad_x_src + (size_t)cur * kRow + toff, sum);
-      sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      ++cur;
-      if (cur == to) {  // the usual case: the next node has edges too
-        if (kVariant & 2) {
-          init_cur = init_nxt;
-          init_nxt = ld_init(cur + 1);
-        } else {
-          init_cur = ld_init(cur);
-        }
-        return;
-      }
-      // a run of edge-less nodes [cur, to): their rows are the residual rows alone
-      if (cur < n_hi) st4(d.grad_x_src + (size_t)cur * kRow + toff, init_nxt);
-      ++cur;
-      while (cur < to) {
-        const int n = min(4, to - cur);
-        float4 r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = i < n ? ld_init(cur + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < n) st4(d.grad_x_src + (size_t)(cur + i) * kRow + toff, r[i]);
-        cur += n;
-      }
-      cur = to;
-      init_cur = ld_init(cur);
-      init_nxt = ld_init(cur + 1);
-    };
-    const int rj = row >> 4, ro = row & 15;
-
-    for (int t = 0; t < n_tiles; ++t) {
-      const int slot = t & 3, b = t & 1;
-      const uint32_t par = (uint32_t)t & 1u, parb = (uint32_t)(t >> 1) & 1u;
-      const int cnt = min(kTE, p1 - (p0 + t * kTE));
-      const bool acc = t > 0;
-      const uint32_t fa = tc::smem_u32(s.F[b]), ha = tc::smem_u32(s.H1[b]), bz = tc::smem_u32(s.BZ[b]);
-      const uint32_t ga = tc::smem_u32(s.G[b]), xa = ga - kTM * kC * 2;  // xa: the 16 KB in front of G[b]
-      __nv_bfloat16* G = s.G[b];
-      const uint32_t kA = 128u * b, kB = 128u * b + 64u;
-      if (t >= 2) {  // G[b] was last read by the [gW1 | gb1] MMA of tile t-2
-        tc::mbar_wait(&s.empty[b], parb ^ 1u);
-        tc::tc_fence_after();
-      }
-      tc::mbar_wait(&s.full[b], parb);  // role R has finished set b
-      tc::tc_fence_after();
-      if (rt == 0 && (t == 0 || !(kVariant & 1))) {  // kern = basis Wk^T  (for t > 0 it was issued at the end of tile t-1)
-        tc::issue_mma(tmem + kR2, tc::view_k(bz, kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-        tc::mma_commit(&s.bar_c[0]);
-      }
-      tc::mbar_wait(&s.bar_g, par);  // the producer's rows have landed; its ring slot is visible
-      tc::mbar_wait(&s.bar_c[0], par);
-      tc::tc_fence_after();
-      {
-        float* gxb = s.GX + (((rj * 2 + ch) * kO + ro) << 5);
-        const float* xsb = s.XS + (((s.lead[slot][rj] * 2 + ch) * kO + ro) << 5);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16], gkv[16];
-          tc::tmem_ld16(lane_addr + kR2 + c0, v);
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const int off = ((4 * i + e4) ^ (ro & 7)) << 2;
-            const float4 gm = ld4(gxb + off), x = ld4(xsb + off);
-            const int e = 4 * e4;
-            st4(gxb + off, make_float4(gm.x * v[e], gm.y * v[e + 1], gm.z * v[e + 2], gm.w * v[e + 3]));
-            gkv[e] = gm.x * x.x; gkv[e + 1] = gm.y * x.y; gkv[e + 2] = gm.z * x.z; gkv[e + 3] = gm.w * x.w;
-          }
-          *reinterpret_cast<uint4*>(G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gkv);
-          *reinterpret_cast<uint4*>(G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gkv + 8);
-        }
-      }
-      tc::fence_async_smem();
-      tc::mbar_arrive(&s.xs_free);  // this thread is done with the x_src tile
-      tc::tc_fence_before();
-      tc::group_sync(2, 256);  // (E)
-      if (rt == 0) {
-        tc::tc_fence_after();
-        tc::issue_mma(tmem + kR2, tc::view_k(ga, kTM), tc::view_mn(wk, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-        tc::issue_mma(tmem + kGWk, tc::view_mn(xa, kTM), tc::view_mn(bz, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
-        tc::mma_commit(&s.bar_c[1]);
-      }
-      // src-CSR segmented sum of g_x1 * kern while the tensor core works
-#pragma unroll
-      for (int j = 0; j < kTE; ++j) {
-        if (j < cnt) {
-          const int sn = s.src[slot][j];
-          if (cur < sn) advance(sn);
-          const float4 m = ld4(s.GX + swz_off(j, cg >> 3, o, cg & 7));
-          sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
-        }
-      }
-      tc::fence_async_smem();
-      tc::mbar_arrive(&s.gx_free);  // ... and with the g_x1 tile
-      tc::mbar_wait(&s.bar_c[1], par);
-      tc::tc_fence_after();
-      {
-        uint32_t dpk[16];
-        tc::tmem_ld16_raw(lane_addr + kB + 32 * ch, dpk);  // GELU'(pre2) of this thread's 32 columns, packed fp16 pairs
-        float gp2[32];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16];
-          tc::tmem_ld16(lane_addr + kR2 + c0, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 dg = __half22float2(*reinterpret_cast<const __half2*>(&dpk[8 * i + e]));
-            gp2[16 * i + 2 * e] = v[2 * e] * dg.x;
-            gp2[16 * i + 2 * e + 1] = v[2 * e + 1] * dg.y;
-          }
-          *reinterpret_cast<uint4*>(G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i);
-          *reinterpret_cast<uint4*>(G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(gp2 + 16 * i + 8);
-        }
-        tc::warp_colsum<32>(gp2, lane);
-        s.acc_gb2[q][32 * ch + lane] += gp2[0];
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(2, 256);  // (F)
-      if (rt == 0) {
-        tc::tc_fence_after();
-        tc::issue_mma(tmem + kR2, tc::view_k(ga, kTM), tc::view_mn(w2, kC), tc::idesc_bf16_ex(128, 64, 0, 1), kC / 16, false);
-        tc::issue_mma(tmem + kGW2, tc::view_mn(xa, kTM), tc::view_mn(ha, kTM), tc::idesc_bf16_ex(128, 64, 1, 1), kTM / 16, acc);
-        tc::mma_commit(&s.bar_c[2]);
-      }
-      tc::mbar_wait(&s.bar_c[2], par);
-      tc::tc_fence_after();
-      {
-        uint32_t dpk[16];
-        tc::tmem_ld16_raw(lane_addr + kA + 32 * ch, dpk);  // GELU'(pre1)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = 32 * ch + 16 * i;
-          float v[16];
-          tc::tmem_ld16(lane_addr + kR2 + c0, v);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 dg = __half22float2(*reinterpret_cast<const __half2*>(&dpk[8 * i + e]));
-            v[2 * e] *= dg.x;
-            v[2 * e + 1] *= dg.y;
-          }
-          *reinterpret_cast<uint4*>(G + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack8(v);
-          *reinterpret_cast<uint4*>(G + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack8(v + 8);
-        }
-      }
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      tc::group_sync(2, 256);  // (G)
-      if (rt == 0) {
-        tc::tc_fence_after();
-        // [gW1 | gb1] += gP1^T [F | 1 1]; its completion frees operand set b (role R) and G[b] (tile t+2)
-        tc::issue_mma(tmem + kGW1, tc::view_mn(xa, kTM), tc::view_mn(fa, kTM), tc::idesc_bf16_ex(128, 16, 1, 1), kTM / 16, acc);
-        tc::mma_commit(&s.empty[b]);
-        if ((kVariant & 1) && t + 1 < n_tiles) {
-          // kern of tile t+1 right behind it (kR2 is free: every thread has read gH1), so that its round trip runs
-          // under the start of the next tile instead of in front of the message products
-          tc::mbar_wait(&s.full[b ^ 1], (uint32_t)((t + 1) >> 1) & 1u);
-          tc::tc_fence_after();
-          tc::issue_mma(tmem + kR2, tc::view_k(tc::smem_u32(s.BZ[b ^ 1]), kTM), tc::view_k(wk, kC), tc::idesc_bf16(128, kC), kC / 16, false);
-          tc::mma_commit(&s.bar_c[0]);
-        }
-      }
-    }
-    for (int t = max(0, n_tiles - 2); t < n_tiles; ++t) {  // the last MMAs on both operand sets
-      tc::mbar_wait(&s.empty[t & 1], (uint32_t)(t >> 1) & 1u);
-    }
-    tc::tc_fence_after();
-    if (cur < n_hi) advance(n_hi);
-  }
-  // partial slot of this CTA: gWk[64][64] | gW1b[64][16] (columns 14, 15 = gb1) | gW2[64][64] | gb2[64]
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  float* P = d.grad_partials + (size_t)blockIdx.x * GRL_FUSED_EDGE_GRAD_FLOATS;
-  if (warp < 16) {
-    const int q4 = warp & 3, cq = warp >> 2, row4 = 32 * q4 + lane, c0 = 16 * cq;  // 16 warps: 16 columns per thread
-    const uint32_t la = tmem + ((uint32_t)(32 * q4) << 16);
-    float v[16];
-    auto read = [&](uint32_t col) {
-      if (n_tiles > 0) {
-        tc::tmem_ld16(la + col, v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.f;
-      }
-    };
-    read(kGWk + c0);
-    if (row4 >= 64) {
-      float* p = P + (size_t)(row4 - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-    read(kGW2 + c0);
-    if (row4 >= 64) {
-      float* p = P + kWFloats + 64 * 16 + (size_t)(row4 - 64) * kC + c0;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-    read(kGW1);
-    if (row4 >= 64 && cq == 0) {
-      float* p = P + kWFloats + (size_t)(row4 - 64) * 16;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4) st4(p + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
-    }
-  }
-  if (tid < kC)
-    P[2 * kWFloats + 64 * 16 + tid] = ((s.acc_gb2[0][tid] + s.acc_gb2[1][tid]) + s.acc_gb2[2][tid]) + s.acc_gb2[3][tid];
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
 // ---------------------------------------------------------------------------------------------------
-// backward, third generation: a four-stage pipeline inside one CTA per SM (the product path).
-// ncu on the second generation (profiles/r02_fused_bwd_ws2.md): role R still idles > 50 % of the time; role C's tile period
-// (10.6 k cycles) is a serial chain of FOUR tensor-core round trips (kern -> products -> g_basis -> gP2 -> gH1 -> gP1) that
-// no amount of prefetching shortens.  The chain is therefore cut in two roles that work on consecutive tiles:
-//   producer (warp 20)  index stream + TMA row gathers, one tile ahead                              (as in ws2)
-//   role R  (warps 0..7)   features -> pre1 -> H1, GELU' -> pre2 -> basis, GELU'      into operand set t & 1
+// backward: a four-stage pipeline inside one CTA per SM.
+// A tile's work is a serial chain of tensor-core round trips (pre1 -> pre2 -> kern -> products -> g_basis -> gP2 -> gH1 -> gP1)
+// that no prefetching shortens (the lock-step and two-role generations of this kernel spent 16 k and 10.6 k cycles per tile in
+// it: profiles/r02_*).  The chain is therefore cut into roles that work on consecutive tiles:
+//   producer (warp 24)  owns the index stream and the row gathers, one tile ahead.  Rows arrive through tensor maps
+//                          (cp.async.bulk.tensor.2d, SASS UTMALDG): one 16-row x 32-channel box per (edge, channel half),
+//                          128-byte swizzled, so the row tiles need no padding; (src, dst, leader) of the tile are published
+//                          under the same transaction barrier as the data
+//   role R  (warps 0..7)   features -> pre1 -> H1, GELU' -> pre2 -> basis, GELU' (packed fp16)   into operand set t & 1
 //   role C1 (warps 8..15)  kern MMA, message products (g_x1 * kern in place, g_kern image), issues the g_basis / gWk
 //                          MMAs, src-CSR segmented sum -> grad_x_src
-//   role C2 (warps 16..19) gP2 = g_basis * GELU'(pre2), gb2, issues the gH1 / gW2 MMAs, gP1 = gH1 * GELU'(pre1), issues
+//   role C2 (warps 16..23) gP2 = g_basis * GELU'(pre2), gb2, issues the gH1 / gW2 MMAs, gP1 = gH1 * GELU'(pre1), issues
 //                          the [gW1 | gb1] MMA whose commit frees the operand set
 // TMEM (464 columns): one 64-column scratch for pre1 / pre2 (role R works on one tile at a time), 64 columns per operand
 // set for the two packed fp16 derivative planes, 64 for kern (C1), 64 for g_basis / gH1 (C2), 144 for the weight gradients.
@@ -2024,48 +829,14 @@ int grl_fbconv_edge_fused_bwd(const GrlFusedEdgeDesc* d, grl_stream_t stream) {
   GRL_REQUIRE(d->n_partials > 0 && d->n_partials <= d->n_key, GRL_EINVAL,
               "grl_fbconv_edge_fused_bwd: n_partials=%d must be in [1, n_key]", d->n_partials);
   GRL_REQUIRE(d->n_other > 0, GRL_EINVAL, "grl_fbconv_edge_fused_bwd: n_other=%d (rows of grad_x1) must be set", d->n_other);
-  // GRL_FUSED_BWD=lockstep | ws1 | ws2 select the earlier generations (kept as parity partners and for the profiles);
-  // default (ws3): producer warp + three decoupled roles
-  static const int gen = [] {
-    const char* e = getenv("GRL_FUSED_BWD");
-    if (!e) return 3;
-    if (e[0] == 'l') return 0;
-    return e[0] == 'w' && e[1] == 's' && e[2] >= '1' && e[2] <= '3' ? e[2] - '0' : 3;
-  }();
-  if (gen == 3) {
-    alignas(64) CUtensorMap tm_gx, tm_xs, tm_in;
-    if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
-    if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
-    // residual rows (optional): an unused map over x_src keeps the kernel signature fixed when there are none
-    if (grl::make_row_tensor_map(&tm_in, d->grad_x_src_init ? d->grad_x_src_init : d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
-    const int smem = (int)sizeof(grl::FusedBwdWs3Smem) + 1024;
-    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws3_kernel, smem) != GRL_OK) return GRL_ECUDA;
-    grl::edge_fused_bwd_ws3_kernel<<<d->n_partials, grl::kWs3Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs, tm_in);
-  } else if (gen == 2) {
-    alignas(64) CUtensorMap tm_gx, tm_xs;
-    if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
-    if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
-    const int smem = (int)sizeof(grl::FusedBwdWs2Smem) + 1024;
-    static const int variant = [] { const char* e = getenv("GRL_WS2_VARIANT"); return e ? atoi(e) & 3 : 0; }();
-#define GRL_WS2_LAUNCH(V)                                                                                              \
-  do {                                                                                                                 \
-    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws2_kernel<V>, smem) != GRL_OK) return GRL_ECUDA;    \
-    grl::edge_fused_bwd_ws2_kernel<V><<<d->n_partials, grl::kWs2Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs); \
-  } while (0)
-    if (variant == 0) GRL_WS2_LAUNCH(0);
-    else if (variant == 1) GRL_WS2_LAUNCH(1);
-    else if (variant == 2) GRL_WS2_LAUNCH(2);
-    else GRL_WS2_LAUNCH(3);
-#undef GRL_WS2_LAUNCH
-  } else if (gen == 0) {
-    const int smem = (int)sizeof(grl::FusedBwdSmem);
-    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
-    grl::edge_fused_bwd_kernel<<<d->n_partials, grl::kFusedBwdThreads, smem, (cudaStream_t)stream>>>(*d);
-  } else {
-    const int smem = (int)sizeof(grl::FusedBwdWsSmem);
-    if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws_kernel, smem) != GRL_OK) return GRL_ECUDA;
-    grl::edge_fused_bwd_ws_kernel<<<d->n_partials, grl::kFusedBwdThreads, smem, (cudaStream_t)stream>>>(*d);
-  }
+  alignas(64) CUtensorMap tm_gx, tm_xs, tm_in;
+  if (grl::make_row_tensor_map(&tm_gx, d->grad_x1, d->n_other) != GRL_OK) return GRL_ECUDA;
+  if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
+  // residual rows (optional): an unused map over x_src keeps the kernel signature fixed when there are none
+  if (grl::make_row_tensor_map(&tm_in, d->grad_x_src_init ? d->grad_x_src_init : d->x_src, d->n_key) != GRL_OK) return GRL_ECUDA;
+  const int smem = (int)sizeof(grl::FusedBwdWs3Smem) + 1024;
+  if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_bwd_ws3_kernel, smem) != GRL_OK) return GRL_ECUDA;
+  grl::edge_fused_bwd_ws3_kernel<<<d->n_partials, grl::kWs3Threads, smem, (cudaStream_t)stream>>>(*d, tm_gx, tm_xs, tm_in);
   return grl::check_launch("grl_fbconv_edge_fused_bwd");
 }
 
