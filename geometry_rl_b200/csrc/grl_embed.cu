@@ -49,16 +49,24 @@ __device__ __forceinline__ void embed_features(const GrlEmbedDesc& d, const floa
   for (int i = 0; i < kMaxF; i += 4) st4(dst + i, make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]));
 }
 
-__global__ void __launch_bounds__(kThreads, 2) embed_fwd_kernel(const GrlEmbedDesc d) {
+// FQ = ceil((S + V) / 4): the feature count is a launch constant, so the weight slice of a thread is FQ * 16 registers
+// (HEPi: 7 features -> 32 registers -> four CTAs per SM instead of two).  The channel pairs of a thread ride in packed
+// FFMA2 (two fused multiply-adds per fma-pipe issue slot, each lane rounded like fmaf).
+template <int FQ>
+__global__ void __launch_bounds__(kThreads, FQ <= 2 ? 4 : 2) embed_fwd_kernel(const GrlEmbedDesc d) {
   __shared__ __align__(16) float feat[kEmbTile * kO * kMaxF];
   __shared__ float sc[kEmbTile * kMaxF], vc[kEmbTile * kMaxF * 3];
   const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
-  const int F = d.n_scalars + d.n_vectors, Fq = (F + 3) >> 2;
-  float w[kMaxF][4];  // w[f][i] = W[4 cg + i][f]
+  const int F = d.n_scalars + d.n_vectors;
+  unsigned long long w01[4 * FQ], w23[4 * FQ];  // (W[4 cg][f], W[4 cg + 1][f]), (W[4 cg + 2][f], W[4 cg + 3][f])
 #pragma unroll
-  for (int f = 0; f < kMaxF; ++f)
+  for (int f = 0; f < 4 * FQ; ++f) {
+    float w[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w[f][i] = (f < F) ? __ldg(d.weight + (size_t)(4 * cg + i) * F + f) : 0.f;
+    for (int i = 0; i < 4; ++i) w[i] = (f < F) ? __ldg(d.weight + (size_t)(4 * cg + i) * F + f) : 0.f;
+    w01[f] = pack2(w[0], w[1]);
+    w23[f] = pack2(w[2], w[3]);
+  }
   const int n_tiles = (d.n_nodes + kEmbTile - 1) / kEmbTile;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int n0 = t * kEmbTile, cnt = min(kEmbTile, d.n_nodes - n0);
@@ -70,35 +78,36 @@ __global__ void __launch_bounds__(kThreads, 2) embed_fwd_kernel(const GrlEmbedDe
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
       const float* fr = feat + (j * kO + o) * kMaxF;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned long long a01 = pack2(0.f, 0.f), a23 = a01;
 #pragma unroll
-      for (int qd = 0; qd < kMaxF / 4; ++qd) {
-        if (qd < Fq) {
-          const float4 fv = ld4(fr + 4 * qd);
-          const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
+      for (int qd = 0; qd < FQ; ++qd) {
+        const float4 fv = ld4(fr + 4 * qd);
+        const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            a.x = fmaf(fe[e], w[4 * qd + e][0], a.x);
-            a.y = fmaf(fe[e], w[4 * qd + e][1], a.y);
-            a.z = fmaf(fe[e], w[4 * qd + e][2], a.z);
-            a.w = fmaf(fe[e], w[4 * qd + e][3], a.w);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const unsigned long long ff = pack2(fe[e], fe[e]);
+          a01 = ffma2(ff, w01[4 * qd + e], a01);
+          a23 = ffma2(ff, w23[4 * qd + e], a23);
         }
       }
+      float4 a;
+      unpack2(a01, a.x, a.y);
+      unpack2(a23, a.z, a.w);
       st4(d.x + (size_t)(n0 + j) * kRow + o * kC + 4 * cg, a);
     }
   }
 }
 
 // gW[c][f] = sum_{n,o} grad_x[n][o][c] feat[n][o][f]; per-CTA partial, cross-o reduction through smem.
-__global__ void __launch_bounds__(kThreads, 2) embed_bwd_kernel(const GrlEmbedDesc d) {
+template <int FQ>
+__global__ void __launch_bounds__(kThreads, FQ <= 2 ? 4 : 2) embed_bwd_kernel(const GrlEmbedDesc d) {
   __shared__ __align__(16) float feat[kEmbTile * kO * kMaxF];  // re-used as the reduction buffer at the end
   __shared__ float sc[kEmbTile * kMaxF], vc[kEmbTile * kMaxF * 3];
   const int tid = threadIdx.x, o = tid >> 4, cg = tid & 15;
-  const int F = d.n_scalars + d.n_vectors, Fq = (F + 3) >> 2;
-  float g[kMaxF][4];
+  const int F = d.n_scalars + d.n_vectors;
+  unsigned long long g01[4 * FQ], g23[4 * FQ];
 #pragma unroll
-  for (int f = 0; f < kMaxF; ++f) g[f][0] = g[f][1] = g[f][2] = g[f][3] = 0.f;
+  for (int f = 0; f < 4 * FQ; ++f) g01[f] = g23[f] = pack2(0.f, 0.f);
   const int n_tiles = (d.n_nodes + kEmbTile - 1) / kEmbTile;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int n0 = t * kEmbTile, cnt = min(kEmbTile, d.n_nodes - n0);
@@ -107,22 +116,20 @@ __global__ void __launch_bounds__(kThreads, 2) embed_bwd_kernel(const GrlEmbedDe
     __syncthreads();
     embed_features(d, sc, vc, cnt, feat);
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < cnt; ++j) {
       const float4 gx = ldg4(d.grad_x + (size_t)(n0 + j) * kRow + o * kC + 4 * cg);
+      const unsigned long long gx01 = pack2(gx.x, gx.y), gx23 = pack2(gx.z, gx.w);
       const float* fr = feat + (j * kO + o) * kMaxF;
 #pragma unroll
-      for (int qd = 0; qd < kMaxF / 4; ++qd) {
-        if (qd < Fq) {
-          const float4 fv = ld4(fr + 4 * qd);
-          const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
+      for (int qd = 0; qd < FQ; ++qd) {
+        const float4 fv = ld4(fr + 4 * qd);
+        const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            g[4 * qd + e][0] = fmaf(gx.x, fe[e], g[4 * qd + e][0]);
-            g[4 * qd + e][1] = fmaf(gx.y, fe[e], g[4 * qd + e][1]);
-            g[4 * qd + e][2] = fmaf(gx.z, fe[e], g[4 * qd + e][2]);
-            g[4 * qd + e][3] = fmaf(gx.w, fe[e], g[4 * qd + e][3]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          const unsigned long long ff = pack2(fe[e], fe[e]);
+          g01[4 * qd + e] = ffma2(gx01, ff, g01[4 * qd + e]);
+          g23[4 * qd + e] = ffma2(gx23, ff, g23[4 * qd + e]);
         }
       }
     }
@@ -130,10 +137,13 @@ __global__ void __launch_bounds__(kThreads, 2) embed_bwd_kernel(const GrlEmbedDe
   float* P = d.grad_weight_partials + (size_t)blockIdx.x * kC * F;
   float* red = feat;  // [16 o][64 c]
 #pragma unroll
-  for (int f = 0; f < kMaxF; ++f) {
+  for (int f = 0; f < 4 * FQ; ++f) {
     if (f < F) {
+      float4 g;
+      unpack2(g01[f], g.x, g.y);
+      unpack2(g23[f], g.z, g.w);
       __syncthreads();
-      st4(red + o * kC + 4 * cg, make_float4(g[f][0], g[f][1], g[f][2], g[f][3]));
+      st4(red + o * kC + 4 * cg, g);
       __syncthreads();
       if (tid < kC) {
         float t = 0.f;
@@ -165,9 +175,14 @@ int grl_embed_fwd(const GrlEmbedDesc* d, grl_stream_t stream) {
   if (rc != GRL_OK) return rc;
   GRL_REQUIRE(d->weight && d->x, GRL_EINVAL, "grl_embed_fwd: null pointer");
   const int n_tiles = (d->n_nodes + grl::kEmbTile - 1) / grl::kEmbTile;
-  int grid = 6 * grl::sm_count();
+  const int fq = (d->n_scalars + d->n_vectors + 3) / 4;
+  int grid = (fq <= 2 ? 8 : 6) * grl::sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  grl::embed_fwd_kernel<<<grid, grl::kThreads, 0, (cudaStream_t)stream>>>(*d);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fq == 1) grl::embed_fwd_kernel<1><<<grid, grl::kThreads, 0, st>>>(*d);
+  else if (fq == 2) grl::embed_fwd_kernel<2><<<grid, grl::kThreads, 0, st>>>(*d);
+  else if (fq == 3) grl::embed_fwd_kernel<3><<<grid, grl::kThreads, 0, st>>>(*d);
+  else grl::embed_fwd_kernel<4><<<grid, grl::kThreads, 0, st>>>(*d);
   return grl::check_launch("grl_embed_fwd");
 }
 
@@ -175,7 +190,12 @@ int grl_embed_bwd(const GrlEmbedDesc* d, grl_stream_t stream) {
   const int rc = check_embed(d, "grl_embed_bwd");
   if (rc != GRL_OK) return rc;
   GRL_REQUIRE(d->grad_x && d->grad_weight_partials && d->n_partials > 0, GRL_EINVAL, "grl_embed_bwd: null pointer");
-  grl::embed_bwd_kernel<<<d->n_partials, grl::kThreads, 0, (cudaStream_t)stream>>>(*d);
+  const int fq = (d->n_scalars + d->n_vectors + 3) / 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fq == 1) grl::embed_bwd_kernel<1><<<d->n_partials, grl::kThreads, 0, st>>>(*d);
+  else if (fq == 2) grl::embed_bwd_kernel<2><<<d->n_partials, grl::kThreads, 0, st>>>(*d);
+  else if (fq == 3) grl::embed_bwd_kernel<3><<<d->n_partials, grl::kThreads, 0, st>>>(*d);
+  else grl::embed_bwd_kernel<4><<<d->n_partials, grl::kThreads, 0, st>>>(*d);
   return grl::check_launch("grl_embed_bwd");
 }
 

@@ -270,7 +270,7 @@ class EmbedFn(torch.autograd.Function):
         scalars, vectors, ori3 = ctx.saved_tensors
         N, S, V, dim = ctx.meta
         gx = _f32c(gx)
-        n_p = _n_partials((N + 15) // 16, 2)
+        n_p = _n_partials((N + 15) // 16, 4 if S + V <= 8 else 2)  # resident CTAs per SM of grl_embed_bwd
         partials = torch.empty(n_p, 64 * (S + V), dtype=torch.float32, device=gx.device)
         d = L.GrlEmbedDesc(n_nodes=N, n_scalars=S, n_vectors=V, dim=dim, scalars=L.ptr(scalars), vectors=L.ptr(vectors),
                            ori=L.ptr(ori3), grad_x=L.ptr(gx), grad_weight_partials=L.ptr(partials), n_partials=n_p,
