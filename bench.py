@@ -39,7 +39,8 @@ DEFAULT_MINIBATCH = {"rigid_insertion_multi_hepi_trpl_cfg": 8192, "rigid_pushing
                      "cloth_hanging_multi_hepi_trpl_cfg": 8192, "rope_shaping_hepi_trpl_cfg": 2048}
 # workloads reported under "configs" next to the headline: (config, samples per GPU per step)
 SIDE_WORKLOADS = [("rigid_insertion_multi_hepi_trpl_cfg", 1000), ("rigid_pushing_multi_empn_trpl_cfg", 4096),
-                  ("cloth_hanging_multi_hepi_trpl_cfg", 8192), ("rope_shaping_hepi_trpl_cfg", 2048)]
+                  ("cloth_hanging_multi_hepi_trpl_cfg", 8192), ("rope_shaping_hepi_trpl_cfg", 2048),
+                  ("rigid_insertion_two_agents_multi_transformer_trpl_cfg", 1000)]
 MIN_TIMED_STEPS = 200  # the K-step timed region is repeated until at least this many steps were timed; median region reported
 METRIC = "fwd+bwd+TRPL update samples/sec (policy fwd+bwd, TRPL projection, losses, critic, Adam)"  # BASELINE.json metric
 N_ROTATE = 8  # distinct minibatches cycled through the timed region

@@ -54,6 +54,18 @@ class GrlFusedEdgeDesc(C.Structure):
                 ("grad_x1", _fp), ("grad_x_src", _fp), ("grad_x_src_init", _fp), ("grad_partials", _fp), ("n_other", _i32)]
 
 
+class GrlEncoderDesc(C.Structure):
+    _fields_ = [("n_graphs", _i32), ("n_tokens", _i32), ("n_partials", _i32), ("x", _fp), ("in_proj_weight", _fp),
+                ("in_proj_bias", _fp), ("out_proj_weight", _fp), ("out_proj_bias", _fp), ("linear1_weight", _fp),
+                ("linear1_bias", _fp), ("linear2_weight", _fp), ("linear2_bias", _fp), ("norm1_weight", _fp),
+                ("norm1_bias", _fp), ("norm2_weight", _fp), ("norm2_bias", _fp), ("out", _fp), ("grad_out", _fp),
+                ("grad_x", _fp), ("grad_partials", _fp)]
+
+
+ENCODER_MAX_TOKENS = 56
+ENCODER_GRAD_FLOATS = 192 * 64 + 192 + 3 * (64 * 64 + 64) + 4 * 64
+
+
 class GrlCriticDesc(C.Structure):
     _fields_ = [("n_graphs", _i32), ("n_tokens", _i32), ("n_feat", _i32), ("n_partials", _i32), ("eps", C.c_float),
                 ("count", C.c_double), ("x", _fp), ("w1", _fp), ("b1", _fp), ("gamma", _fp), ("beta", _fp), ("stats", _fp),
@@ -126,6 +138,8 @@ SIGNATURES = {
     "grl_critic_inner_fwd": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
     "grl_critic_inner_bwd_stats": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
     "grl_critic_inner_bwd": (C.c_int, [C.POINTER(GrlCriticDesc), _fp]),
+    "grl_encoder_layer_fwd": (C.c_int, [C.POINTER(GrlEncoderDesc), _fp]),
+    "grl_encoder_layer_bwd": (C.c_int, [C.POINTER(GrlEncoderDesc), _fp]),
     "grl_readout_fwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_readout_bwd": (C.c_int, [C.POINTER(GrlReadoutDesc), _fp]),
     "grl_trpl_loss_fwd": (C.c_int, [C.POINTER(GrlLossDesc), _fp]),

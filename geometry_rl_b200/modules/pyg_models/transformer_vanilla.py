@@ -1,11 +1,13 @@
-"""Transformer baseline policy body: drop-in for geometry_rl/modules/pyg_models/transformer_vanilla.py.
-A 2-layer post-LN nn.TransformerEncoder over <= ~100 tokens is latency-bound library work (SURVEY 8(d),
-row M6); it runs on torch's CUDA kernels, the trust-region / GAE kernels around it are ours."""
+"""Transformer baseline policy body: drop-in for geometry_rl/modules/pyg_models/transformer_vanilla.py (same class
+name, constructor, parameter names).  The 2-layer post-LN encoder over the <= 56 tokens of a graph runs as ONE kernel per
+layer and direction (grl_encoder_layer_fwd / _bwd, K5) on batch-major tokens; options the shipped config never selects
+(active dropout, concat_global, other widths) take the nn.TransformerEncoder path on torch's kernels."""
 from typing import Dict
 
 import torch
 from torch import nn
 
+from ... import ops
 from .pyg_compat import MLP
 
 
@@ -46,5 +48,12 @@ class TransformerVanilla(nn.Module):
             h = h[:, slice(mask.start + 1, mask.stop + 1)]
             h = torch.cat([cls.expand(-1, h.shape[1], -1), h], dim=-1)
         else:
-            h = self.transformer_encoder(x.permute(1, 0, 2)).permute(1, 0, 2)[:, mask]
+            layers = self.transformer_encoder.layers
+            if self.transformer_encoder.norm is None and all(ops.encoder_layer_supported(x, l) for l in layers):
+                h = x
+                for l in layers:
+                    h = ops.encoder_layer(h, l)
+                h = h[:, mask]
+            else:
+                h = self.transformer_encoder(x.permute(1, 0, 2)).permute(1, 0, 2)[:, mask]
         return self.fc_out(h.reshape(-1, h.shape[-1]))

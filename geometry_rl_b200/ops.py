@@ -706,6 +706,79 @@ def critic_inner(x, w1, b1, gamma, beta, eps, all_reduce=None, world_size=1):
 # ------------------------------------------------------------------------------------------------
 # K3: GAE
 # ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# K5: transformer encoder layer (M6 baseline)
+# ------------------------------------------------------------------------------------------------
+ENCODER_MAX_TOKENS = L.ENCODER_MAX_TOKENS
+
+
+class EncoderLayerFn(torch.autograd.Function):
+    """x [B,S,64] -> nn.TransformerEncoderLayer(64, 2, 64, dropout 0, post-LN, ReLU)(x) with the module's own parameter
+    tensors (transformer_vanilla.py:30-36): one kernel forward, one backward (recomputes from x)."""
+
+    @staticmethod
+    def forward(ctx, x, in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b):
+        x = _f32c(x)
+        B, S, D = x.shape
+        assert D == 64 and tuple(in_w.shape) == (192, 64) and tuple(w1.shape) == (64, 64) and tuple(w2.shape) == (64, 64)
+        params = [_f32c(t.detach()) for t in (in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b)]
+        out = torch.empty_like(x)
+        d = EncoderLayerFn._desc(x, params, B, S)
+        d.out = L.ptr(out)
+        L.call("grl_encoder_layer_fwd", C.byref(d), shape=(B * S, B * S, 0))
+        ctx.save_for_backward(x, *params)
+        return out
+
+    @staticmethod
+    def _desc(x, p, B, S):
+        return L.GrlEncoderDesc(n_graphs=B, n_tokens=S, n_partials=0, x=L.ptr(x), in_proj_weight=L.ptr(p[0]),
+                                in_proj_bias=L.ptr(p[1]), out_proj_weight=L.ptr(p[2]), out_proj_bias=L.ptr(p[3]),
+                                linear1_weight=L.ptr(p[4]), linear1_bias=L.ptr(p[5]), linear2_weight=L.ptr(p[6]),
+                                linear2_bias=L.ptr(p[7]), norm1_weight=L.ptr(p[8]), norm1_bias=L.ptr(p[9]),
+                                norm2_weight=L.ptr(p[10]), norm2_bias=L.ptr(p[11]))
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, *params = ctx.saved_tensors
+        B, S, _ = x.shape
+        g_out = _f32c(g_out)
+        g_x = torch.empty_like(x)
+        n_p = _n_partials(B)
+        part = torch.empty(n_p, L.ENCODER_GRAD_FLOATS, dtype=torch.float32, device=x.device)
+        d = EncoderLayerFn._desc(x, params, B, S)
+        d.n_partials, d.grad_out, d.grad_x, d.grad_partials = n_p, L.ptr(g_out), L.ptr(g_x), L.ptr(part)
+        L.call("grl_encoder_layer_bwd", C.byref(d), shape=(B * S, B * S, 0))
+        g = _reduce(part)
+        o = 0
+        grads = []
+        for shape in ((192, 64), (192,), (64, 64), (64,), (64, 64), (64,), (64, 64), (64,), (64,), (64,), (64,), (64,)):
+            n = 1
+            for v in shape:
+                n *= v
+            grads.append(g[o:o + n].view(*shape))
+            o += n
+        return (g_x, *grads)
+
+
+def encoder_layer(x: torch.Tensor, layer: "torch.nn.TransformerEncoderLayer") -> torch.Tensor:
+    """`layer(x.transpose(0, 1)).transpose(0, 1)` for a batch-major x [B,S,64]."""
+    a = layer.self_attn
+    return EncoderLayerFn.apply(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, layer.linear1.weight,
+                                layer.linear1.bias, layer.linear2.weight, layer.linear2.bias, layer.norm1.weight,
+                                layer.norm1.bias, layer.norm2.weight, layer.norm2.bias)
+
+
+def encoder_layer_supported(x: torch.Tensor, layer) -> bool:
+    """The kernel covers what the shipped transformer config builds (transformer.yaml + transformer_vanilla.py:30-36):
+    width 64, 2 heads, feed-forward 64, ReLU, post-LN, no active dropout, at most ENCODER_MAX_TOKENS tokens per graph."""
+    a = layer.self_attn
+    drop = layer.training and (layer.dropout.p > 0 or layer.dropout1.p > 0 or layer.dropout2.p > 0 or a.dropout > 0)
+    return (x.is_cuda and x.dim() == 3 and x.shape[-1] == 64 and x.shape[1] <= ENCODER_MAX_TOKENS and a.embed_dim == 64
+            and a.num_heads == 2 and a.in_proj_weight is not None and layer.linear1.out_features == 64
+            and not layer.norm_first and layer.activation is torch.nn.functional.relu and not drop
+            and layer.norm1.eps == 1e-5 and layer.norm2.eps == 1e-5)
+
+
 def gae(reward, value_T1, done, terminated, gamma: float, lmbda: float):
     """reward/done/terminated [B,T], value_T1 [B,T+1] -> (advantage, value_target) [B,T]."""
     reward, value_T1 = _f32c(reward), _f32c(value_T1)

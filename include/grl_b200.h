@@ -317,6 +317,41 @@ int grl_readout_fwd(const GrlReadoutDesc* d, grl_stream_t stream);
 int grl_readout_bwd(const GrlReadoutDesc* d, grl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5  One post-LN transformer encoder layer over the tokens of a graph (transformer baseline, M6): replaces the
+ * nn.TransformerEncoderLayer(d_model = 64, nhead = 2, dim_feedforward = 64, dropout = 0, ReLU) call of
+ * modules/pyg_models/transformer_vanilla.py:30-36,76-92 — ~30 library launches per layer and direction (in/out
+ * projections, batched QK^T, softmax, PV, two LayerNorms, the feed-forward pair, residual adds) — by one kernel per
+ * direction.  Tokens are batch-major [n_graphs][n_tokens][64]; parameters in torch's layouts.  The backward
+ * recomputes the layer's forward from x and leaves the parameter gradients in one partial slot per CTA.
+ * ------------------------------------------------------------------------------------------ */
+#define GRL_ENCODER_MAX_TOKENS 56
+/* partial layout: gWqkv[192][64] | gbqkv[192] | gWo[64][64] | gbo[64] | gW1[64][64] | gb1[64] | gW2[64][64] | gb2[64] |
+ *                 g_norm1.weight[64] | g_norm1.bias[64] | g_norm2.weight[64] | g_norm2.bias[64]                        */
+#define GRL_ENCODER_GRAD_FLOATS (192 * 64 + 192 + 3 * (64 * 64 + 64) + 4 * 64)
+typedef struct {
+  int32_t n_graphs, n_tokens, n_partials;
+  const float* x;                /* [n_graphs][n_tokens][64] layer input                                          */
+  const float* in_proj_weight;   /* [192][64] self_attn.in_proj_weight (q | k | v rows)                           */
+  const float* in_proj_bias;     /* [192]                                                                         */
+  const float* out_proj_weight;  /* [64][64]  self_attn.out_proj.weight                                           */
+  const float* out_proj_bias;    /* [64]                                                                          */
+  const float* linear1_weight;   /* [64][64]                                                                      */
+  const float* linear1_bias;     /* [64]                                                                          */
+  const float* linear2_weight;   /* [64][64]                                                                      */
+  const float* linear2_bias;     /* [64]                                                                          */
+  const float* norm1_weight;     /* [64]                                                                          */
+  const float* norm1_bias;
+  const float* norm2_weight;
+  const float* norm2_bias;
+  float* out;                    /* forward out: [n_graphs][n_tokens][64]                                         */
+  const float* grad_out;         /* backward in                                                                   */
+  float* grad_x;                 /* backward out                                                                  */
+  float* grad_partials;          /* [n_partials][GRL_ENCODER_GRAD_FLOATS]; the backward launches n_partials CTAs   */
+} GrlEncoderDesc;
+int grl_encoder_layer_fwd(const GrlEncoderDesc* d, grl_stream_t stream);
+int grl_encoder_layer_bwd(const GrlEncoderDesc* d, grl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K3  GAE: replaces torchrl.objectives.value.GAE(...)(data) at examples/torchrl/train.py:134-140,
  * 249-252 (the advantage arithmetic; the critic call stays with the caller).
  * reward/done/terminated [B][T], value [B][T+1] (shifted=True layout) -> adv, value_target [B][T].

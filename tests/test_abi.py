@@ -41,7 +41,8 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_layouts_match_the_c_compiler(lib):
     structs = {"GrlEmbedDesc": lib.GrlEmbedDesc, "GrlBasisDesc": lib.GrlBasisDesc, "GrlConvDesc": lib.GrlConvDesc,
                "GrlProjDesc": lib.GrlProjDesc, "GrlLossDesc": lib.GrlLossDesc, "GrlReadoutDesc": lib.GrlReadoutDesc,
-               "GrlFusedEdgeDesc": lib.GrlFusedEdgeDesc, "GrlCriticDesc": lib.GrlCriticDesc}
+               "GrlFusedEdgeDesc": lib.GrlFusedEdgeDesc, "GrlCriticDesc": lib.GrlCriticDesc,
+               "GrlEncoderDesc": lib.GrlEncoderDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for name, cls in structs.items():
         lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
