@@ -119,10 +119,16 @@ __device__ __forceinline__ void stage_w1_b1_b2(__nv_bfloat16* __restrict__ img, 
 // ---------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------
+// float offset of the 16-byte chunk k (channels 4k..4k+3 of the half) of row (entry j, orientation o) in a swizzled row tile
+__device__ __forceinline__ int swz_off(int j, int half, int o, int k) {
+  return (((j * 2 + half) * kO + o) << 5) + ((k ^ (o & 7)) << 2);
+}
+
 struct FusedFwdSmem {
   __nv_bfloat16 F[kTM * 16];          // [2 chunks][128][8]
   __half HB[kTM * kC];                // H1 = GELU(pre1), then (same bytes) the basis tile; [8 chunks][128][8] fp16
-  float XS[kTileFloats];              // gathered x_src rows, then the messages in place
+  float XS[kTM * kC];                 // gathered x_src rows ([8 entries][2 halves][16 rows][32 floats]: 2 KB TMA boxes,
+                                      // 128-byte swizzled, at 1024-byte multiples), then the messages in place
   __nv_bfloat16 W1b[2 * kC * 16];     // [2 chunks][128 rows][8 f]: rows 0..63 = [W1 | b1], rows 64..127 = [0 | b2]
   __half W2h[kC * kC];                // [8 chunks][64 rows n][8 k]
   __half Wkh[kC * kC];                // [8 chunks][64 rows c][8 j]
@@ -132,9 +138,10 @@ struct FusedFwdSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFusedEdgeDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  FusedFwdSmem& s = *reinterpret_cast<FusedFwdSmem*>(smem_raw);
+__global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFusedEdgeDesc d, const __grid_constant__ CUtensorMap tm_xs) {
+  extern __shared__ unsigned char smem_raw[];
+  FusedFwdSmem& s = *reinterpret_cast<FusedFwdSmem*>(
+      smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));  // the swizzle atoms want a 1024-byte aligned base
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, ch = warp >> 2, row = 32 * q + lane;
   const int o = tid >> 4, cg = tid & 15;  // mapping of the segmented-sum phase
@@ -196,23 +203,30 @@ __global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFu
     load_idx(t + 4, es_b, ed_b);
     tc::fence_async_smem();  // generic-proxy accesses to XS (tile t-1) before the bulk engine rewrites it
     __syncthreads();         // (A) everyone is done with tile t-1
-    // x_src rows of this tile through the bulk-copy engine: thread r < 128 requests the 256-byte orientation row r;
-    // they land under the two MLP stages below
-    if (tid < kTM) {
-      const int j = tid >> 4, oo = tid & 15;
-      float* drow = s.XS + tid * kLDT;
+    // x_src rows of this tile through tensor-map TMA: lane j < cnt of warp 4 requests the two 16-row x 32-channel boxes of
+    // entry j (16 copies per tile instead of 128 per-row bulk copies, whose elect-and-broadcast issue loops were 17 % of
+    // the kernel's instructions); they land under the two MLP stages below
+    if (tid >= kTM && tid < kTM + kTE) {
+      const int j = tid - kTM;
       if (j < cnt) {
-        tc::bulk_g2s(drow, d.x_src + (size_t)s.src[slot][j] * kRow + oo * kC, kC * 4u, &s.bar_x);
-      } else {
-#pragma unroll
-        for (int c = 0; c < kC; c += 4) *reinterpret_cast<float4*>(drow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int srow = s.src[slot][j] * kO;
+        tc::tma_load_2d(s.XS + (j * 2 + 0) * 512, &tm_xs, 0, srow, &s.bar_x);
+        tc::tma_load_2d(s.XS + (j * 2 + 1) * 512, &tm_xs, 32, srow, &s.bar_x);
       }
-      if (tid == 0) tc::mbar_expect_tx(&s.bar_x, (uint32_t)cnt * kO * kC * 4u);
+      if (j == 0) tc::mbar_expect_tx(&s.bar_x, (uint32_t)cnt * kO * kC * 4u);
+    }
+    if (cnt < kTE) {  // rows past the end of the list: zeros
+      for (int i = tid; i < (kTE - cnt) * kRow / 4; i += kThreads)
+        reinterpret_cast<float4*>(s.XS + cnt * kRow)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < kTM) {
+      const int j = tid >> 4;
       pos.emit(d, s.F, tid);
       // positions of tile t+1 (its indices were published one iteration ago)
       const int nb = p0 + (t + 1) * kTE + j;
       pos.load(d, s.src[(t + 1) & 3][j], s.dst[(t + 1) & 3][j], t + 1 < n_tiles && nb < p1);
-    } else if (tid < kTM + kTE && t + 1 < n_tiles) {  // next tile's x_src rows -> L2
+    }
+    if (tid >= kTM && tid < kTM + kTE && t + 1 < n_tiles) {  // next tile's x_src rows -> L2
       const int j = tid - kTM;
       if (p0 + (t + 1) * kTE + j < p1) tc::prefetch_l2(d.x_src + (size_t)s.src[(t + 1) & 3][j] * kRow, kRow * 4u);
     }
@@ -280,12 +294,14 @@ __global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFu
       const int c0 = 32 * ch + 16 * i;
       float v[16];
       tc::tmem_ld16(lane_addr + c0, v);
-      float* xs = s.XS + row * kLDT + c0;
+      float* xs = s.XS + ((((row >> 4) * 2 + ch) * kO + (row & 15)) << 5);
 #pragma unroll
-      for (int e = 0; e < 16; e += 4) {
-        float4 x = ld4(xs + e);
+      for (int e4 = 0; e4 < 4; ++e4) {
+        float* px = xs + (((4 * i + e4) ^ (row & 7)) << 2);
+        const int e = 4 * e4;
+        float4 x = ld4(px);
         x.x *= v[e]; x.y *= v[e + 1]; x.z *= v[e + 2]; x.w *= v[e + 3];
-        st4(xs + e, x);
+        st4(px, x);
       }
     }
     tc::tc_fence_before();
@@ -300,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 3) edge_fused_fwd_kernel(const GrlFu
           sum = make_float4(0.f, 0.f, 0.f, 0.f);
           ++cur;
         }
-        const float4 m = ld4(s.XS + (16 * j + o) * kLDT + 4 * cg);
+        const float4 m = ld4(s.XS + swz_off(j, cg >> 3, o, cg & 7));
         sum.x += m.x; sum.y += m.y; sum.z += m.z; sum.w += m.w;
       }
     }
@@ -336,10 +352,6 @@ __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-// float offset of the 16-byte chunk k (channels 4k..4k+3 of the half) of row (entry j, orientation o) in a swizzled row tile
-__device__ __forceinline__ int swz_off(int j, int half, int o, int k) {
-  return (((j * 2 + half) * kO + o) << 5) + ((k ^ (o & 7)) << 2);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // backward: a four-stage pipeline inside one CTA per SM.
@@ -814,11 +826,14 @@ int grl_fbconv_edge_fused_fwd(const GrlFusedEdgeDesc* d, grl_stream_t stream) {
   const int rc = fused_check(d, "grl_fbconv_edge_fused_fwd");
   if (rc != GRL_OK) return rc;
   GRL_REQUIRE(d->x1, GRL_EINVAL, "grl_fbconv_edge_fused_fwd: x1 is null");
-  const int smem = (int)sizeof(grl::FusedFwdSmem);
+  GRL_REQUIRE(d->n_other > 0, GRL_EINVAL, "grl_fbconv_edge_fused_fwd: n_other=%d (rows of x_src) must be set", d->n_other);
+  alignas(64) CUtensorMap tm_xs;
+  if (grl::make_row_tensor_map(&tm_xs, d->x_src, d->n_other) != GRL_OK) return GRL_ECUDA;
+  const int smem = (int)sizeof(grl::FusedFwdSmem) + 1024;
   if (grl::ensure_dynamic_smem((const void*)grl::edge_fused_fwd_kernel, smem) != GRL_OK) return GRL_ECUDA;
   int grid = 3 * grl::sm_count();
   if (grid > d->n_key) grid = d->n_key;
-  grl::edge_fused_fwd_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d);
+  grl::edge_fused_fwd_kernel<<<grid, grl::kThreads, smem, (cudaStream_t)stream>>>(*d, tm_xs);
   return grl::check_launch("grl_fbconv_edge_fused_fwd");
 }
 
