@@ -296,17 +296,18 @@ __device__ __forceinline__ __half2 gelu_h2(__half2 x) {
   const __half2 hx = __hmul2(x, half);
   return __hfma2(hx, t, hx);
 }
-// value and derivative: dy = 0.5 (1 + t) + 0.5 x (1 - t^2) (k + 3 kc x^2)
+// value and derivative with e = 0.5 (1 + t):  y = x e,  dy = e + x (1 - t^2) (k / 2 + 3 kc / 2 x^2)   (9 fma-pipe ops + 1 MUFU)
 __device__ __forceinline__ void gelu_h2(__half2 x, __half2& y, __half2& dy) {
   const __half2 k = __floats2half2_rn(0.7978845608028654f, 0.7978845608028654f);
   const __half2 kc = __floats2half2_rn(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
-  const __half2 k3 = __floats2half2_rn(3.0f * 0.7978845608028654f * 0.044715f, 3.0f * 0.7978845608028654f * 0.044715f);
+  const __half2 kh = __floats2half2_rn(0.5f * 0.7978845608028654f, 0.5f * 0.7978845608028654f);
+  const __half2 k3h = __floats2half2_rn(1.5f * 0.7978845608028654f * 0.044715f, 1.5f * 0.7978845608028654f * 0.044715f);
   const __half2 half = __floats2half2_rn(0.5f, 0.5f), one = __floats2half2_rn(1.0f, 1.0f);
   const __half2 x2 = __hmul2(x, x);
   const __half2 t = tanh_h2(__hmul2(x, __hfma2(x2, kc, k)));
-  const __half2 hx = __hmul2(x, half);
-  y = __hfma2(hx, t, hx);
-  dy = __hfma2(__hmul2(hx, __hfma2(__hneg2(t), t, one)), __hfma2(x2, k3, k), __hfma2(t, half, half));
+  const __half2 e = __hfma2(t, half, half);
+  y = __hmul2(x, e);
+  dy = __hfma2(__hmul2(x, __hfma2(__hneg2(t), t, one)), __hfma2(x2, k3h, kh), e);
 }
 __device__ __forceinline__ uint4 pack_h8(const __half2 (&h)[4]) {
   uint4 o;
