@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
-SKIP=70 TAG=r02 bash tools/_run_profiles.sh | tail -3
-timeout 600 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo bench rc=$?
+timeout 1200 python -m pytest tests -q -m gpu --tb=short > gpurun_out/r02_gputests.log 2>&1; echo tests rc=$?; tail -2 gpurun_out/r02_gputests.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_smoke.log 2>&1; echo smoke rc=$?; tail -2 gpurun_out/r02_smoke.log
+timeout 900 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo bench rc=$?
 timeout 600 python bench.py --impl reference > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; echo ref rc=$?
-timeout 600 python tools/bf16_parity_report.py > gpurun_out/r02_bf16_parity.txt 2>&1; echo parity rc=$?; tail -5 gpurun_out/r02_bf16_parity.txt
+SKIP=70 TAG=r02 bash tools/_run_profiles.sh | head -2
