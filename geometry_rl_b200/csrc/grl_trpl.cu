@@ -17,17 +17,25 @@ struct KlEval {
   double kl, dkl;
 };
 
-// KL(eta) of c~(eta) = (eta + 1) / (eta / o + 1 / c) against o, and d KL / d eta.
-__device__ __forceinline__ KlEval kl_eval(const double (&c)[kMaxK], const double (&o)[kMaxK], int k, double eta) {
+// KL(eta) of c~(eta) = (eta + 1) / (eta / o + 1 / c) against o, and d KL / d eta, from the per-dimension invariants
+// io = 1 / o, ic = 1 / c, lo = log o (formed once per sample): one division and one logarithm per dimension and
+// evaluation instead of five and two - the solve is a serial chain of fp64 operations in ONE thread, so its length is
+// the kernel's duration whatever the batch size.
+struct KlInv {
+  double io[kMaxK], ic[kMaxK], lo[kMaxK];
+};
+__device__ __forceinline__ KlEval kl_eval(const KlInv& q, int k, double eta) {
   KlEval r{0.0, 0.0};
+  const double e1 = eta + 1.0, ie1 = 1.0 / e1;
 #pragma unroll
   for (int i = 0; i < kMaxK; ++i) {
     if (i < k) {
-      const double D = eta / o[i] + 1.0 / c[i];
-      const double ct = (eta + 1.0) / D;
-      r.kl += ct / o[i] - 1.0 + log(o[i]) - log(ct);
-      const double dct = (1.0 / c[i] - 1.0 / o[i]) / (D * D);
-      r.dkl += (1.0 / o[i] - 1.0 / ct) * dct;
+      const double D = fma(eta, q.io[i], q.ic[i]);
+      const double rD = 1.0 / D;
+      const double ct = e1 * rD;                       // c~(eta)
+      r.kl += fma(ct, q.io[i], -1.0) + q.lo[i] - log(ct);
+      const double dct = (q.ic[i] - q.io[i]) * rD * rD;
+      r.dkl += (q.io[i] - D * ie1) * dct;              // 1 / ct = D / (eta + 1)
     }
   }
   r.kl *= 0.5;
@@ -70,21 +78,28 @@ __global__ void __launch_bounds__(128) trpl_fwd_kernel(const GrlProjDesc d) {
   // ---- covariance part -----------------------------------------------------------------------
   if (d.proj_type == 0) {
     double c[kMaxK], o[kMaxK];
+    KlInv q;
 #pragma unroll
-    for (int i = 0; i < kMaxK; ++i) { c[i] = (double)(v[i] * v[i]); o[i] = (double)(vo[i] * vo[i]); }
+    for (int i = 0; i < kMaxK; ++i) {
+      c[i] = (double)(v[i] * v[i]);
+      o[i] = (double)(vo[i] * vo[i]);
+      q.io[i] = 1.0 / o[i];
+      q.ic[i] = 1.0 / c[i];
+      q.lo[i] = i < k ? log(o[i]) : 0.0;
+    }
     const double eps = (double)d.eps_cov;
     double eta = 0.0;
-    KlEval f = kl_eval(c, o, k, 0.0);
+    KlEval f = kl_eval(q, k, 0.0);
     if (f.kl > eps) {
       double lo = 0.0, hi = 1.0;
       for (int it = 0; it < 200; ++it) {  // bracket: KL is decreasing in eta
-        if (kl_eval(c, o, k, hi).kl <= eps) break;
+        if (kl_eval(q, k, hi).kl <= eps) break;
         lo = hi;
         hi *= 2.0;
       }
       eta = 0.5 * (lo + hi);
       for (int it = 0; it < 100; ++it) {  // safeguarded Newton on KL(eta) - eps
-        f = kl_eval(c, o, k, eta);
+        f = kl_eval(q, k, eta);
         const double res = f.kl - eps;
         if (res > 0.0) lo = eta; else hi = eta;
         if (fabs(res) <= 1e-14 * eps || (hi - lo) <= 1e-15 * hi) break;
