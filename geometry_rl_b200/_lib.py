@@ -151,6 +151,7 @@ SIGNATURES = {
     "grl_trpl_fwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),
     "grl_trpl_bwd": (C.c_int, [C.POINTER(GrlProjDesc), _fp]),
     "grl_tc_selftest_gemm": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _fp]),
+    "grl_tc_selftest_gemm_ts": (C.c_int, [_fp, _fp, _fp, C.c_int, _fp]),
     "grl_tc_debug_mma": (C.c_int, [_fp, C.c_int, _fp, C.c_int, _fp, C.c_int, C.c_int] + [C.c_uint32] * 8 + [_fp]),
     "grl_tc_latency_probe": (C.c_int, [_fp, _fp]),
 }

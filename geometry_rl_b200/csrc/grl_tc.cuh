@@ -176,6 +176,32 @@ __device__ __forceinline__ void issue_mma_fast(uint32_t tmem_d, const Op& a, con
 #pragma unroll
   for (int k = 1; k < KSTEPS; ++k) mma_f16_words(tmem_d, a.lo + k * a.step, a.hi, b.lo + k * b.step, b.hi, idesc, 1u);
 }
+// A operand from TENSOR MEMORY (TS mode): row m of A sits in TMEM lane m, its K elements packed two 16-bit values per
+// 32-bit column (element 2 j in the low half of column j); one MMA consumes K = 16 = 8 columns.  An epilogue thread
+// that owns row m therefore feeds the next GEMM with tcgen05.st of the packed pairs it already holds - no shared-memory
+// image, no fence.proxy.async, and the MMA does not re-read a 4 KB A tile from shared memory per K step.
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D (+)= A_tmem[128 x 16 ksteps] * B^T: A at columns tmem_a, tmem_a + 8, ...; B as an operand view in shared memory
+__device__ __forceinline__ void issue_mma_ts(uint32_t tmem_d, uint32_t tmem_a, const OpView& b, uint32_t idesc, int ksteps,
+                                             bool accumulate_first) {
+  const uint32_t blo = desc_lo(b.addr, b.lbo), bhi = desc_hi(b.sbo), bs = b.adv >> 4;
+#pragma unroll
+  for (int k = 0; k < ksteps; ++k)
+    mma_f16_ts(tmem_d, tmem_a + 8u * k, blo + k * bs, bhi, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+}
+
 // generic entry used by every kernel: the operand views' descriptor words are formed once, each K step adds a constant;
 // ksteps is a compile-time constant at every call site, so the loop unrolls into back-to-back UTCHMMA.
 __device__ __forceinline__ void issue_mma(uint32_t tmem_d, const OpView& a, const OpView& b, uint32_t idesc, int ksteps,

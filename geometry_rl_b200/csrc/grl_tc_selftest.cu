@@ -65,6 +65,71 @@ extern "C" int grl_tc_selftest_gemm(const float* A, const float* B, float* D, in
   GRL_REQUIRE(false, GRL_EUNSUPPORTED, "grl_tc_selftest_gemm: (N,K)=(%d,%d) not instantiated", N, K);
 }
 
+// ---- TS-mode self-test: D[128 x 64] = fp16(A[128 x K]) * fp16(B[64 x K])^T with A fed from TENSOR MEMORY ------------
+namespace grl {
+template <int K>
+__global__ void __launch_bounds__(128) tc_selftest_ts_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                             float* __restrict__ D) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __half* sB = reinterpret_cast<__half*>(smem_raw);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
+  tc::stage_weight_f16(sB, B, 64, K, K);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base, lane_addr = tmem + ((uint32_t)(32 * warp) << 16);
+  constexpr uint32_t kColA = 128;  // A: K / 2 packed columns from column 128; D: columns 0..63
+  // thread = row: pack its K values into fp16 pairs and store them into its TMEM lane, 16 columns (32 values) at a time
+#pragma unroll 1
+  for (int c = 0; c < K / 2; c += 16) {
+    uint32_t r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const __half2 h = __floats2half2_rn(A[(size_t)tid * K + 2 * (c + j)], A[(size_t)tid * K + 2 * (c + j) + 1]);
+      r[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    tc::tmem_st16(lane_addr + kColA + c, r);
+  }
+  tc::tmem_st_wait();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc::tc_fence_after();
+    tc::issue_mma_ts(tmem, tmem + kColA, tc::view_k(tc::smem_u32(sB), 64), tc::idesc_f16_ex(128, 64, 0, 0, 0, 0), K / 16, false);
+    tc::mma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)tid * 64 + c0 + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+}  // namespace grl
+
+extern "C" int grl_tc_selftest_gemm_ts(const float* A, const float* B, float* D, int K, grl_stream_t stream) {
+  GRL_REQUIRE(A && B && D, GRL_EINVAL, "grl_tc_selftest_gemm_ts: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K == 64) grl::tc_selftest_ts_kernel<64><<<1, 128, 64 * 64 * 2, s>>>(A, B, D);
+  else if (K == 256) grl::tc_selftest_ts_kernel<256><<<1, 128, 64 * 256 * 2, s>>>(A, B, D);
+  else GRL_REQUIRE(false, GRL_EUNSUPPORTED, "grl_tc_selftest_gemm_ts: K=%d not instantiated", K);
+  return grl::check_launch("grl_tc_selftest_gemm_ts");
+}
+
 // ---- raw debug hook: caller supplies the shared-memory images and every descriptor field ------------------
 namespace grl {
 __global__ void __launch_bounds__(128) tc_debug_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* __restrict__ b_img,

@@ -453,6 +453,9 @@ int grl_dp_combine(const double* gathered, int world, int n, int n_sum, double* 
  * TMEM (tcgen05.mma kind::f16).  (N,K) in {(64,16),(64,64),(256,64),(64,256)}.  Test hook only.
  * ------------------------------------------------------------------------------------------ */
 int grl_tc_selftest_gemm(const float* A, const float* B, float* D, int N, int K, grl_stream_t stream);
+/* The same with the A operand fed from tensor memory (TS mode: tcgen05.st of packed fp16 pairs, lane = row), N = 64,
+ * K in {64, 256}.  Pins the TMEM operand layout the kernels rely on. */
+int grl_tc_selftest_gemm_ts(const float* A, const float* B, float* D, int K, grl_stream_t stream);
 /* Raw hook behind tests/test_gpu_tc.py's layout probes: the caller supplies the bf16 shared-memory images of
  * both operands and every descriptor field (byte offsets, per-K-step advance, instruction descriptor). */
 int grl_tc_debug_mma(const void* a_img, int a_bytes, const void* b_img, int b_bytes, float* D, int N, int n_ksteps,

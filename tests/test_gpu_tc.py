@@ -21,6 +21,23 @@ def test_tcgen05_gemm_selftest(N, K):
     assert err < 1e-5, f"tcgen05 GEMM N={N} K={K}: rel err {err}"
 
 
+@pytest.mark.parametrize("K", [64, 256])
+def test_tcgen05_gemm_with_the_a_operand_in_tensor_memory(K):
+    """TS mode: A rows written into TMEM by their owning threads (tcgen05.st, packed fp16 pairs, lane = row), B from shared
+    memory.  Pins the operand layout: element (m, k) = half (k & 1) of column k / 2 of lane m."""
+    from geometry_rl_b200 import _lib as L
+    g = torch.Generator().manual_seed(77 + K)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(64, K, generator=g)
+    D = torch.full((128, 64), float("nan"), device="cuda")
+    Ad, Bd = A.cuda(), B.cuda()
+    L.call("grl_tc_selftest_gemm_ts", L.ptr(Ad), L.ptr(Bd), L.ptr(D), K)
+    torch.cuda.synchronize()
+    ref = A.half().float() @ B.half().float().t()
+    err = float((D.cpu() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 1e-5, f"TS-mode GEMM K={K}: rel err {err}"
+
+
 def _conv_inputs(B, n_per, deg, seed):
     """Random homogeneous graph batch + layer parameters for one FiberConvFn call."""
     from geometry_rl_b200 import ops
