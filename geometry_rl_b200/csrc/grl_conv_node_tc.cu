@@ -19,7 +19,10 @@ constexpr int kLDX = 72;  // X2 row stride (floats): conflict-free for the threa
 //   * operands are fp16 (LayerNorm and GELU outputs are O(1); 11-bit mantissa instead of bf16's 8),
 //   * b1 rides in the contraction: K = 80 with y[:, 64:66] = 1 and W1[:, 64:66] = (hi, lo) fp16 split of b1,
 //   * GELU is evaluated two elements per instruction (HFMA2 / MUFU.TANH.F16, grl_tc.cuh gelu_h2),
-//   * D2 (GEMM2 accumulator) re-uses the first 64 TMEM columns of D1, so a group needs 256 columns.
+//   * the hidden activations never touch shared memory: each thread packs GELU(D1) of its row into fp16 pairs and stores
+//     them back into its own TMEM lane (tcgen05.st) over the D1 columns it has already read; GEMM2 takes that as its A
+//     operand (TS mode) and accumulates into D1 columns 64..127, so a group still needs 256 columns;
+//   * with no hidden-layer image aliasing the x1 tile, the next tile's x1 rows are requested as soon as GEMM1 has retired.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kNF2Threads = 512;
 constexpr int kK1 = 80;  // GEMM1 contraction length: 64 channels + 2 bias columns + 14 zero columns
@@ -31,7 +34,6 @@ struct NodeFwd2Group {
       float X2[kTM * kLDX];  // fibre conv output (phase B reads thread-pair-per-row: stride 72)
     } x;
     __half A1[kTM * kK1];    // y: [10 chunks][128 rows][8]   (aliases X1, dead after phase A)
-    __half A2[kTM * kH];     // hidden: [32 chunks][128 rows][8]   (aliases X1 + X2, dead after GEMM1)
   } u;
 };
 
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
   if (tile < n_tiles)
     stage_x1_dense(G.u.x.X1, d.x1 + (size_t)tile * kTE * kRow, min(kTE, d.n_dst - tile * kTE), gt, &s.bar_x[grp]);
   const uint32_t tmem = s.tmem_base + 256u * grp;
-  const uint32_t a1_addr = tc::smem_u32(G.u.A1), a2_addr = tc::smem_u32(G.u.A2);
+  const uint32_t a1_addr = tc::smem_u32(G.u.A1);
   const uint32_t w1_addr = tc::smem_u32(s.W1h), w2_addr = tc::smem_u32(s.W2h);
   const int q = gw & 3, hh = gw >> 2;
   const int row = 32 * q + lane;
@@ -205,32 +207,46 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
       tc::issue_mma_rolled(tmem, tc::view_k(a1_addr, kTM), tc::view_k(w1_addr, kH), tc::idesc_f16_ex(128, kH, 0, 0, 0, 0), kK1 / 16, false);
       tc::mma_commit(&s.bar[grp][0]);
     }
-    // ---- D: hidden = GELU(D1) -> A2 (aliases X1 / X2 / A1, which nobody reads any more) ----------------
+    // ---- D: hidden = GELU(D1), packed fp16, back into this thread's TMEM lane (A operand of GEMM2) -----------------
     tc::mbar_wait(&s.bar[grp][0], parity);
     tc::tc_fence_after();
+    // A1 (= the X1 bytes) is free: request the group's next x1 tile now, it lands under the GELU and GEMM2
+    {
+      const int nt = tile + tile_stride;
+      if (nt < n_tiles) {
+        tc::fence_async_smem();  // generic-proxy accesses to the tile before the bulk engine rewrites it
+        stage_x1_dense(G.u.x.X1, d.x1 + (size_t)nt * kTE * kRow, min(kTE, d.n_dst - nt * kTE), gt, &s.bar_x[grp]);
+      }
+    }
     {
 #pragma unroll 2
       for (int i = 0; i < 8; ++i) {
-        const int c0 = 128 * hh + 16 * i;
+        const int c0 = 128 * hh + 16 * i;  // hidden units c0 .. c0 + 15 of this thread's row
         float v[16];
         tc::tmem_ld16(lane_addr + c0, v);
-        __half2 h0[4], h1[4];
+        uint32_t r[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          h0[e] = tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]));
-          h1[e] = tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]));
+          const __half2 a = tc::gelu_h2(__floats2half2_rn(v[2 * e], v[2 * e + 1]));
+          const __half2 b = tc::gelu_h2(__floats2half2_rn(v[8 + 2 * e], v[8 + 2 * e + 1]));
+          r[e] = *reinterpret_cast<const uint32_t*>(&a);
+          r[4 + e] = *reinterpret_cast<const uint32_t*>(&b);
         }
-        *reinterpret_cast<uint4*>(G.u.A2 + ((size_t)(c0 >> 3) * kTM + row) * 8) = tc::pack_h8(h0);
-        *reinterpret_cast<uint4*>(G.u.A2 + ((size_t)((c0 >> 3) + 1) * kTM + row) * 8) = tc::pack_h8(h1);
+        // packed columns 128 hh + 8 i .. + 7: always behind this thread's own reads, never in the other half's range
+        tc::tmem_st8(lane_addr + 128 * hh + 8 * i, r);
       }
+      tc::tmem_st_wait();
     }
-    // ---- E: GEMM2  D2[128 x 64] = hidden W2^T  (into the first 64 columns of D1: every D1 read is done) ----
-    tc::fence_async_smem();
+    // ---- E: GEMM2  D2[128 x 64] = hidden W2^T, A from tensor memory, into D1 columns 64..127 (all read by now) ----
     tc::tc_fence_before();
     tc::group_sync(bar_id, 256);
     if (gt == 0) {
       tc::tc_fence_after();
-      tc::issue_mma_rolled(tmem, tc::view_k(a2_addr, kTM), tc::view_k(w2_addr, kC), tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), kH / 16, false);
+      const tc::OpView w2v = tc::view_k(w2_addr, kC);
+      tc::OpView w2hi = w2v;
+      w2hi.addr += 8 * w2v.adv;  // K steps 8..15 (hidden units 128..255)
+      tc::issue_mma_ts(tmem + 64, tmem, w2v, tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), 8, false);
+      tc::issue_mma_ts(tmem + 64, tmem + 128, w2hi, tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), 8, true);
       tc::mma_commit(&s.bar[grp][1]);
     }
     // x_dst of this thread's two 16-column pieces: issued BEFORE the wait so the DRAM round trip hides behind GEMM2
@@ -250,18 +266,11 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
     }
     tc::mbar_wait(&s.bar[grp][1], parity);
     tc::tc_fence_after();
-    // A2 (= X1 / X2) is free again: prefetch the group's next tile while the epilogue streams out
-    {
-      const int nt = tile + tile_stride;
-      if (nt < n_tiles) {
-        stage_x1_dense(G.u.x.X1, d.x1 + (size_t)nt * kTE * kRow, min(kTE, d.n_dst - nt * kTE), gt, &s.bar_x[grp]);
-      }
-    }
     // ---- F: out = x_dst + D2 + b2 -------------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       float v[16];
-      tc::tmem_ld16(lane_addr + 32 * hh + 16 * i, v);
+      tc::tmem_ld16(lane_addr + 64 + 32 * hh + 16 * i, v);
       if (live) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
