@@ -32,7 +32,7 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
 int ensure_dynamic_smem(const void* func, int bytes);
-int make_row_tensor_map(void* out_tensor_map_128B, const float* base, long long n_nodes);  // grl_util.cu  // per (kernel, device), see grl_util.cu
+int make_row_tensor_map(void* out_tensor_map_128B, const float* base, long long n_nodes, int box_rows = 16);  // grl_util.cu
 
 #define GRL_REQUIRE(cond, code, ...)  \
   do {                                \

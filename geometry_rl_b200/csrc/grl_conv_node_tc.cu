@@ -3,6 +3,8 @@
 // Same math and reference lines as grl_conv_node.cu (ponita/conv.py:88-114, ponita/ponita.py:163-175,219-230);
 // the two contractions run as [128 x 80] x [80 x 256] and [128 x 256] x [256 x 64] fp16 MMAs with fp32
 // accumulation, everything else (fibre conv, LayerNorm, residual) stays fp32 on the CUDA cores.
+#include <cuda.h>
+
 #include "grl_common.cuh"
 #include "grl_tc.cuh"
 
@@ -22,7 +24,10 @@ constexpr int kLDX = 72;  // X2 row stride (floats): conflict-free for the threa
 //   * the hidden activations never touch shared memory: each thread packs GELU(D1) of its row into fp16 pairs and stores
 //     them back into its own TMEM lane (tcgen05.st) over the D1 columns it has already read; GEMM2 takes that as its A
 //     operand (TS mode) and accumulates into D1 columns 64..127, so a group still needs 256 columns;
-//   * with no hidden-layer image aliasing the x1 tile, the next tile's x1 rows are requested as soon as GEMM1 has retired.
+//   * with no hidden-layer image aliasing the x1 tile, the next tile's x1 rows are requested as soon as GEMM1 has retired;
+//   * the residual rows x_dst of the tile arrive through tensor-map TMA (two 128-row x 32-channel boxes, 128-byte swizzled)
+//     into the bytes of X2 once the LayerNorm has consumed them - no residual values parked in registers across GEMM2
+//     (at the 128-register cap they went through local memory and their load latency sat in front of the epilogue).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kNF2Threads = 512;
 constexpr int kK1 = 80;  // GEMM1 contraction length: 64 channels + 2 bias columns + 14 zero columns
@@ -44,6 +49,7 @@ struct NodeFwd2Smem {
   float b2[kC], bias[kC], lng[kC], lnb[kC];
   uint64_t bar[2][2];
   uint64_t bar_x[2];         // per group: transaction barrier of the bulk copy that stages its x1 tile
+  uint64_t bar_d[2];         // per group: transaction barrier of the TMA boxes that stage its x_dst tile
   uint32_t tmem_base;
 };
 
@@ -65,9 +71,10 @@ __device__ __forceinline__ void stage_x1_dense(float* __restrict__ X1, const flo
 }
 
 template <bool kAcc>
-__global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(const GrlConvDesc d) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  NodeFwd2Smem& s = *reinterpret_cast<NodeFwd2Smem*>(smem_raw);
+__global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(const GrlConvDesc d, const __grid_constant__ CUtensorMap tm_xd) {
+  extern __shared__ unsigned char smem_raw[];
+  NodeFwd2Smem& s = *reinterpret_cast<NodeFwd2Smem*>(
+      smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));  // the swizzle atoms want a 1024-byte aligned base
   const int tid = threadIdx.x;
   const int grp = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
   NodeFwd2Group& G = s.g[grp];
@@ -81,6 +88,8 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
     tc::mbar_init(&s.bar[1][1], 1);
     tc::mbar_init(&s.bar_x[0], 1);
     tc::mbar_init(&s.bar_x[1], 1);
+    tc::mbar_init(&s.bar_d[0], 1);
+    tc::mbar_init(&s.bar_d[1], 1);
     tc::fence_mbar_init();
   }
   if (tid < 32) tc::tmem_alloc(&s.tmem_base, 512);
@@ -206,6 +215,11 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
       tc::tc_fence_after();
       tc::issue_mma_rolled(tmem, tc::view_k(a1_addr, kTM), tc::view_k(w1_addr, kH), tc::idesc_f16_ex(128, kH, 0, 0, 0, 0), kK1 / 16, false);
       tc::mma_commit(&s.bar[grp][0]);
+      // X2 has been consumed by the LayerNorm (barrier above): the tile's residual rows land there under GEMM1 .. GEMM2.
+      // Rows past the end of the tensor are zero-filled by the TMA unit and still count towards the byte total.
+      tc::mbar_expect_tx(&s.bar_d[grp], 2u * kTM * 32u * 4u);
+      tc::tma_load_2d(G.u.x.X2, &tm_xd, 0, n0 * kO, &s.bar_d[grp]);
+      tc::tma_load_2d(G.u.x.X2 + kTM * 32, &tm_xd, 32, n0 * kO, &s.bar_d[grp]);
     }
     // ---- D: hidden = GELU(D1), packed fp16, back into this thread's TMEM lane (A operand of GEMM2) -----------------
     tc::mbar_wait(&s.bar[grp][0], parity);
@@ -249,24 +263,14 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
       tc::issue_mma_ts(tmem + 64, tmem + 128, w2hi, tc::idesc_f16_ex(128, kC, 0, 0, 0, 0), 8, true);
       tc::mma_commit(&s.bar[grp][1]);
     }
-    // x_dst of this thread's two 16-column pieces: issued BEFORE the wait so the DRAM round trip hides behind GEMM2
-    // (ncu r02: with the loads inside the epilogue, 45 % of the stall samples sat on their first use)
     const int node = n0 + (row >> 4);
     const bool live = node < d.n_dst;
     const size_t off = (size_t)(live ? node : 0) * kRow + (row & 15) * kC + 32 * hh;
-    float4 xd[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) xd[e] = ldg4(d.x_dst + off + 4 * e);
-    if (kAcc) {  // HeteroConv group "sum": out already holds the other edge type's result
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float4 old = ldg4(d.out + off + 4 * e);
-        xd[e].x += old.x; xd[e].y += old.y; xd[e].z += old.z; xd[e].w += old.w;
-      }
-    }
     tc::mbar_wait(&s.bar[grp][1], parity);
     tc::tc_fence_after();
-    // ---- F: out = x_dst + D2 + b2 -------------------------------------------------------------------
+    // ---- F: out = x_dst + D2 + b2 (x_dst from the swizzled tile: chunk k of row r sits at chunk position k ^ (r & 7)) ----
+    tc::mbar_wait(&s.bar_d[grp], parity);
+    const float* xrow = G.u.x.X2 + hh * (kTM * 32) + row * 32;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       float v[16];
@@ -275,7 +279,11 @@ __global__ void __launch_bounds__(kNF2Threads, 1) fbconv_node_fwd_tc2_kernel(con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float4 bb = ld4(s.b2 + 32 * hh + 16 * i + 4 * e);
-          const float4 x = xd[4 * i + e];
+          float4 x = ld4(xrow + (((4 * i + e) ^ (row & 7)) << 2));
+          if (kAcc) {  // HeteroConv group "sum": out already holds the other edge type's result
+            const float4 old = ldg4(d.out + off + 16 * i + 4 * e);
+            x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w;
+          }
           st4(d.out + off + 16 * i + 4 * e, make_float4(x.x + (v[4 * e] + bb.x), x.y + (v[4 * e + 1] + bb.y),
                                                        x.z + (v[4 * e + 2] + bb.z), x.w + (v[4 * e + 3] + bb.w)));
         }
@@ -297,12 +305,14 @@ extern "C" int grl_fbconv_node_fwd_tc(const GrlConvDesc* d, grl_stream_t stream)
   GRL_REQUIRE(d->x1 && d->fiber_kernel && d->bias && d->ln_g && d->ln_b && d->w1 && d->b1 && d->w2 && d->b2 && d->x_dst &&
                   d->out, GRL_EINVAL, "grl_fbconv_node_fwd_tc: null pointer");
   const int n_tiles = (d->n_dst + grl::kTE - 1) / grl::kTE;
-  const int smem2 = (int)sizeof(grl::NodeFwd2Smem);
+  const int smem2 = (int)sizeof(grl::NodeFwd2Smem) + 1024;
   if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_fwd_tc2_kernel<false>, smem2) != GRL_OK) return GRL_ECUDA;
   if (grl::ensure_dynamic_smem((const void*)grl::fbconv_node_fwd_tc2_kernel<true>, smem2) != GRL_OK) return GRL_ECUDA;
+  alignas(64) CUtensorMap tm_xd;  // x_dst as [n_dst * 16 rows][64]: boxes of a whole 8-node tile x one channel half
+  if (grl::make_row_tensor_map(&tm_xd, d->x_dst, d->n_dst, grl::kTM) != GRL_OK) return GRL_ECUDA;
   int grid = grl::sm_count();
   if (2 * grid > n_tiles) grid = (n_tiles + 1) / 2;
-  if (d->accumulate_out) grl::fbconv_node_fwd_tc2_kernel<true><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d);
-  else grl::fbconv_node_fwd_tc2_kernel<false><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d);
+  if (d->accumulate_out) grl::fbconv_node_fwd_tc2_kernel<true><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d, tm_xd);
+  else grl::fbconv_node_fwd_tc2_kernel<false><<<grid, grl::kNF2Threads, smem2, (cudaStream_t)stream>>>(*d, tm_xd);
   return grl::check_launch("grl_fbconv_node_fwd_tc");
 }

@@ -31,7 +31,7 @@ static EncodeTiledFn encode_tiled_fn() {
 // Tensor map over a latent tensor viewed as [n_nodes * 16 orientation rows][64 fp32]: box = 16 rows x 32 channels
 // (one node, one channel half = 2 KB), SWIZZLE_128B: the 16-byte chunk c of row r lands at chunk position c ^ (r & 7)
 // of its 128-byte line, so threads that own one ROW each (TMEM lane = row) read any chunk conflict-free.
-int make_row_tensor_map(void* out, const float* base, long long n_nodes) {
+int make_row_tensor_map(void* out, const float* base, long long n_nodes, int box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -39,7 +39,7 @@ int make_row_tensor_map(void* out, const float* base, long long n_nodes) {
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)kC, (cuuint64_t)n_nodes * kO};
   const cuuint64_t gstride[1] = {(cuuint64_t)kC * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)kO};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};  // 16 = one node (gathers), 128 = a contiguous 8-node tile
   const cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
