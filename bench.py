@@ -76,17 +76,21 @@ def parse():
 # helpers
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons of EVERY GPU of the job, sampled every 50 ms while the timed region runs (rank 0
+    samples for all local ranks: under data parallelism the step time is the slowest rank's, so one power-capped GPU
+    explains a scaling loss that rank 0's own clocks would hide)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices):
+        self.indices = [int(i) for i in (indices if isinstance(indices, (list, tuple, range)) else [indices])]
+        self.proc, self.lines = None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", ",".join(str(i) for i in self.indices), "-lms", "50"],
+                                         stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -101,23 +105,26 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        per_gpu, mx, reasons = {}, None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                per_gpu.setdefault(int(f[0]), []).append(float(f[1]))
+                mx = float(f[2])
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        med = {g: sorted(v)[len(v) // 2] for g, v in per_gpu.items() if v}
+        out = {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+               "samples": sum(len(v) for v in per_gpu.values())}
+        if len(med) > 1:
+            out["sm_mhz_per_gpu"] = [med[g] for g in sorted(med)]  # median under load, one entry per GPU of the job
+        return out
 
 
 def measured_traffic(kernel, workload, minibatch):
@@ -399,20 +406,22 @@ def measure(args, cfg_name, B, precision, dev, dp, rank, world, local, steps, fu
     repeats = args.repeats or max(1, -(-MIN_TIMED_STEPS // steps))
     if not full:
         repeats = min(repeats, 3)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(list(range(world)) if world > 1 else local)
     barrier()
     if rank == 0 and full:
         sampler.start()
     launches0 = _lib.launch_count
-    regions = []
+    regions, host_ms = [], []
     torch.cuda.profiler.start()  # `ncu --profile-from-start off` captures exactly the timed steps
     for r in range(repeats):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             out = step(dev_batches[i % N_ROTATE])
         e1.record()
+        host_ms.append((time.perf_counter() - t_host) * 1e3)  # host time to ENQUEUE the region (no sync inside)
         barrier()
         regions.append(max_over_ranks(e0.elapsed_time(e1)))
     torch.cuda.profiler.stop()
@@ -421,7 +430,10 @@ def measure(args, cfg_name, B, precision, dev, dp, rank, world, local, steps, fu
     ms = sorted(regions)[len(regions) // 2]  # median K-step region (each region is exactly K steps, max over ranks)
     res = {"precision": precision, "value": B * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
            "clocks": clocks, "gpu_launches": launches, "cuda_graph": use_graph, "B": B, "model": cfg.model,
-           "regions_ms": [round(x, 3) for x in regions]}
+           "regions_ms": [round(x, 3) for x in regions],
+           # host-side cost of enqueueing one step (max over ranks of the median region): close to ms_per_step means the
+           # launching thread, not the GPU, paces the job
+           "host_enqueue_ms_per_step": round(max_over_ranks(sorted(host_ms)[len(host_ms) // 2]) / steps, 3)}
     res.update(workload_shape(cfg, actor, host_batches[0], dev, precision))
     if not full:
         del lrn, actor, critic, loss_module, dev_batches, host_batches
@@ -434,20 +446,20 @@ def measure(args, cfg_name, B, precision, dev, dp, rank, world, local, steps, fu
     if tl_path:
         from torch.profiler import ProfilerActivity, profile
         barrier()
-        if rank == 0:
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                step(dev_batches[0])
-                torch.cuda.synchronize()
-            trace = tl_path + ".trace.json"
-            prof.export_chrome_trace(trace)
-            ev = json.load(open(trace)).get("traceEvents", [])
-            rows = sorted(([e["name"], e.get("args", {}).get("stream"), e["ts"], e["dur"]] for e in ev
-                           if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e), key=lambda r: r[2])
-            t0 = rows[0][2] if rows else 0
-            json.dump([[r[0], r[1], round(r[2] - t0, 3), r[3]] for r in rows], open(tl_path, "w"))
-            os.remove(trace)
-        else:
+        # every rank records its own copy (rank r > 0 writes <path>.rank<r>): a straggler shows up as the rank whose
+        # kernels are long, not as the rank that waits for it inside the gradient all-reduce
+        my_path = tl_path if rank == 0 else f"{tl_path}.rank{rank}"
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
             step(dev_batches[0])
+            torch.cuda.synchronize()
+        trace = my_path + ".trace.json"
+        prof.export_chrome_trace(trace)
+        ev = json.load(open(trace)).get("traceEvents", [])
+        rows = sorted(([e["name"], e.get("args", {}).get("stream"), e["ts"], e["dur"]] for e in ev
+                       if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e), key=lambda r: r[2])
+        t0 = rows[0][2] if rows else 0
+        json.dump([[r[0], r[1], round(r[2] - t0, 3), r[3]] for r in rows], open(my_path, "w"))
+        os.remove(trace)
         barrier()
 
     # ---- end to end: pinned host minibatch -> H2D -> step -> loss scalar D2H, every step ----------------
@@ -606,6 +618,7 @@ def run_ours(args):
                         "timing": f"{len(main_res['regions_ms'])} timed regions of exactly {args.steps} steps each (barrier + "
                                   f"synchronize on both sides, CUDA events, max over ranks); value = median region",
                         "regions_ms": main_res["regions_ms"],
+                        "host_enqueue_ms_per_step": main_res["host_enqueue_ms_per_step"],
                         "latent_mb": main_res["latent_mb"]},
             "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
             "roofline": main_res["roofline"], "cpu_baseline": cpu, "configs": side,

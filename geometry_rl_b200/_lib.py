@@ -113,6 +113,7 @@ SIGNATURES = {
     "grl_abi_version": (C.c_int, []),
     "grl_last_error": (C.c_char_p, []),
     "grl_sm_count": (C.c_int, []),
+    "grl_reserve_sms": (C.c_int, [C.c_int]),
     "grl_knn_edge_ptr": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     "grl_knn_graph": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int64, _fp]),
     "grl_radius_neighbors": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp]),
@@ -250,3 +251,10 @@ def sm_count() -> int:
     if _sm is None:
         _sm = load().grl_sm_count()
     return _sm
+
+
+def reserve_sms(n: int) -> None:
+    """Leave `n` SMs out of every persistent kernel's grid (see grl_reserve_sms in include/grl_b200.h)."""
+    global _sm
+    check(load().grl_reserve_sms(int(n)), "grl_reserve_sms")
+    _sm = None

@@ -1,6 +1,7 @@
 // Error plumbing, device query and the deterministic cross-CTA partial reduction.
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -69,8 +70,11 @@ int check_launch(const char* what) {
   return GRL_OK;
 }
 
+// SMs the persistent kernels leave free (grl_reserve_sms): a process-wide launch policy, 0 by default.
+static std::atomic<int> g_reserved_sms{0};
+
 int sm_count() {
-  // immutable per-device capability cache (the only global state behind the ABI)
+  // immutable per-device capability cache
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -79,7 +83,8 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
   }
-  return cached[dev];
+  const int usable = cached[dev] - g_reserved_sms.load(std::memory_order_relaxed);
+  return usable > 1 ? usable : 1;
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: set it once per (kernel, device)
@@ -170,6 +175,11 @@ extern "C" {
 int grl_abi_version(void) { return 1; }
 const char* grl_last_error(void) { return grl::g_err; }
 int grl_sm_count(void) { return grl::sm_count(); }
+int grl_reserve_sms(int n) {
+  GRL_REQUIRE(n >= 0 && n <= 64, GRL_EINVAL, "grl_reserve_sms: n=%d outside [0, 64]", n);
+  grl::g_reserved_sms.store(n, std::memory_order_relaxed);
+  return GRL_OK;
+}
 
 int grl_reduce_partials(const float* partials, int n_partials, int64_t n_floats, float* out, int accumulate,
                         grl_stream_t stream) {

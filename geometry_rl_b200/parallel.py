@@ -40,6 +40,9 @@ class _GraphNormStats(torch.autograd.Function):
         return gx, None
 
 
+SIDE_STREAM_RESERVED_SMS = 4
+
+
 class DataParallel:
     def __init__(self, group=None, side_group: bool = False):
         """`side_group=True` creates a SECOND communicator (`self.side`) for the critic branch: the learner then
@@ -53,6 +56,14 @@ class DataParallel:
         self.rank = dist.get_rank(group)
         self.collectives = 0
         self.side = DataParallel(group=dist.new_group(), side_group=False) if side_group else None
+        if side_group and torch.cuda.is_available():
+            # The critic branch's collectives then run CONCURRENTLY with the actor's persistent kernels.  A collective
+            # that waits for a late rank spins on its SMs, and a persistent grid that fills every SM cannot place the CTAs
+            # that belong there until it ends: measured at 8 GPUs (profiles/r02_timeline_n8_ranks.md) the edge backward
+            # stretched from 1.8 to 3.3 ms under a 1.7 ms all-reduce, on most ranks.  Tiny collectives use one CTA each;
+            # two communicators can be active at once: four SMs stay out of the kernels' grids.
+            from . import _lib
+            _lib.reserve_sms(SIDE_STREAM_RESERVED_SMS)
 
     def all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
         dist.all_reduce(t, op=op, group=self.group)

@@ -44,6 +44,12 @@ int grl_abi_version(void);
 const char* grl_last_error(void);
 /* Number of SMs of the current device (grid sizing for the persistent kernels). */
 int grl_sm_count(void);
+/* Launch policy for jobs that run collectives CONCURRENTLY with the kernels (data parallelism with the critic branch on its
+ * own stream): every persistent kernel of this library sizes its grid to fill all SMs, so a CTA of a collective that is
+ * spinning on an SM (waiting for its peers) keeps one CTA of the kernel from starting until the collective ends - and a
+ * late CTA of a persistent grid doubles the kernel's duration.  With n SMs reserved the grids are sized for
+ * (SMs - n) and both kinds of CTA always find a free SM.  Process-wide; grl_sm_count() reports the reduced number. */
+int grl_reserve_sms(int n);
 
 /* ------------------------------------------------------------------------------------------
  * K1  edge construction -> sorted CSR
