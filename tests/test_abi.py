@@ -100,3 +100,19 @@ def test_loss_scalar_indices_match_the_header_enum(lib):
     assert macro("GRL_LOSS_STATS") == lib.LOSS_STATS and macro("GRL_LOSS_SUMS") == lib.LOSS_SUMS
     assert macro("GRL_READOUT_MAX_OUT") == lib.READOUT_MAX_OUT
     assert len(names) <= lib.LOSS_SCALARS
+
+
+def test_sm_reservation_policy_is_reflected_in_the_reported_sm_count():
+    """grl_reserve_sms(n): persistent grids are sized for (SMs - n) (DataParallel(side_group=True) leaves 4 to the critic
+    stream's collectives).  No GPU needed: without a device the library reports 148 SMs."""
+    from geometry_rl_b200 import _lib as L
+    L.reserve_sms(0)
+    full = L.sm_count()
+    try:
+        L.reserve_sms(4)
+        assert L.sm_count() == full - 4
+        with pytest.raises(RuntimeError):
+            L.reserve_sms(-1)
+    finally:
+        L.reserve_sms(0)
+    assert L.sm_count() == full
