@@ -116,3 +116,32 @@ def test_sm_reservation_policy_is_reflected_in_the_reported_sm_count():
     finally:
         L.reserve_sms(0)
     assert L.sm_count() == full
+
+
+def test_encoder_kernel_gate_declines_what_the_kernel_does_not_cover():
+    """ops.encoder_layer_supported: the K5 kernels take CUDA tensors of the shipped transformer shape only; anything else
+    (CPU tensors, other widths / head counts, active dropout, too many tokens) stays on nn.TransformerEncoder."""
+    import torch
+    from geometry_rl_b200 import ops
+    ok = torch.nn.TransformerEncoderLayer(d_model=64, nhead=2, dim_feedforward=64, dropout=0.0)
+    x = torch.zeros(2, 50, 64)
+    assert not ops.encoder_layer_supported(x, ok)  # CPU tensor
+    meta = torch.zeros(2, 50, 64, device="meta")
+    assert not ops.encoder_layer_supported(meta, ok)
+    # the shape / option checks, evaluated on a stand-in that claims to live on a CUDA device
+    class _Cuda:
+        is_cuda = True
+        def __init__(self, shape):
+            self.shape = shape
+        def dim(self):
+            return len(self.shape)
+    assert ops.encoder_layer_supported(_Cuda((2, 50, 64)), ok)
+    assert not ops.encoder_layer_supported(_Cuda((2, ops.ENCODER_MAX_TOKENS + 1, 64)), ok)
+    assert not ops.encoder_layer_supported(_Cuda((2, 50, 32)), ok)
+    drop = torch.nn.TransformerEncoderLayer(d_model=64, nhead=2, dim_feedforward=64, dropout=0.1)
+    assert not ops.encoder_layer_supported(_Cuda((2, 50, 64)), drop)      # training mode, p > 0
+    assert ops.encoder_layer_supported(_Cuda((2, 50, 64)), drop.eval())    # inactive dropout is fine
+    for bad in (torch.nn.TransformerEncoderLayer(64, 4, 64, 0.0), torch.nn.TransformerEncoderLayer(64, 2, 128, 0.0),
+                torch.nn.TransformerEncoderLayer(64, 2, 64, 0.0, activation="gelu"),
+                torch.nn.TransformerEncoderLayer(64, 2, 64, 0.0, norm_first=True)):
+        assert not ops.encoder_layer_supported(_Cuda((2, 50, 64)), bad)
